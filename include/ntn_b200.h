@@ -1,0 +1,161 @@
+/*
+ * ntn_b200.h -- C-ABI of the B200-native NTN cost+gradient hot path.
+ *
+ * This is the drop-in boundary for the path that Run_NTN's L-BFGS loop calls once per
+ * function evaluation in c0der1337/Neural_Tensor_Network_For_KB_Completion:
+ *
+ *     IPair<Double,double[]> NTN.computeAt(double[] theta)        src/NTN.java:92-443
+ *
+ * plus the state that method reads implicitly from the DataFactory singleton
+ * (src/DataFactory.java:21,67,89-98,393-437,583-595,614-684).  A JNI / Panama-FFM / ctypes
+ * binding of the reference binds exactly these symbols.  Plain pointers
+ * and sizes only; no C++/torch types.  Every function returns 0 on success and a negative
+ * NTN_E* code otherwise; ntn_last_error() gives the text.  There is NO CPU fallback: without
+ * a CUDA device ntn_create fails with NTN_ECUDA.
+ *
+ * Threading: one handle = one host thread at a time (the reference's NTN/DataFactory are a
+ * stateful object and a non-thread-safe singleton).  One handle drives one GPU; under data
+ * parallelism there is one process and one handle per GPU (DESIGN.md "Multi-GPU").
+ */
+#ifndef NTN_B200_H
+#define NTN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTN_OK        0
+#define NTN_EINVAL   -1   /* bad argument / index out of range / call order          */
+#define NTN_ECUDA    -2   /* CUDA runtime error (no device, OOM, launch failure)      */
+#define NTN_ESTATE   -3   /* missing set_entity_words / set_batch / frozen vectors    */
+#define NTN_EUNSUP   -4   /* shape outside what the kernels are built for            */
+
+#define NTN_ACT_TANH     0   /* Run_NTN.java:78 */
+#define NTN_ACT_SIGMOID  1
+
+#define NTN_WV_FROZEN    0   /* entity vectors from the load-time word vectors: what the
+                                reference does (DataFactory.java:393-437 reads worvectorWordVec,
+                                never theta -- SURVEY.md App. B1) */
+#define NTN_WV_THETA     1   /* entity vectors from theta's word block (the differentiable,
+                                intended behaviour; createEntityVectorsByWordEmbeddings :515-581) */
+
+#define NTN_GEMM_AUTO     0  /* tcgen05 when the shape allows it, else SIMT            */
+#define NTN_GEMM_SIMT     1  /* FP32 CUDA-core contractions (A/B reference path)       */
+#define NTN_GEMM_TCGEN05  2  /* tcgen05/TMEM + TMA, 3xTF32 split                       */
+
+#define NTN_SCORE_REFERENCE_EVAL 0 /* NTN.calculateScoreOfaTripple, NTN.java:713-736: no activation,
+                                      U scales only the bilinear term (App. B6) */
+#define NTN_SCORE_TRAIN          1 /* u' f(e1'W e2 + V[e1;e2] + b), NTN.java:163-205 */
+
+typedef struct ntn_handle ntn_handle;
+
+/* Constructor arguments of NTN (NTN.java:42-66) + the DataFactory sizes it reads. */
+typedef struct ntn_config {
+    int32_t d;              /* embeddingSize            (Run_NTN.java:73)  1..256            */
+    int32_t k;              /* sliceSize                (Run_NTN.java:76)  1..8              */
+    int32_t R;              /* numberOfRelations                                             */
+    int32_t Ne;             /* numberOfEntities                                              */
+    int32_t Nw;             /* numOfWords                                                    */
+    int32_t batch_divisor;  /* batchSize: divisor of cost and gradient (NTN.java:398-401,429-430) */
+    float   lambda;         /* lamda (Run_NTN.java:79)                                       */
+    int32_t activation;     /* NTN_ACT_*                                                     */
+    int32_t wv_source;      /* NTN_WV_*                                                      */
+    int32_t gemm_path;      /* NTN_GEMM_*                                                    */
+    int32_t device;         /* CUDA device ordinal                                           */
+    float   reg_scale;      /* multiplies the regulariser (cost and gradient).  1 for a single
+                               process; 1/G on each of G data-parallel ranks so that the SUM
+                               all-reduce of the per-rank results is the full-batch result   */
+} ntn_config;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int  ntn_create(const ntn_config* cfg, ntn_handle** out);
+void ntn_destroy(ntn_handle* h);
+/* Text of the last error on this handle (h == NULL: last ntn_create failure on this thread). */
+const char* ntn_last_error(const ntn_handle* h);
+
+/* NTN.getDimension / domainDimension (NTN.java:445-448,770-773):
+ * P = R*k*d*d + R*2d*k + R*k + R*k + d*Nw. */
+int64_t ntn_dimension(const ntn_handle* h);
+
+/* ---- DataFactory state the path reads ------------------------------------------------- */
+/* Entity -> word maps.  fwd_* is the CSR of words averaged into the entity vector
+ * (DataFactory.java:405-434, with multiplicity, "unknown" fallback already applied);
+ * bwd_* is getWordIndexes(i) (DataFactory.java:646-684) and len_bwd[i] = entityLength(i)
+ * (:583-595), the divisor in NTN.java:420.  bwd_off/bwd_idx may be NULL (= forward lists).
+ * Word ids in [0,Nw); every entity needs >= 1 forward word; len_bwd[i] <= 0 is rejected
+ * (the reference divides by zero there, App. B8).  Host pointers; copied. */
+int ntn_set_entity_words(ntn_handle* h,
+                         const int32_t* fwd_off /* Ne+1 */, const int32_t* fwd_idx,
+                         const int32_t* bwd_off /* Ne+1 or NULL */, const int32_t* bwd_idx,
+                         const int32_t* len_bwd /* Ne */);
+
+/* Load-time word vectors, d x Nw row-major (= DataFactory.wordVectorMaxtrixLoaded,
+ * DataFactory.java:383-387).  Required when wv_source == NTN_WV_FROZEN. */
+int ntn_set_frozen_wv(ntn_handle* h, const float* wv /* d*Nw */);
+
+/* The batch job (DataFactory.generateNewTrainingBatchJob, DataFactory.java:116-136): n columns
+ * (e1, rel, e2, e3_corrupt) in batch order.  Indices are validated.  Columns sharing
+ * (e1, rel, e2) are grouped internally; results do not depend on column order. */
+int ntn_set_batch(ntn_handle* h, int64_t n,
+                  const int32_t* e1, const int32_t* rel, const int32_t* e2, const int32_t* e3);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* computeAt (NTN.java:92-443).  theta and grad are host arrays of P doubles in the reference's
+ * flattening order W | V | b | U | wordvectors (NTN.java:450-526); values are rounded to FP32
+ * on entry exactly as Util.convertDoubleArrayToFlattenedINDArray does (Util.java:49-55).
+ * corrupt_side[r] != 0  <=>  the reference's Math.random() > 0.5 for relation r (NTN.java:146):
+ * negatives are (e1, e3); 0: (e3, e2).  n_active (may be NULL) = this call's increment of the
+ * reference's `update` counter (NTN.java:222). */
+int ntn_eval(ntn_handle* h, const double* theta, const uint8_t* corrupt_side /* R */,
+             double* cost, double* grad, int64_t* n_active);
+
+/* Same with FP32 host arrays (halves the bytes that cross PCIe; same arithmetic). */
+int ntn_eval_f32(ntn_handle* h, const float* theta, const uint8_t* corrupt_side,
+                 double* cost, float* grad, int64_t* n_active);
+
+/* Device-resident fast path: theta never leaves HBM.  d_theta / d_grad are DEVICE pointers to
+ * ntn_internal_dimension() floats in the library's internal layout (same small blocks, word
+ * vectors word-major and padded; convert with the two functions below).  Runs on the handle's
+ * stream; cost / n_active are host pointers, written after a stream synchronise (pass NULL for
+ * both to skip the synchronise and read them later with ntn_last_cost). */
+int ntn_eval_dev(ntn_handle* h, const float* d_theta, const uint8_t* corrupt_side,
+                 float* d_grad, double* cost, int64_t* n_active);
+int ntn_last_cost(ntn_handle* h, double* cost, int64_t* n_active);   /* synchronises */
+
+int64_t ntn_internal_dimension(const ntn_handle* h);
+/* reference-order FP32 device vector (P) <-> internal-order device vector */
+int ntn_to_internal_dev(ntn_handle* h, const float* d_ref, float* d_int);
+int ntn_from_internal_dev(ntn_handle* h, const float* d_int, float* d_ref);
+/* host double[P] (reference order) <-> internal-order device vector */
+int ntn_upload_theta(ntn_handle* h, const double* theta, float* d_int);
+int ntn_download_theta(ntn_handle* h, const float* d_int, double* theta);
+
+/* Use the caller's CUDA stream (a cudaStream_t cast to void*; NULL = the handle's own). */
+int ntn_set_stream(ntn_handle* h, void* cuda_stream);
+void* ntn_get_stream(ntn_handle* h);
+
+/* ---- eval-side scoring ("next" row N1) -------------------------------------------------- */
+/* Scores of n triples (NTN.computeBestThresholds / getPrediction, NTN.java:587-712). */
+int ntn_score(ntn_handle* h, const double* theta, int64_t n,
+              const int32_t* e1, const int32_t* rel, const int32_t* e2,
+              int32_t mode /* NTN_SCORE_* */, double* scores);
+
+/* ---- introspection --------------------------------------------------------------------- */
+/* Kernel launches issued by the last ntn_eval* call, and which contraction path it took. */
+int ntn_last_launch_count(const ntn_handle* h);
+int ntn_active_gemm_path(const ntn_handle* h);
+/* Per-phase device times of the last ntn_eval* (ms), filled only after ntn_set_profiling(h,1).
+ * names: entity_build, w_prep, gemm_fwd, score, gemm_dw, gemm_ge, entity_pull, word_pull, finalize */
+int ntn_set_profiling(ntn_handle* h, int on);
+int ntn_last_phase_ms(ntn_handle* h, float* ms /* NTN_NUM_PHASES */);
+#define NTN_NUM_PHASES 9
+const char* ntn_phase_name(int i);
+
+const char* ntn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTN_B200_H */

@@ -1,0 +1,227 @@
+"""ctypes binding of include/ntn_b200.h (the C-ABI shared library ``libntn_b200.so``).
+
+No fallback of any kind: if the library has not been built (``python -c 'import
+__graft_entry__ as g; g.build()'`` or ``make -C .../csrc``) loading raises, and every
+compute call raises ``NTNError`` on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libntn_b200.so")
+
+NTN_OK, NTN_EINVAL, NTN_ECUDA, NTN_ESTATE, NTN_EUNSUP = 0, -1, -2, -3, -4
+ACT_TANH, ACT_SIGMOID = 0, 1
+WV_FROZEN, WV_THETA = 0, 1
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+SCORE_REFERENCE_EVAL, SCORE_TRAIN = 0, 1
+NUM_PHASES = 9
+
+
+class NTNError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ntn_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("d", C.c_int32), ("k", C.c_int32), ("R", C.c_int32), ("Ne", C.c_int32), ("Nw", C.c_int32),
+                ("batch_divisor", C.c_int32), ("lambda_", C.c_float), ("activation", C.c_int32),
+                ("wv_source", C.c_int32), ("gemm_path", C.c_int32), ("device", C.c_int32),
+                ("reg_scale", C.c_float)]
+
+
+# name -> (restype, argtypes): every symbol include/ntn_b200.h declares
+_P = C.c_void_p
+_I32P = C.POINTER(C.c_int32)
+SYMBOLS = {
+    "ntn_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
+    "ntn_destroy": (None, [_P]),
+    "ntn_last_error": (C.c_char_p, [_P]),
+    "ntn_dimension": (C.c_int64, [_P]),
+    "ntn_set_entity_words": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "ntn_set_frozen_wv": (C.c_int, [_P, _P]),
+    "ntn_set_batch": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
+    "ntn_eval": (C.c_int, [_P, _P, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int64)]),
+    "ntn_eval_f32": (C.c_int, [_P, _P, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int64)]),
+    "ntn_eval_dev": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "ntn_last_cost": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "ntn_internal_dimension": (C.c_int64, [_P]),
+    "ntn_to_internal_dev": (C.c_int, [_P, _P, _P]),
+    "ntn_from_internal_dev": (C.c_int, [_P, _P, _P]),
+    "ntn_upload_theta": (C.c_int, [_P, _P, _P]),
+    "ntn_download_theta": (C.c_int, [_P, _P, _P]),
+    "ntn_set_stream": (C.c_int, [_P, _P]),
+    "ntn_get_stream": (_P, [_P]),
+    "ntn_score": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, _P]),
+    "ntn_last_launch_count": (C.c_int, [_P]),
+    "ntn_active_gemm_path": (C.c_int, [_P]),
+    "ntn_set_profiling": (C.c_int, [_P, C.c_int]),
+    "ntn_last_phase_ms": (C.c_int, [_P, _P]),
+    "ntn_phase_name": (C.c_char_p, [C.c_int]),
+    "ntn_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and type every entry point.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c \"import __graft_entry__ as g; g.build()\"` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)        # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Handle:
+    """Thin RAII wrapper over ntn_handle*.  All arrays are NumPy; device pointers are ints."""
+
+    def __init__(self, d, k, R, Ne, Nw, batch_divisor, lam, activation="tanh", wv_source="frozen",
+                 gemm_path="auto", device=0, reg_scale=1.0):
+        self.lib = load()
+        cfg = Config(d, k, R, Ne, Nw, batch_divisor, lam,
+                     {"tanh": ACT_TANH, "sigmoid": ACT_SIGMOID}[activation],
+                     {"frozen": WV_FROZEN, "theta": WV_THETA}[wv_source],
+                     {"auto": GEMM_AUTO, "simt": GEMM_SIMT, "tcgen05": GEMM_TCGEN05}[gemm_path],
+                     device, reg_scale)
+        self.h = C.c_void_p()
+        rc = self.lib.ntn_create(C.byref(cfg), C.byref(self.h))
+        if rc != NTN_OK:
+            self.h = None
+            raise NTNError(rc, self.lib.ntn_last_error(None).decode())
+        self.P = self.lib.ntn_dimension(self.h)
+        self.Pint = self.lib.ntn_internal_dimension(self.h)
+        self.R = R
+
+    def _ck(self, rc):
+        if rc != NTN_OK:
+            raise NTNError(rc, self.lib.ntn_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ntn_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- state ----
+    def set_entity_words(self, fwd_off, fwd_idx, bwd_off=None, bwd_idx=None, len_bwd=None):
+        fo, fi = _i32(fwd_off), _i32(fwd_idx)
+        bo = None if bwd_off is None else _i32(bwd_off)
+        bi = None if bwd_idx is None else _i32(bwd_idx)
+        lb = _i32(np.diff(fo) if len_bwd is None else len_bwd)
+        self._ck(self.lib.ntn_set_entity_words(self.h, _ptr(fo), _ptr(fi), _ptr(bo), _ptr(bi), _ptr(lb)))
+
+    def set_frozen_wv(self, wv):
+        wv = np.ascontiguousarray(wv, dtype=np.float32)
+        self._ck(self.lib.ntn_set_frozen_wv(self.h, _ptr(wv)))
+
+    def set_batch(self, e1, rel, e2, e3):
+        e1, rel, e2, e3 = _i32(e1), _i32(rel), _i32(e2), _i32(e3)
+        assert len(e1) == len(rel) == len(e2) == len(e3)
+        self._ck(self.lib.ntn_set_batch(self.h, len(e1), _ptr(e1), _ptr(rel), _ptr(e2), _ptr(e3)))
+
+    # ---- hot path ----
+    def _side(self, corrupt_side):
+        s = np.ascontiguousarray(corrupt_side, dtype=np.uint8)
+        assert s.size == self.R
+        return s
+
+    def eval(self, theta, corrupt_side, grad_out=None):
+        """computeAt with host double arrays in the reference's order -> (cost, grad, n_active)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        assert theta.size == self.P
+        grad = np.empty(self.P, np.float64) if grad_out is None else grad_out
+        s = self._side(corrupt_side)
+        cost, nact = C.c_double(), C.c_int64()
+        self._ck(self.lib.ntn_eval(self.h, _ptr(theta), _ptr(s), C.byref(cost), _ptr(grad), C.byref(nact)))
+        return cost.value, grad, nact.value
+
+    def eval_f32(self, theta, corrupt_side, grad_out=None):
+        theta = np.ascontiguousarray(theta, dtype=np.float32)
+        assert theta.size == self.P
+        grad = np.empty(self.P, np.float32) if grad_out is None else grad_out
+        s = self._side(corrupt_side)
+        cost, nact = C.c_double(), C.c_int64()
+        self._ck(self.lib.ntn_eval_f32(self.h, _ptr(theta), _ptr(s), C.byref(cost), _ptr(grad), C.byref(nact)))
+        return cost.value, grad, nact.value
+
+    def eval_dev(self, d_theta: int, corrupt_side, d_grad: int, sync=True):
+        s = self._side(corrupt_side)
+        if sync:
+            cost, nact = C.c_double(), C.c_int64()
+            self._ck(self.lib.ntn_eval_dev(self.h, d_theta, _ptr(s), d_grad, C.byref(cost), C.byref(nact)))
+            return cost.value, nact.value
+        self._ck(self.lib.ntn_eval_dev(self.h, d_theta, _ptr(s), d_grad, None, None))
+        return None
+
+    def last_cost(self):
+        cost, nact = C.c_double(), C.c_int64()
+        self._ck(self.lib.ntn_last_cost(self.h, C.byref(cost), C.byref(nact)))
+        return cost.value, nact.value
+
+    def to_internal_dev(self, d_ref: int, d_int: int):
+        self._ck(self.lib.ntn_to_internal_dev(self.h, d_ref, d_int))
+
+    def from_internal_dev(self, d_int: int, d_ref: int):
+        self._ck(self.lib.ntn_from_internal_dev(self.h, d_int, d_ref))
+
+    def upload_theta(self, theta, d_int: int):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        assert theta.size == self.P
+        self._ck(self.lib.ntn_upload_theta(self.h, _ptr(theta), d_int))
+
+    def download_theta(self, d_int: int):
+        out = np.empty(self.P, np.float64)
+        self._ck(self.lib.ntn_download_theta(self.h, d_int, _ptr(out)))
+        return out
+
+    def set_stream(self, cuda_stream: int | None):
+        self._ck(self.lib.ntn_set_stream(self.h, cuda_stream))
+
+    def score(self, theta, e1, rel, e2, mode="reference_eval"):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        e1, rel, e2 = _i32(e1), _i32(rel), _i32(e2)
+        out = np.empty(len(e1), np.float64)
+        m = {"reference_eval": SCORE_REFERENCE_EVAL, "train": SCORE_TRAIN}[mode]
+        self._ck(self.lib.ntn_score(self.h, _ptr(theta), len(e1), _ptr(e1), _ptr(rel), _ptr(e2), m, _ptr(out)))
+        return out
+
+    # ---- introspection ----
+    @property
+    def launches(self):
+        return self.lib.ntn_last_launch_count(self.h)
+
+    @property
+    def gemm_path(self):
+        return {GEMM_SIMT: "simt", GEMM_TCGEN05: "tcgen05"}.get(self.lib.ntn_active_gemm_path(self.h), "?")
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.ntn_set_profiling(self.h, int(on)))
+
+    def phase_ms(self):
+        ms = np.zeros(NUM_PHASES, np.float32)
+        self._ck(self.lib.ntn_last_phase_ms(self.h, _ptr(ms)))
+        return {self.lib.ntn_phase_name(i).decode(): float(ms[i]) for i in range(NUM_PHASES)}

@@ -1,0 +1,576 @@
+// C-ABI entry points (include/ntn_b200.h): handle lifetime, DataFactory state upload and batch
+// indexing, and the evaluation driver that strings the kernels together.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <thread>
+
+#include "ntn_internal.h"
+
+int ntn_reg_part_count(const NtnDims& dm);                    // ntn_kernels.cu
+int ntn_tc_supported(const ntn_handle* h);                     // gemm_tcgen05.cu
+int ntn_tc_prepare_batch(ntn_handle* h);
+void ntn_tc_release(ntn_handle* h);
+int ntn_tc_w_prep(ntn_handle* h, const float* theta);
+int ntn_tc_gemm_fwd(ntn_handle* h);
+int ntn_tc_gemm_dw(ntn_handle* h);
+int ntn_tc_gemm_ge(ntn_handle* h);
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return NTN_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+#define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
+
+template <typename T> static int dev_alloc(ntn_handle* h, T** p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) n = 1;
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    return NTN_OK;
+}
+template <typename T> static int dev_upload(ntn_handle* h, T** p, const std::vector<T>& v) {
+    int rc = dev_alloc(h, p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) CK(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return NTN_OK;
+}
+template <typename T> static void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+static NtnDims make_dims(const ntn_config& c) {
+    NtnDims m{};
+    m.d = c.d; m.k = c.k; m.R = c.R; m.Ne = c.Ne; m.Nw = c.Nw;
+    m.dq = (int)round_up(c.d, 4);
+    m.Kp = (int)round_up(c.d + 1, 8);
+    m.Np = (int)round_up((int64_t)c.k * m.dq + c.k, 16);
+    int64_t d = c.d, k = c.k, R = c.R;
+    m.oW = 0;
+    m.oV = m.oW + R * k * d * d;
+    m.ob = m.oV + R * 2 * d * k;
+    m.oU = m.ob + R * k;
+    m.oWVref = m.oU + R * k;
+    m.P = m.oWVref + d * (int64_t)c.Nw;
+    m.oWVint = round_up(m.oWVref, 4);
+    m.Pint = m.oWVint + (int64_t)c.Nw * m.dq;
+    return m;
+}
+
+extern "C" const char* ntn_version(void) { return "ntn_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* ntn_last_error(const ntn_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+static const char* kPhaseNames[NTN_NUM_PHASES] = {"entity_build", "w_prep", "gemm_fwd", "score", "gemm_dw",
+                                                  "gemm_ge", "entity_pull", "word_pull", "finalize"};
+extern "C" const char* ntn_phase_name(int i) { return (i >= 0 && i < NTN_NUM_PHASES) ? kPhaseNames[i] : ""; }
+
+extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
+    if (!cfg || !out) { g_create_err = "null argument"; return NTN_EINVAL; }
+    *out = nullptr;
+    if (cfg->d < 1 || cfg->d > 256 || cfg->k < 1 || cfg->k > 8) {
+        g_create_err = "unsupported shape: need 1 <= d <= 256 and 1 <= k <= 8";
+        return NTN_EUNSUP;
+    }
+    if (cfg->R < 1 || cfg->Ne < 1 || cfg->Nw < 1 || cfg->batch_divisor < 1) {
+        g_create_err = "R, Ne, Nw and batch_divisor must be positive";
+        return NTN_EINVAL;
+    }
+    if (cfg->activation != NTN_ACT_TANH && cfg->activation != NTN_ACT_SIGMOID) {
+        g_create_err = "activation must be NTN_ACT_TANH or NTN_ACT_SIGMOID";
+        return NTN_EINVAL;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
+        return NTN_ECUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "device ordinal out of range"; return NTN_EINVAL; }
+    ntn_handle* h = new ntn_handle();
+    h->cfg = *cfg;
+    if (h->cfg.reg_scale == 0.f) h->cfg.reg_scale = 1.f;
+    h->dm = make_dims(*cfg);
+    h->device = cfg->device;
+    auto bail = [&](int rc) { g_create_err = h->err; ntn_destroy(h); return rc; };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(NTN_ECUDA); } } while (0)
+    CKC(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        h->err = "this library is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return bail(NTN_ECUDA);
+    }
+    CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    const NtnDims& dm = h->dm;
+    CKC(cudaMalloc((void**)&h->E, (size_t)dm.Ne * dm.Kp * sizeof(float)));
+    CKC(cudaMalloc((void**)&h->gE, (size_t)dm.Ne * dm.dq * sizeof(float)));
+    CKC(cudaMalloc((void**)&h->Waug, (size_t)dm.R * dm.Kp * dm.Np * sizeof(float)));
+    CKC(cudaMalloc((void**)&h->side, dm.R));
+    CKC(cudaMallocHost((void**)&h->h_side, dm.R));
+    h->n_reg_part = ntn_reg_part_count(dm);
+    CKC(cudaMalloc((void**)&h->reg_part, (size_t)h->n_reg_part * sizeof(double)));
+    CKC(cudaMalloc((void**)&h->d_out, 4 * sizeof(double)));
+    CKC(cudaMallocHost((void**)&h->h_out, 4 * sizeof(double)));
+    for (int i = 0; i <= NTN_NUM_PHASES; ++i) CKC(cudaEventCreate(&h->ev[i]));
+#undef CKC
+    *out = h;
+    return NTN_OK;
+}
+
+static void free_batch(DeviceBatch& b) {
+    dev_free(b.u_e1); dev_free(b.u_e2); dev_free(b.u_rel); dev_free(b.c_off); dev_free(b.c_e3);
+    dev_free(b.t_rel); dev_free(b.t_u0); dev_free(b.t_n); dev_free(b.ch_rel); dev_free(b.ch_u0); dev_free(b.ch_n);
+    dev_free(b.relch_off); dev_free(b.reltile_off); dev_free(b.inc_off); dev_free(b.inc_u); dev_free(b.inc_code);
+    dev_free(b.eh_ent); dev_free(b.eh_begin); dev_free(b.eh_end); dev_free(b.eh_first); dev_free(b.eh_count);
+    dev_free(b.T); dev_free(b.M); dev_free(b.GA); dev_free(b.acoef); dev_free(b.ccoef); dev_free(b.dWpart);
+    dev_free(b.tp_cost); dev_free(b.tp_nact); dev_free(b.tp_dU); dev_free(b.eh_part);
+    b = DeviceBatch();
+}
+
+extern "C" void ntn_destroy(ntn_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    ntn_tc_release(h);
+    free_batch(h->b);
+    DeviceWords& w = h->w;
+    dev_free(w.fwd_off); dev_free(w.fwd_idx); dev_free(w.w_off); dev_free(w.w_ent); dev_free(w.len_bwd);
+    dev_free(w.wh_word); dev_free(w.wh_begin); dev_free(w.wh_end); dev_free(w.wh_first); dev_free(w.wh_count);
+    dev_free(w.wh_part);
+    dev_free(h->wv_frozen); dev_free(h->E); dev_free(h->gE); dev_free(h->Waug); dev_free(h->side);
+    dev_free(h->reg_part); dev_free(h->d_out); dev_free(h->d_ref_theta); dev_free(h->d_ref_grad);
+    dev_free(h->d_int_theta); dev_free(h->d_int_grad);
+    if (h->h_side) cudaFreeHost(h->h_side);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    for (int i = 0; i <= NTN_NUM_PHASES; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+extern "C" int64_t ntn_dimension(const ntn_handle* h) { return h ? h->dm.P : -1; }
+extern "C" int64_t ntn_internal_dimension(const ntn_handle* h) { return h ? h->dm.Pint : -1; }
+extern "C" int ntn_last_launch_count(const ntn_handle* h) { return h ? h->launches : -1; }
+extern "C" int ntn_active_gemm_path(const ntn_handle* h) { return h ? h->gemm_path_active : -1; }
+
+extern "C" int ntn_set_stream(ntn_handle* h, void* s) {
+    if (!h) return NTN_EINVAL;
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return NTN_OK;
+}
+extern "C" void* ntn_get_stream(ntn_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int ntn_set_profiling(ntn_handle* h, int on) { if (!h) return NTN_EINVAL; h->profiling = on != 0; return NTN_OK; }
+
+// Split the lists longer than NTN_HUB_SEG into segments (hub words like "unknown", hub entities).
+static void build_hub_segments(const std::vector<int>& off, int nrows, std::vector<int>& seg_row,
+                               std::vector<int>& seg_begin, std::vector<int>& seg_end, std::vector<int>& first,
+                               std::vector<int>& count) {
+    first.assign(nrows, -1);
+    count.assign(nrows, 0);
+    for (int r = 0; r < nrows; ++r) {
+        int n = off[r + 1] - off[r];
+        if (n <= NTN_HUB_SEG) continue;
+        first[r] = (int)seg_row.size();
+        for (int b = off[r]; b < off[r + 1]; b += NTN_HUB_SEG) {
+            seg_row.push_back(r);
+            seg_begin.push_back(b);
+            seg_end.push_back(std::min(b + NTN_HUB_SEG, off[r + 1]));
+            count[r]++;
+        }
+    }
+}
+
+extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const int32_t* fwd_idx,
+                                    const int32_t* bwd_off, const int32_t* bwd_idx, const int32_t* len_bwd) {
+    if (!h) return NTN_EINVAL;
+    if (!fwd_off || !fwd_idx || !len_bwd) FAIL(NTN_EINVAL, "null argument");
+    CK(cudaSetDevice(h->device));
+    const NtnDims& dm = h->dm;
+    if (!bwd_off || !bwd_idx) { bwd_off = fwd_off; bwd_idx = fwd_idx; }
+    if (fwd_off[0] != 0 || bwd_off[0] != 0) FAIL(NTN_EINVAL, "CSR offsets must start at 0");
+    for (int n = 0; n < dm.Ne; ++n) {
+        if (fwd_off[n + 1] <= fwd_off[n]) FAIL(NTN_EINVAL, "entity " + std::to_string(n) + " has no forward word");
+        if (bwd_off[n + 1] < bwd_off[n]) FAIL(NTN_EINVAL, "backward CSR offsets not monotone");
+        if (len_bwd[n] <= 0)
+            FAIL(NTN_EINVAL, "entityLength(" + std::to_string(n) + ") <= 0: the reference divides by zero here (NTN.java:420)");
+    }
+    int nf = fwd_off[dm.Ne], nb = bwd_off[dm.Ne];
+    for (int j = 0; j < nf; ++j) if (fwd_idx[j] < 0 || fwd_idx[j] >= dm.Nw) FAIL(NTN_EINVAL, "forward word index out of range");
+    for (int j = 0; j < nb; ++j) if (bwd_idx[j] < 0 || bwd_idx[j] >= dm.Nw) FAIL(NTN_EINVAL, "backward word index out of range");
+    DeviceWords& w = h->w;
+    w.nnz_f = nf; w.nnz_b = nb;
+    std::vector<int> vfo(fwd_off, fwd_off + dm.Ne + 1), vfi(fwd_idx, fwd_idx + nf);
+    // inverse CSR word -> entities (stable counting sort: entities ascending, multiplicity kept),
+    // the order NTN.java:414-426 visits them in.
+    std::vector<int> woff(dm.Nw + 1, 0), went(nb);
+    for (int j = 0; j < nb; ++j) woff[bwd_idx[j] + 1]++;
+    for (int i = 0; i < dm.Nw; ++i) woff[i + 1] += woff[i];
+    {
+        std::vector<int> cur(woff.begin(), woff.end() - 1);
+        for (int n = 0; n < dm.Ne; ++n)
+            for (int j = bwd_off[n]; j < bwd_off[n + 1]; ++j) went[cur[bwd_idx[j]]++] = n;
+    }
+    std::vector<float> lb(dm.Ne);
+    for (int n = 0; n < dm.Ne; ++n) lb[n] = (float)len_bwd[n];
+    std::vector<int> sr, sb, se, first, count;
+    build_hub_segments(woff, dm.Nw, sr, sb, se, first, count);
+    w.n_hub_segs = (int)sr.size();
+    int rc;
+    if ((rc = dev_upload(h, &w.fwd_off, vfo)) || (rc = dev_upload(h, &w.fwd_idx, vfi)) ||
+        (rc = dev_upload(h, &w.w_off, woff)) || (rc = dev_upload(h, &w.w_ent, went)) ||
+        (rc = dev_upload(h, &w.len_bwd, lb)) || (rc = dev_upload(h, &w.wh_word, sr)) ||
+        (rc = dev_upload(h, &w.wh_begin, sb)) || (rc = dev_upload(h, &w.wh_end, se)) ||
+        (rc = dev_upload(h, &w.wh_first, first)) || (rc = dev_upload(h, &w.wh_count, count)) ||
+        (rc = dev_alloc(h, &w.wh_part, (size_t)w.n_hub_segs * dm.dq)))
+        return rc;
+    CK(cudaStreamSynchronize(h->stream));     // host vectors go out of scope
+    w.set = true;
+    return NTN_OK;
+}
+
+extern "C" int ntn_set_frozen_wv(ntn_handle* h, const float* wv) {
+    if (!h) return NTN_EINVAL;
+    if (!wv) FAIL(NTN_EINVAL, "null argument");
+    CK(cudaSetDevice(h->device));
+    const NtnDims& dm = h->dm;
+    float* tmp = nullptr;
+    size_t n = (size_t)dm.d * dm.Nw;
+    CK(cudaMalloc((void**)&tmp, n * sizeof(float)));
+    int rc = dev_alloc(h, &h->wv_frozen, (size_t)dm.Nw * dm.dq);
+    if (rc) { cudaFree(tmp); return rc; }
+    cudaError_t e = cudaMemcpyAsync(tmp, wv, n * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) { ntn_launch_transpose_wv_host_layout(h, tmp, h->wv_frozen); e = cudaStreamSynchronize(h->stream); }
+    cudaFree(tmp);
+    if (e != cudaSuccess) FAIL(NTN_ECUDA, std::string("set_frozen_wv: ") + cudaGetErrorString(e));
+    return NTN_OK;
+}
+
+extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const int32_t* rel, const int32_t* e2,
+                             const int32_t* e3) {
+    if (!h) return NTN_EINVAL;
+    if (n < 0 || (n > 0 && (!e1 || !rel || !e2 || !e3))) FAIL(NTN_EINVAL, "null argument");
+    if (n > (int64_t)1 << 30) FAIL(NTN_EUNSUP, "batch too large");
+    CK(cudaSetDevice(h->device));
+    const NtnDims& dm = h->dm;
+    for (int64_t j = 0; j < n; ++j) {
+        if (e1[j] < 0 || e1[j] >= dm.Ne || e2[j] < 0 || e2[j] >= dm.Ne || e3[j] < 0 || e3[j] >= dm.Ne)
+            FAIL(NTN_EINVAL, "entity index out of range in column " + std::to_string(j));
+        if (rel[j] < 0 || rel[j] >= dm.R) FAIL(NTN_EINVAL, "relation index out of range in column " + std::to_string(j));
+    }
+    // group the columns by (rel, e1, e2): the C corrupt copies of one training triple
+    // (DataFactory.java:123-129) become one unique triple with a list of e3.
+    std::vector<int> order((size_t)n);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (rel[a] != rel[b]) return rel[a] < rel[b];
+        if (e1[a] != e1[b]) return e1[a] < e1[b];
+        if (e2[a] != e2[b]) return e2[a] < e2[b];
+        return a < b;
+    });
+    std::vector<int> u_e1, u_e2, u_rel, c_off, c_e3((size_t)n), col_u((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        int j = order[i];
+        if (i == 0 || rel[j] != u_rel.back() || e1[j] != u_e1.back() || e2[j] != u_e2.back()) {
+            u_e1.push_back(e1[j]); u_e2.push_back(e2[j]); u_rel.push_back(rel[j]);
+            c_off.push_back((int)i);
+        }
+        c_e3[i] = e3[j];
+        col_u[i] = (int)u_e1.size() - 1;
+    }
+    c_off.push_back((int)n);
+    int Nu = (int)u_e1.size();
+    std::vector<int> rel_off(dm.R + 1, 0);
+    for (int u = 0; u < Nu; ++u) rel_off[u_rel[u] + 1]++;
+    for (int r = 0; r < dm.R; ++r) rel_off[r + 1] += rel_off[r];
+    std::vector<int> t_rel, t_u0, t_n, ch_rel, ch_u0, ch_n, relch_off(dm.R + 1, 0), reltile_off(dm.R + 1, 0);
+    for (int r = 0; r < dm.R; ++r) {
+        for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += NTN_TILE_ROWS) {
+            t_rel.push_back(r); t_u0.push_back(u0); t_n.push_back(std::min(NTN_TILE_ROWS, rel_off[r + 1] - u0));
+        }
+        for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += NTN_CHUNK_ROWS) {
+            ch_rel.push_back(r); ch_u0.push_back(u0); ch_n.push_back(std::min(NTN_CHUNK_ROWS, rel_off[r + 1] - u0));
+        }
+        reltile_off[r + 1] = (int)t_rel.size();
+        relch_off[r + 1] = (int)ch_rel.size();
+    }
+    // entity -> incidents: (e1 role, e2 role, corrupt columns), stable counting sort by entity
+    int n_inc = 2 * Nu + (int)n;
+    std::vector<int> inc_off(dm.Ne + 1, 0), inc_u(n_inc), inc_code(n_inc);
+    for (int u = 0; u < Nu; ++u) { inc_off[u_e1[u] + 1]++; inc_off[u_e2[u] + 1]++; }
+    for (int64_t c = 0; c < n; ++c) inc_off[c_e3[c] + 1]++;
+    for (int e = 0; e < dm.Ne; ++e) inc_off[e + 1] += inc_off[e];
+    {
+        std::vector<int> cur(inc_off.begin(), inc_off.end() - 1);
+        for (int u = 0; u < Nu; ++u) { int p = cur[u_e1[u]]++; inc_u[p] = u; inc_code[p] = -1; }
+        for (int u = 0; u < Nu; ++u) { int p = cur[u_e2[u]]++; inc_u[p] = u; inc_code[p] = -2; }
+        for (int64_t c = 0; c < n; ++c) { int p = cur[c_e3[c]]++; inc_u[p] = col_u[c]; inc_code[p] = (int)c; }
+    }
+    std::vector<int> sr, sb, se, first, count;
+    build_hub_segments(inc_off, dm.Ne, sr, sb, se, first, count);
+
+    CK(cudaStreamSynchronize(h->stream));
+    free_batch(h->b);
+    DeviceBatch& b = h->b;
+    b.N = n; b.Nu = Nu; b.ntiles = (int)t_rel.size(); b.nchunks = (int)ch_rel.size(); b.n_inc = n_inc;
+    b.n_ent_hub_segs = (int)sr.size();
+    int rc;
+    if ((rc = dev_upload(h, &b.u_e1, u_e1)) || (rc = dev_upload(h, &b.u_e2, u_e2)) || (rc = dev_upload(h, &b.u_rel, u_rel)) ||
+        (rc = dev_upload(h, &b.c_off, c_off)) || (rc = dev_upload(h, &b.c_e3, c_e3)) ||
+        (rc = dev_upload(h, &b.t_rel, t_rel)) || (rc = dev_upload(h, &b.t_u0, t_u0)) || (rc = dev_upload(h, &b.t_n, t_n)) ||
+        (rc = dev_upload(h, &b.ch_rel, ch_rel)) || (rc = dev_upload(h, &b.ch_u0, ch_u0)) || (rc = dev_upload(h, &b.ch_n, ch_n)) ||
+        (rc = dev_upload(h, &b.relch_off, relch_off)) || (rc = dev_upload(h, &b.reltile_off, reltile_off)) ||
+        (rc = dev_upload(h, &b.inc_off, inc_off)) || (rc = dev_upload(h, &b.inc_u, inc_u)) ||
+        (rc = dev_upload(h, &b.inc_code, inc_code)) || (rc = dev_upload(h, &b.eh_ent, sr)) ||
+        (rc = dev_upload(h, &b.eh_begin, sb)) || (rc = dev_upload(h, &b.eh_end, se)) ||
+        (rc = dev_upload(h, &b.eh_first, first)) || (rc = dev_upload(h, &b.eh_count, count)) ||
+        (rc = dev_alloc(h, &b.T, (size_t)Nu * dm.Np)) || (rc = dev_alloc(h, &b.M, (size_t)Nu * dm.Np)) ||
+        (rc = dev_alloc(h, &b.GA, (size_t)Nu * dm.Kp)) || (rc = dev_alloc(h, &b.acoef, (size_t)Nu * dm.k)) ||
+        (rc = dev_alloc(h, &b.ccoef, (size_t)n * dm.k)) ||
+        (rc = dev_alloc(h, &b.dWpart, (size_t)b.nchunks * dm.Kp * dm.Np)) ||
+        (rc = dev_alloc(h, &b.tp_cost, (size_t)b.ntiles)) || (rc = dev_alloc(h, &b.tp_nact, (size_t)b.ntiles)) ||
+        (rc = dev_alloc(h, &b.tp_dU, (size_t)b.ntiles * dm.k)) ||
+        (rc = dev_alloc(h, &b.eh_part, (size_t)b.n_ent_hub_segs * dm.dq)))
+        return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    // contraction path for this batch
+    h->gemm_path_active = NTN_GEMM_SIMT;
+    if (h->cfg.gemm_path != NTN_GEMM_SIMT) {
+        if (ntn_tc_supported(h)) {
+            rc = ntn_tc_prepare_batch(h);
+            if (rc) return rc;
+            h->gemm_path_active = NTN_GEMM_TCGEN05;
+        } else if (h->cfg.gemm_path == NTN_GEMM_TCGEN05) {
+            FAIL(NTN_EUNSUP, "tcgen05 contraction path does not support this shape");
+        }
+    }
+    return NTN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the evaluation driver                                          NTN.computeAt, NTN.java:92-443
+// ------------------------------------------------------------------------------------------
+static int eval_internal(ntn_handle* h, const float* d_theta, const uint8_t* corrupt_side, float* d_grad) {
+    const NtnDims& dm = h->dm;
+    if (!h->w.set) FAIL(NTN_ESTATE, "ntn_set_entity_words has not been called");
+    if (!corrupt_side) FAIL(NTN_EINVAL, "corrupt_side is null");
+    const float* wvt;
+    if (h->cfg.wv_source == NTN_WV_FROZEN) {
+        if (!h->wv_frozen) FAIL(NTN_ESTATE, "wv_source is NTN_WV_FROZEN but ntn_set_frozen_wv has not been called");
+        wvt = h->wv_frozen;
+    } else {
+        wvt = d_theta + dm.oWVint;
+    }
+    h->launches = 0;
+    const bool prof = h->profiling;
+    int pe = 0;
+    auto mark = [&]() { if (prof) cudaEventRecord(h->ev[pe++], h->stream); };
+    // h_side is reused across calls: make sure the previous evaluation has consumed it
+    // (it has if the caller synchronised; otherwise this is a no-op wait on our own stream)
+    CK(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < dm.R; ++r) h->h_side[r] = corrupt_side[r] ? 1 : 0;
+    CK(cudaMemcpyAsync(h->side, h->h_side, dm.R, cudaMemcpyHostToDevice, h->stream));
+    const bool tc = h->gemm_path_active == NTN_GEMM_TCGEN05 && h->b.ntiles > 0;
+    int rc;
+    mark(); ntn_launch_entity_build(h, wvt);                               // NTN.java:103
+    mark();
+    if (tc) { if ((rc = ntn_tc_w_prep(h, d_theta))) return rc; } else ntn_launch_w_prep(h, d_theta);
+    mark();
+    if (tc) { if ((rc = ntn_tc_gemm_fwd(h))) return rc; } else ntn_launch_gemm_fwd_simt(h);    // :163-197
+    mark(); ntn_launch_score(h, d_theta);                                  // :200-289
+    mark();
+    if (tc) { if ((rc = ntn_tc_gemm_dw(h))) return rc; } else ntn_launch_gemm_dw_simt(h);      // :301-349
+    mark();
+    if (tc) { if ((rc = ntn_tc_gemm_ge(h))) return rc; } else ntn_launch_gemm_ge_simt(h);      // :352-388
+    mark(); ntn_launch_entity_pull(h);                                     // Util.java:74-98
+    mark(); ntn_launch_word_pull(h, d_theta, d_grad);                      // :411-430
+    mark(); ntn_launch_finalize(h, d_theta, d_grad);                       // :398-401,433-438
+    mark();
+    CK(cudaMemcpyAsync(h->h_out, h->d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaGetLastError());
+    return NTN_OK;
+}
+
+extern "C" int ntn_last_cost(ntn_handle* h, double* cost, int64_t* n_active) {
+    if (!h) return NTN_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    if (cost) *cost = h->h_out[0];
+    if (n_active) *n_active = (int64_t)llround(h->h_out[1]);
+    if (h->profiling)
+        for (int i = 0; i < NTN_NUM_PHASES; ++i) cudaEventElapsedTime(&h->phase_ms[i], h->ev[i], h->ev[i + 1]);
+    return NTN_OK;
+}
+
+extern "C" int ntn_last_phase_ms(ntn_handle* h, float* ms) {
+    if (!h || !ms) return NTN_EINVAL;
+    for (int i = 0; i < NTN_NUM_PHASES; ++i) ms[i] = h->phase_ms[i];
+    return NTN_OK;
+}
+
+extern "C" int ntn_eval_dev(ntn_handle* h, const float* d_theta, const uint8_t* corrupt_side, float* d_grad,
+                            double* cost, int64_t* n_active) {
+    if (!h) return NTN_EINVAL;
+    if (!d_theta || !d_grad) FAIL(NTN_EINVAL, "null device pointer");
+    CK(cudaSetDevice(h->device));
+    int rc = eval_internal(h, d_theta, corrupt_side, d_grad);
+    if (rc) return rc;
+    if (cost || n_active) return ntn_last_cost(h, cost, n_active);
+    return NTN_OK;
+}
+
+extern "C" int ntn_to_internal_dev(ntn_handle* h, const float* d_ref, float* d_int) {
+    if (!h) return NTN_EINVAL;
+    if (!d_ref || !d_int) FAIL(NTN_EINVAL, "null device pointer");
+    CK(cudaSetDevice(h->device));
+    ntn_launch_to_internal(h, d_ref, d_int);
+    CK(cudaGetLastError());
+    return NTN_OK;
+}
+extern "C" int ntn_from_internal_dev(ntn_handle* h, const float* d_int, float* d_ref) {
+    if (!h) return NTN_EINVAL;
+    if (!d_ref || !d_int) FAIL(NTN_EINVAL, "null device pointer");
+    CK(cudaSetDevice(h->device));
+    ntn_launch_from_internal(h, d_int, d_ref);
+    CK(cudaGetLastError());
+    return NTN_OK;
+}
+
+// host <-> pinned staging with type conversion, split over a few threads (the arrays are ~57 MB)
+template <typename S, typename D> static void convert_parallel(const S* src, D* dst, int64_t n) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<int64_t>(std::max(1u, std::min(hw, 8u)), std::max<int64_t>(1, n / (1 << 18)));
+    auto work = [=](int t) {
+        int64_t a = n * t / nt, b = n * (t + 1) / nt;
+        for (int64_t i = a; i < b; ++i) dst[i] = (D)src[i];      // double -> float rounds like Util.java:49-55
+    };
+    if (nt <= 1) { work(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
+static int ensure_host_path(ntn_handle* h) {
+    const NtnDims& dm = h->dm;
+    int rc;
+    if (!h->d_ref_theta && (rc = dev_alloc(h, &h->d_ref_theta, (size_t)dm.P))) return rc;
+    if (!h->d_ref_grad && (rc = dev_alloc(h, &h->d_ref_grad, (size_t)dm.P))) return rc;
+    if (!h->d_int_theta && (rc = dev_alloc(h, &h->d_int_theta, (size_t)dm.Pint))) return rc;
+    if (!h->d_int_grad && (rc = dev_alloc(h, &h->d_int_grad, (size_t)dm.Pint))) return rc;
+    if (!h->h_stage) CK(cudaMallocHost((void**)&h->h_stage, (size_t)dm.P * sizeof(float)));
+    return NTN_OK;
+}
+
+template <typename TH, typename TG>
+static int eval_host(ntn_handle* h, const TH* theta, const uint8_t* corrupt_side, double* cost, TG* grad, int64_t* n_active) {
+    if (!h) return NTN_EINVAL;
+    if (!theta || !grad || !cost) FAIL(NTN_EINVAL, "null argument");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_host_path(h);
+    if (rc) return rc;
+    const NtnDims& dm = h->dm;
+    CK(cudaStreamSynchronize(h->stream));
+    convert_parallel(theta, h->h_stage, dm.P);
+    CK(cudaMemcpyAsync(h->d_ref_theta, h->h_stage, (size_t)dm.P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    ntn_launch_to_internal(h, h->d_ref_theta, h->d_int_theta);
+    rc = eval_internal(h, h->d_int_theta, corrupt_side, h->d_int_grad);
+    if (rc) return rc;
+    int launches = h->launches + 2;
+    ntn_launch_from_internal(h, h->d_int_grad, h->d_ref_grad);
+    h->launches = launches + 2;
+    CK(cudaMemcpyAsync(h->h_stage, h->d_ref_grad, (size_t)dm.P * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    rc = ntn_last_cost(h, cost, n_active);
+    if (rc) return rc;
+    convert_parallel(h->h_stage, grad, dm.P);
+    return NTN_OK;
+}
+
+extern "C" int ntn_eval(ntn_handle* h, const double* theta, const uint8_t* corrupt_side, double* cost, double* grad,
+                        int64_t* n_active) {
+    return eval_host<double, double>(h, theta, corrupt_side, cost, grad, n_active);
+}
+extern "C" int ntn_eval_f32(ntn_handle* h, const float* theta, const uint8_t* corrupt_side, double* cost, float* grad,
+                            int64_t* n_active) {
+    return eval_host<float, float>(h, theta, corrupt_side, cost, grad, n_active);
+}
+
+extern "C" int ntn_upload_theta(ntn_handle* h, const double* theta, float* d_int) {
+    if (!h) return NTN_EINVAL;
+    if (!theta || !d_int) FAIL(NTN_EINVAL, "null argument");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_host_path(h);
+    if (rc) return rc;
+    const NtnDims& dm = h->dm;
+    CK(cudaStreamSynchronize(h->stream));
+    convert_parallel(theta, h->h_stage, dm.P);
+    CK(cudaMemcpyAsync(h->d_ref_theta, h->h_stage, (size_t)dm.P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    ntn_launch_to_internal(h, h->d_ref_theta, d_int);
+    CK(cudaStreamSynchronize(h->stream));
+    return NTN_OK;
+}
+extern "C" int ntn_download_theta(ntn_handle* h, const float* d_int, double* theta) {
+    if (!h) return NTN_EINVAL;
+    if (!theta || !d_int) FAIL(NTN_EINVAL, "null argument");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_host_path(h);
+    if (rc) return rc;
+    const NtnDims& dm = h->dm;
+    ntn_launch_from_internal(h, d_int, h->d_ref_grad);
+    CK(cudaMemcpyAsync(h->h_stage, h->d_ref_grad, (size_t)dm.P * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    convert_parallel(h->h_stage, theta, dm.P);
+    return NTN_OK;
+}
+
+extern "C" int ntn_score(ntn_handle* h, const double* theta, int64_t n, const int32_t* e1, const int32_t* rel,
+                         const int32_t* e2, int32_t mode, double* scores) {
+    if (!h) return NTN_EINVAL;
+    if (!theta || (n > 0 && (!e1 || !rel || !e2 || !scores))) FAIL(NTN_EINVAL, "null argument");
+    if (mode != NTN_SCORE_REFERENCE_EVAL && mode != NTN_SCORE_TRAIN) FAIL(NTN_EINVAL, "bad score mode");
+    if (!h->w.set) FAIL(NTN_ESTATE, "ntn_set_entity_words has not been called");
+    CK(cudaSetDevice(h->device));
+    const NtnDims& dm = h->dm;
+    for (int64_t j = 0; j < n; ++j)
+        if (e1[j] < 0 || e1[j] >= dm.Ne || e2[j] < 0 || e2[j] >= dm.Ne || rel[j] < 0 || rel[j] >= dm.R)
+            FAIL(NTN_EINVAL, "index out of range in triple " + std::to_string(j));
+    int rc = ensure_host_path(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    convert_parallel(theta, h->h_stage, dm.P);
+    CK(cudaMemcpyAsync(h->d_ref_theta, h->h_stage, (size_t)dm.P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    ntn_launch_to_internal(h, h->d_ref_theta, h->d_int_theta);
+    const float* wvt;
+    if (h->cfg.wv_source == NTN_WV_FROZEN) {                   // NTN.java:592,677: same stale vectors at eval time
+        if (!h->wv_frozen) FAIL(NTN_ESTATE, "wv_source is NTN_WV_FROZEN but ntn_set_frozen_wv has not been called");
+        wvt = h->wv_frozen;
+    } else {
+        wvt = h->d_int_theta + dm.oWVint;
+    }
+    ntn_launch_entity_build(h, wvt);
+    int *d_e1 = nullptr, *d_rel = nullptr, *d_e2 = nullptr; double* d_s = nullptr;
+    size_t nn = (size_t)std::max<int64_t>(n, 1);
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc((void**)&d_e1, nn * 4)) == cudaSuccess && (e = cudaMalloc((void**)&d_rel, nn * 4)) == cudaSuccess &&
+        (e = cudaMalloc((void**)&d_e2, nn * 4)) == cudaSuccess && (e = cudaMalloc((void**)&d_s, nn * 8)) == cudaSuccess && n > 0) {
+        cudaMemcpyAsync(d_e1, e1, n * 4, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(d_rel, rel, n * 4, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(d_e2, e2, n * 4, cudaMemcpyHostToDevice, h->stream);
+        ntn_launch_score_eval(h, h->d_int_theta, d_e1, d_rel, d_e2, n, mode, d_s);
+        cudaMemcpyAsync(scores, d_s, n * 8, cudaMemcpyDeviceToHost, h->stream);
+        e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
+    cudaFree(d_e1); cudaFree(d_rel); cudaFree(d_e2); cudaFree(d_s);
+    if (e != cudaSuccess) FAIL(NTN_ECUDA, std::string("ntn_score: ") + cudaGetErrorString(e));
+    return NTN_OK;
+}

@@ -1,0 +1,128 @@
+// Internal definitions shared by the C-ABI translation unit and the kernel translation units.
+// Not part of the public boundary (that is include/ntn_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ntn_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// Shapes.  The CUDA path is built on the de-duplicated, augmented formulation:
+//   * entity rows carry a constant 1 at index d, so the V and b terms of NTN.java:182-197 ride
+//     along in the same contraction as the bilinear term of NTN.java:163-179;
+//   * columns that share (e1, rel, e2) share one row of T' (the C corrupt copies of a training
+//     triple, DataFactory.java:123-129).
+//   dq  = d rounded up to 4       pitch of one slice inside a T'/M row, and of a word row
+//   Kp  = d+1 rounded up to 8     pitch of an entity row (index d holds 1.0f)
+//   Np  = k*dq+k rounded up to 16 pitch of a T'/M row: k slices of dq, then k "beta"/coef-sum slots
+// ------------------------------------------------------------------------------------------
+struct NtnDims {
+    int d, k, R, Ne, Nw;
+    int dq, Kp, Np;
+    int64_t P;                   // reference dimension
+    int64_t oW, oV, ob, oU;      // block offsets (same in both layouts)
+    int64_t oWVref;              // reference layout: word block d x Nw row-major
+    int64_t oWVint;              // internal layout: word block Nw x dq row-major (16-byte aligned)
+    int64_t Pint;
+};
+
+#define NTN_TILE_ROWS   128      // unique triples per score tile (one relation per tile)
+#define NTN_CHUNK_ROWS  512      // unique triples per dW split-K chunk (one relation per chunk)
+#define NTN_HUB_SEG     256      // incident-list segment length for hub words / hub entities
+
+struct DeviceBatch {
+    int64_t N = 0;               // columns
+    int Nu = 0;                  // unique (rel, e1, e2)
+    int ntiles = 0, nchunks = 0;
+    int n_inc = 0;               // incidents = 2*Nu + N
+    int n_ent_hub_segs = 0;
+    // unique triples, sorted by (rel, e1, e2)
+    int *u_e1 = nullptr, *u_e2 = nullptr, *u_rel = nullptr;
+    int *c_off = nullptr;        // Nu+1: corrupt columns of each unique triple
+    int *c_e3 = nullptr;         // N
+    int *t_rel = nullptr, *t_u0 = nullptr, *t_n = nullptr;        // score tiles
+    int *ch_rel = nullptr, *ch_u0 = nullptr, *ch_n = nullptr;     // dW chunks
+    int *relch_off = nullptr;    // R+1: chunk range per relation
+    int *reltile_off = nullptr;  // R+1: tile range per relation
+    // entity -> incidents (pull lists), sorted by (entity, code, u)
+    int *inc_off = nullptr;      // Ne+1
+    int *inc_u = nullptr;        // unique triple of the incident
+    int *inc_code = nullptr;     // -1: entity is e1 of u, -2: e2 of u, >=0: corrupt column id
+    // hub entities (incident list longer than NTN_HUB_SEG): segments + partial rows
+    int *eh_ent = nullptr, *eh_begin = nullptr, *eh_end = nullptr;   // per segment
+    int *eh_first = nullptr;     // Ne: first segment id of a hub entity, -1 otherwise
+    int *eh_count = nullptr;     // Ne: number of segments
+    // per-evaluation intermediates
+    float *T = nullptr;          // Nu x Np   T' = [E_anchor | 1] * Waug
+    float *M = nullptr;          // Nu x Np   backward coefficients folded with the gathered rows
+    float *GA = nullptr;         // Nu x Kp   anchor-entity gradient rows
+    float *acoef = nullptr;      // Nu x k    a_{u,s}
+    float *ccoef = nullptr;      // N  x k    c_{col,s}
+    float *dWpart = nullptr;     // nchunks x Kp x Np
+    double *tp_cost = nullptr;   // ntiles
+    int *tp_nact = nullptr;      // ntiles
+    float *tp_dU = nullptr;      // ntiles x k
+    float *eh_part = nullptr;    // n_ent_hub_segs x dq
+};
+
+struct DeviceWords {
+    bool set = false;
+    int nnz_f = 0, nnz_b = 0;
+    int *fwd_off = nullptr, *fwd_idx = nullptr;    // entity -> forward words
+    int *w_off = nullptr, *w_ent = nullptr;        // word -> entities of the backward lists (inverse CSR)
+    float *len_bwd = nullptr;                      // Ne, as float
+    int n_hub_segs = 0;
+    int *wh_word = nullptr, *wh_begin = nullptr, *wh_end = nullptr;
+    int *wh_first = nullptr, *wh_count = nullptr;  // Nw
+    float *wh_part = nullptr;                      // n_hub_segs x dq
+};
+
+struct ntn_handle {
+    ntn_config cfg;
+    NtnDims dm;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    DeviceWords w;
+    DeviceBatch b;
+    float *wv_frozen = nullptr;   // Nw x dq (internal word-major), or null
+    float *E = nullptr;           // Ne x Kp
+    float *gE = nullptr;          // Ne x dq
+    float *Waug = nullptr;        // R x Kp x Np   (row p, column n)
+    uint8_t *side = nullptr;      // R (device)
+    uint8_t *h_side = nullptr;    // R (pinned)
+    double *reg_part = nullptr;   // partial sums of theta^2
+    int n_reg_part = 0;
+    // results
+    double *d_out = nullptr;      // [0]=cost, [1]=n_active (as double)
+    double *h_out = nullptr;      // pinned mirror
+    // host-path staging
+    float *d_ref_theta = nullptr, *d_ref_grad = nullptr;   // P (reference order)
+    float *d_int_theta = nullptr, *d_int_grad = nullptr;   // Pint
+    float *h_stage = nullptr;     // pinned, P floats
+    int launches = 0;
+    int gemm_path_active = NTN_GEMM_SIMT;
+    bool profiling = false;
+    cudaEvent_t ev[NTN_NUM_PHASES + 1] = {};
+    float phase_ms[NTN_NUM_PHASES] = {};
+    void *tc = nullptr;           // tcgen05 path state (gemm_tcgen05.cu)
+};
+
+// ---- kernel launchers (ntn_kernels.cu) ---------------------------------------------------
+void ntn_launch_entity_build(ntn_handle* h, const float* wvt);
+void ntn_launch_w_prep(ntn_handle* h, const float* theta);
+void ntn_launch_gemm_fwd_simt(ntn_handle* h);
+void ntn_launch_score(ntn_handle* h, const float* theta);
+void ntn_launch_gemm_dw_simt(ntn_handle* h);
+void ntn_launch_gemm_ge_simt(ntn_handle* h);
+void ntn_launch_entity_pull(ntn_handle* h);
+void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad);
+void ntn_launch_finalize(ntn_handle* h, const float* theta, float* grad);
+void ntn_launch_to_internal(ntn_handle* h, const float* d_ref, float* d_int);
+void ntn_launch_from_internal(ntn_handle* h, const float* d_int, float* d_ref);
+void ntn_launch_transpose_wv_host_layout(ntn_handle* h, const float* d_wv_ref /* d x Nw */, float* d_wvt);
+void ntn_launch_score_eval(ntn_handle* h, const float* theta, const int* e1, const int* rel, const int* e2,
+                           int64_t n, int mode, double* out);

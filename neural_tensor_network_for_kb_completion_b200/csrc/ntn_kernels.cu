@@ -1,0 +1,932 @@
+// Hand-written sm_100a kernels of the NTN cost+gradient path: everything except the tcgen05
+// contractions (gemm_tcgen05.cu).  Each kernel cites the reference statements it replaces
+// (/root/reference/src/NTN.java unless another file is named) and DESIGN.md gives its roofline.
+//
+// Formulation (SURVEY.md App. A "dedupe identity"): for a unique training triple u
+// of relation r with anchor entity A (e1 if the relation corrupts the tail, NTN.java:146-150,
+// else e2) and other entity O:
+//   T'_u[s,:] = [E_A | 1] * Waug_r  = W_r[s]-contracted anchor row + the V half that multiplies
+//               the non-anchor side; beta_u[s] = anchor-side V term + b      (NTN.java:163-197)
+//   pre+ = T'_u[s,:].E_O + beta,  pre-_c = T'_u[s,:].E_{e3_c} + beta          (per corrupt column c)
+//   M_u[s,:] = a_{u,s} E_O + sum_c c_{c,s} E_{e3_c},  coefsum = a + sum_c c   (NTN.java:280-388)
+//   dWaug_r = [E_A | 1]^T [M | coefsum]  -> dW, dV, db                        (NTN.java:301-349)
+//   GA_u = [M | coefsum] Waug_r^T        -> gradient of the anchor entity     (NTN.java:352-388)
+//   gE[O] += sum_s a T',  gE[e3_c] += sum_s c_c T'                            (Util.java:74-98)
+#include <assert.h>
+#include <math.h>
+#include <stdio.h>
+
+#include "ntn_internal.h"
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
+    acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y);
+    acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
+}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+template <int ACT> __device__ __forceinline__ float act_fn(float x) {
+    if (ACT == NTN_ACT_TANH) return tanhf(x);               // NTN.java:200-201
+    return 1.0f / (1.0f + expf(-x));
+}
+template <int ACT> __device__ __forceinline__ float act_diff(float z) {   // NTN.java:744-759
+    if (ACT == NTN_ACT_TANH) return 1.0f - z * z;
+    return z * (1.0f - z);
+}
+
+// ==========================================================================================
+// K1  entity build: segmented mean of word rows               DataFactory.java:393-437
+//     E[n, 0:d] = (1/cnt) sum_j WVt[word_j(n), :],  E[n, d] = 1,  E[n, d+1:Kp] = 0
+//     One warp per entity, lanes over float4 chunks.  HBM-bound: reads nnz*dq, writes Ne*Kp.
+// ==========================================================================================
+__global__ void __launch_bounds__(256) k_entity_build(const float* __restrict__ wvt, const int* __restrict__ off,
+                                                      const int* __restrict__ idx, float* __restrict__ E,
+                                                      int Ne, int d, int dq, int Kp) {
+    int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (n >= Ne) return;
+    int j0 = __ldg(off + n), j1 = __ldg(off + n + 1);
+    int cnt = j1 - j0;
+    for (int c = lane; c * 4 < Kp; c += 32) {
+        float4 acc = zero4();
+        if (c * 4 < dq) {
+            for (int j = j0; j < j1; ++j) {                          // word order, like :410-418
+                float4 v = ldg4(wvt + (size_t)__ldg(idx + j) * dq + c * 4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            if (cnt > 1) {                                           // :420 (single word: copy, :429)
+                float fc = (float)cnt;
+                acc.x /= fc; acc.y /= fc; acc.z /= fc; acc.w /= fc;
+            }
+        }
+        float* a = reinterpret_cast<float*>(&acc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int p = c * 4 + i;
+            if (p == d) a[i] = 1.0f; else if (p > d) a[i] = 0.0f;
+        }
+        *reinterpret_cast<float4*>(E + (size_t)n * Kp + c * 4) = acc;
+    }
+}
+
+// ==========================================================================================
+// K2  Waug_r [Kp x Np] from theta and this evaluation's corrupt sides.
+//     tail (side=1):  Waug[p][s*dq+q] = W_r[s][p][q]   Waug[d][s*dq+q] = V_r[d+q][s]
+//                     Waug[p][k*dq+s] = V_r[p][s]      Waug[d][k*dq+s] = b_r[s]
+//     head (side=0):  Waug[p][s*dq+q] = W_r[s][q][p]   Waug[d][s*dq+q] = V_r[q][s]
+//                     Waug[p][k*dq+s] = V_r[d+p][s]    Waug[d][k*dq+s] = b_r[s]
+//     (replaces the element-wise slice copies of NTN.java:166-169,376-383)
+// ==========================================================================================
+__global__ void __launch_bounds__(256) k_w_prep(const float* __restrict__ theta, const uint8_t* __restrict__ side,
+                                                float* __restrict__ Waug, NtnDims dm) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = (int64_t)dm.Kp * dm.Np;
+    if (i >= per * dm.R) return;
+    int r = (int)(i / per);
+    int rem = (int)(i - (int64_t)r * per);
+    int p = rem / dm.Np, n = rem - p * dm.Np;
+    int d = dm.d, k = dm.k, dq = dm.dq;
+    bool tail = side[r] != 0;
+    const float* W = theta + dm.oW + (int64_t)r * k * d * d;
+    const float* V = theta + dm.oV + (int64_t)r * 2 * d * k;
+    float v = 0.f;
+    if (n < k * dq) {
+        int s = n / dq, q = n - s * dq;
+        if (q < d) {
+            if (p < d) v = tail ? W[((int64_t)s * d + p) * d + q] : W[((int64_t)s * d + q) * d + p];
+            else if (p == d) v = tail ? V[(d + q) * k + s] : V[q * k + s];
+        }
+    } else if (n < k * dq + k) {
+        int s = n - k * dq;
+        if (p < d) v = tail ? V[p * k + s] : V[(d + p) * k + s];
+        else if (p == d) v = theta[dm.ob + (int64_t)r * k + s];
+    }
+    Waug[i] = v;
+}
+
+// ==========================================================================================
+// SIMT FP32 contractions (the A/B reference path for the tcgen05 kernels; NTN_GEMM_SIMT).
+// 64x64x16 tiles, 256 threads, 4x4 register micro-tile.
+// ==========================================================================================
+#define GBM 64
+#define GBN 64
+#define GBK 16
+#define GPAD 68
+
+struct GemmTables {
+    const int *t_rel, *t_u0, *t_n;      // tile / chunk table
+    const int *u_e1, *u_e2;
+    const uint8_t* side;
+};
+
+__device__ __forceinline__ int anchor_of(const GemmTables& tb, int u, bool tail) {
+    return tail ? __ldg(tb.u_e1 + u) : __ldg(tb.u_e2 + u);
+}
+
+__device__ __forceinline__ void gemm_compute_tile(const float (*As)[GPAD], const float (*Bs)[GPAD], float acc[4][4],
+                                                  int ty, int tx) {
+#pragma unroll
+    for (int kk = 0; kk < GBK; ++kk) {
+        float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+}
+
+// forward: T'[u0+m][n] = sum_p E[anchor(u0+m)][p] * Waug_r[p][n]     (NTN.java:163-197)
+// grid.x = tiles*2 (64-row halves of the 128-row score tile), grid.y = ceil(Np/64)
+__global__ void __launch_bounds__(256) k_gemm_fwd_simt(GemmTables tb, const float* __restrict__ E,
+                                                       const float* __restrict__ Waug, float* __restrict__ T,
+                                                       int Kp, int Np) {
+    __shared__ __align__(16) float As[GBK][GPAD];
+    __shared__ __align__(16) float Bs[GBK][GPAD];
+    int tile = blockIdx.x >> 1, half = blockIdx.x & 1;
+    int r = tb.t_rel[tile], u0 = tb.t_u0[tile] + half * GBM, rows = tb.t_n[tile] - half * GBM;
+    if (rows <= 0) return;
+    if (rows > GBM) rows = GBM;
+    bool tail = tb.side[r] != 0;
+    int n0 = blockIdx.y * GBN;
+    const float* B = Waug + (size_t)r * Kp * Np;
+    int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+    int am = t >> 2, akq = (t & 3) * 4;            // A: k-contiguous rows, gathered
+    int bk = t >> 4, bnq = (t & 15) * 4;           // B: n-contiguous
+    const float* arow = nullptr;
+    if (am < rows) arow = E + (size_t)anchor_of(tb, u0 + am, tail) * Kp;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < Kp; k0 += GBK) {
+        float4 av = zero4(), bv = zero4();
+        if (arow && k0 + akq < Kp) av = ldg4(arow + k0 + akq);
+        if (k0 + bk < Kp && n0 + bnq < Np) bv = ldg4(B + (size_t)(k0 + bk) * Np + n0 + bnq);
+        As[akq + 0][am] = av.x; As[akq + 1][am] = av.y; As[akq + 2][am] = av.z; As[akq + 3][am] = av.w;
+        *reinterpret_cast<float4*>(&Bs[bk][bnq]) = bv;
+        __syncthreads();
+        gemm_compute_tile(As, Bs, acc, ty, tx);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = ty * 4 + i;
+        if (m < rows && n0 + tx * 4 < Np)
+            *reinterpret_cast<float4*>(T + (size_t)(u0 + m) * Np + n0 + tx * 4) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
+// anchor-entity gradient rows: GA[u0+m][p] = sum_n M[u0+m][n] * Waug_r[p][n]   (NTN.java:352-388)
+__global__ void __launch_bounds__(256) k_gemm_ge_simt(GemmTables tb, const float* __restrict__ M,
+                                                      const float* __restrict__ Waug, float* __restrict__ GA,
+                                                      int Kp, int Np) {
+    __shared__ __align__(16) float As[GBK][GPAD];
+    __shared__ __align__(16) float Bs[GBK][GPAD];
+    int tile = blockIdx.x >> 1, half = blockIdx.x & 1;
+    int r = tb.t_rel[tile], u0 = tb.t_u0[tile] + half * GBM, rows = tb.t_n[tile] - half * GBM;
+    if (rows <= 0) return;
+    if (rows > GBM) rows = GBM;
+    int n0 = blockIdx.y * GBN;                     // over p in [0,Kp)
+    const float* B = Waug + (size_t)r * Kp * Np;
+    int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+    int am = t >> 2, akq = (t & 3) * 4;            // A = M rows, k(=n')-contiguous
+    int bn = t >> 2, bkq = (t & 3) * 4;            // B(k=n', n=p) = Waug[p][n'], k-contiguous
+    const float* arow = (am < rows) ? M + (size_t)(u0 + am) * Np : nullptr;
+    const float* brow = (n0 + bn < Kp) ? B + (size_t)(n0 + bn) * Np : nullptr;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < Np; k0 += GBK) {
+        float4 av = zero4(), bv = zero4();
+        if (arow && k0 + akq < Np) av = ldg4(arow + k0 + akq);
+        if (brow && k0 + bkq < Np) bv = ldg4(brow + k0 + bkq);
+        As[akq + 0][am] = av.x; As[akq + 1][am] = av.y; As[akq + 2][am] = av.z; As[akq + 3][am] = av.w;
+        Bs[bkq + 0][bn] = bv.x; Bs[bkq + 1][bn] = bv.y; Bs[bkq + 2][bn] = bv.z; Bs[bkq + 3][bn] = bv.w;
+        __syncthreads();
+        gemm_compute_tile(As, Bs, acc, ty, tx);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = ty * 4 + i;
+        if (m < rows && n0 + tx * 4 < Kp)
+            *reinterpret_cast<float4*>(GA + (size_t)(u0 + m) * Kp + n0 + tx * 4) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
+// dWaug split-K partial: part[chunk][p][n] = sum_{u in chunk} E[anchor(u)][p] * M[u][n]   (NTN.java:301-349)
+// grid.x = chunks, grid.y = ceil(Kp/64) * ceil(Np/64)
+__global__ void __launch_bounds__(256) k_gemm_dw_simt(GemmTables tb, const float* __restrict__ E,
+                                                      const float* __restrict__ M, float* __restrict__ part,
+                                                      int Kp, int Np) {
+    __shared__ __align__(16) float As[GBK][GPAD];
+    __shared__ __align__(16) float Bs[GBK][GPAD];
+    __shared__ int s_anchor[GBK];
+    int ch = blockIdx.x;
+    int r = tb.t_rel[ch], u0 = tb.t_u0[ch], rows = tb.t_n[ch];
+    bool tail = tb.side[r] != 0;
+    int ntn = (Np + GBN - 1) / GBN;
+    int m0 = (blockIdx.y / ntn) * GBM, n0 = (blockIdx.y % ntn) * GBN;
+    int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+    int ak = t >> 4, amq = (t & 15) * 4;           // A(m=p, k=u): m-contiguous, rows gathered over k
+    int bk = t >> 4, bnq = (t & 15) * 4;           // B(k=u, n): n-contiguous
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < rows; k0 += GBK) {
+        if (t < GBK) s_anchor[t] = (k0 + t < rows) ? anchor_of(tb, u0 + k0 + t, tail) : -1;
+        __syncthreads();
+        float4 av = zero4(), bv = zero4();
+        int an = s_anchor[ak];
+        if (an >= 0 && m0 + amq < Kp) av = ldg4(E + (size_t)an * Kp + m0 + amq);
+        if (k0 + bk < rows && n0 + bnq < Np) bv = ldg4(M + (size_t)(u0 + k0 + bk) * Np + n0 + bnq);
+        *reinterpret_cast<float4*>(&As[ak][amq]) = av;
+        *reinterpret_cast<float4*>(&Bs[bk][bnq]) = bv;
+        __syncthreads();
+        gemm_compute_tile(As, Bs, acc, ty, tx);
+        __syncthreads();
+    }
+    float* C = part + (size_t)ch * Kp * Np;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m < Kp && n0 + tx * 4 < Np)
+            *reinterpret_cast<float4*>(C + (size_t)m * Np + n0 + tx * 4) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
+// ==========================================================================================
+// K4  score / hinge / backward-coefficient kernel (the fused epilogue of the forward contraction)
+//     NTN.java:200-222 (activation, u-dot, hinge, cost, update), :272-289 (dU, temp, db),
+//     and the column-wise halves of :301-388 folded into M.
+//     One block per 128-row tile of one relation; one warp per unique triple at a time; lanes over
+//     float4 chunks of the d-vector.  Gathers of E rows are L2 hits (E is 30 MB vs 126 MB L2).
+// ==========================================================================================
+struct ScoreArgs {
+    const float *theta, *E, *T;
+    float *M, *acoef, *ccoef;
+    const int *t_rel, *t_u0, *t_n, *u_e1, *u_e2, *c_off, *c_e3;
+    const uint8_t* side;
+    double* tp_cost; int* tp_nact; float* tp_dU;
+    int d, dq, Kp, Np;
+    int64_t oU;
+};
+
+template <int KS, int CH, int ACT>
+__global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
+    __shared__ double s_cost[8];
+    __shared__ int s_nact[8];
+    __shared__ float s_dU[8][KS];
+    const int tile = blockIdx.x;
+    const int r = a.t_rel[tile], u0 = a.t_u0[tile], rows = a.t_n[tile];
+    const bool tail = a.side[r] != 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dq = a.dq, d = a.d;
+    float U[KS];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) U[s] = __ldg(a.theta + a.oU + (int64_t)r * KS + s);
+    // per-lane chunk validity and tail mask (elements >= d inside the last float4 are dropped)
+    bool cv[CH]; float4 cm[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        int p = (lane + 32 * c) * 4;
+        cv[c] = p < dq;
+        cm[c] = make_float4(p < d ? 1.f : 0.f, p + 1 < d ? 1.f : 0.f, p + 2 < d ? 1.f : 0.f, p + 3 < d ? 1.f : 0.f);
+    }
+    double cost_w = 0.0; int nact_w = 0; float dU_w[KS];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) dU_w[s] = 0.f;
+
+    for (int i = warp; i < rows; i += 8) {
+        const int u = u0 + i;
+        const int other = tail ? __ldg(a.u_e2 + u) : __ldg(a.u_e1 + u);
+        const float* Trow = a.T + (size_t)u * a.Np;
+        float4 t[KS][CH]; float beta[KS];
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) t[s][c] = cv[c] ? ldg4(Trow + s * dq + (lane + 32 * c) * 4) : zero4();
+            beta[s] = __ldg(Trow + KS * dq + s);
+        }
+        float4 eo[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            eo[c] = cv[c] ? ldg4(a.E + (size_t)other * a.Kp + (lane + 32 * c) * 4) : zero4();
+            eo[c].x *= cm[c].x; eo[c].y *= cm[c].y; eo[c].z *= cm[c].z; eo[c].w *= cm[c].w;
+        }
+        // positive column (shared by all corrupt copies of this triple)
+        float zp[KS], tp[KS], sp = 0.f;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc += dot4(t[s][c], eo[c]);
+            float pre = warp_sum(acc) + beta[s];
+            zp[s] = act_fn<ACT>(pre);
+            sp = fmaf(U[s], zp[s], sp);                               // :204
+            tp[s] = act_diff<ACT>(zp[s]) * U[s];                      // :280
+        }
+        float4 Macc[KS][CH]; float csum[KS];
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            csum[s] = 0.f;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) Macc[s][c] = zero4();
+        }
+        int cnt = 0;
+        const int c0 = __ldg(a.c_off + u), c1 = __ldg(a.c_off + u + 1);
+        for (int col = c0; col < c1; ++col) {
+            const int e3 = __ldg(a.c_e3 + col);
+            float4 ev[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                ev[c] = cv[c] ? ldg4(a.E + (size_t)e3 * a.Kp + (lane + 32 * c) * 4) : zero4();
+                ev[c].x *= cm[c].x; ev[c].y *= cm[c].y; ev[c].z *= cm[c].z; ev[c].w *= cm[c].w;
+            }
+            float zn[KS], sn = 0.f;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) acc += dot4(t[s][c], ev[c]);
+                float pre = warp_sum(acc) + beta[s];
+                zn[s] = act_fn<ACT>(pre);
+                sn = fmaf(U[s], zn[s], sn);                           // :205
+            }
+            const bool active = (sp + 1.0f) > sn;                     // :213 (strict, FP32)
+            float cc[KS];
+            if (active) {
+                cost_w += (double)((sp - sn) + 1.0f);                 // :221
+                ++nact_w; ++cnt;                                      // :222
+#pragma unroll
+                for (int s = 0; s < KS; ++s) {
+                    dU_w[s] += zp[s] - zn[s];                         // :273
+                    cc[s] = -act_diff<ACT>(zn[s]) * U[s];             // :281
+                    csum[s] += cc[s];
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) fma4(Macc[s][c], cc[s], ev[c]);
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < KS; ++s) cc[s] = 0.f;
+            }
+            if (lane < KS) {
+                float v = 0.f;
+#pragma unroll
+                for (int s = 0; s < KS; ++s) if (s == lane) v = cc[s];
+                a.ccoef[(size_t)col * KS + lane] = v;
+            }
+        }
+        float* Mrow = a.M + (size_t)u * a.Np;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            float as = (float)cnt * tp[s];                            // positive side: one per active copy
+            csum[s] += as;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                fma4(Macc[s][c], as, eo[c]);
+                if (cv[c]) *reinterpret_cast<float4*>(Mrow + s * dq + (lane + 32 * c) * 4) = Macc[s][c];
+            }
+            if (lane == 0) a.acoef[(size_t)u * KS + s] = as;
+        }
+        // coefficient sums ride in the k slots after the slices; zero the rest of the row
+        for (int n = KS * dq + lane; n < a.Np; n += 32) {
+            float v = 0.f;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) if (n == KS * dq + s) v = csum[s];
+            Mrow[n] = v;
+        }
+    }
+    if (lane == 0) {
+        s_cost[warp] = cost_w; s_nact[warp] = nact_w;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) s_dU[warp][s] = dU_w[s];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                           // fixed order: deterministic
+        double c = 0.0; int n = 0;
+        for (int w = 0; w < 8; ++w) { c += s_cost[w]; n += s_nact[w]; }
+        a.tp_cost[tile] = c; a.tp_nact[tile] = n;
+    }
+    if (threadIdx.x < KS) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += s_dU[w][threadIdx.x];
+        a.tp_dU[(size_t)tile * KS + threadIdx.x] = v;
+    }
+}
+
+// ==========================================================================================
+// K7  entity-gradient pull (replaces the 8*k*R dense scatter products of Util.java:74-98 and the
+//     dense adds of NTN.java:372,388).  One warp per entity walks its incident list in a fixed
+//     order -- no float atomics, bit-reproducible.
+// ==========================================================================================
+struct PullArgs {
+    const float *T, *GA, *acoef, *ccoef;
+    const int *u_rel, *inc_off, *inc_u, *inc_code;
+    const uint8_t* side;
+    float* gE;
+    const int *eh_first, *eh_count, *eh_ent, *eh_begin, *eh_end;
+    float* eh_part;
+    int Ne, dq, Kp, Np, n_segs;
+};
+
+template <int KS, int CH>
+__device__ __forceinline__ void pull_range(const PullArgs& a, int j0, int j1, int lane, const bool cv[CH], float4 acc[CH]) {
+    for (int j = j0; j < j1; ++j) {
+        const int u = __ldg(a.inc_u + j), code = __ldg(a.inc_code + j);
+        const bool tail = a.side[__ldg(a.u_rel + u)] != 0;
+        const bool anchor = (code == -1 && tail) || (code == -2 && !tail);
+        if (anchor) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                if (cv[c]) {
+                    float4 v = ldg4(a.GA + (size_t)u * a.Kp + (lane + 32 * c) * 4);
+                    acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+                }
+        } else {
+            const float* cf = (code >= 0) ? a.ccoef + (size_t)code * KS : a.acoef + (size_t)u * KS;
+            float co[KS]; bool any = false;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) { co[s] = __ldg(cf + s); any |= (co[s] != 0.f); }
+            if (!any) continue;                                       // inactive column (NTN.java:229-239)
+            const float* Trow = a.T + (size_t)u * a.Np;
+#pragma unroll
+            for (int s = 0; s < KS; ++s)
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                    if (cv[c]) fma4(acc[c], co[s], ldg4(Trow + s * a.dq + (lane + 32 * c) * 4));
+        }
+    }
+}
+
+template <int KS, int CH>
+__global__ void __launch_bounds__(256) k_entity_pull_hub(PullArgs a) {
+    int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (seg >= a.n_segs) return;
+    bool cv[CH]; float4 acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { cv[c] = (lane + 32 * c) * 4 < a.dq; acc[c] = zero4(); }
+    pull_range<KS, CH>(a, a.eh_begin[seg], a.eh_end[seg], lane, cv, acc);
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+        if (cv[c]) *reinterpret_cast<float4*>(a.eh_part + (size_t)seg * a.dq + (lane + 32 * c) * 4) = acc[c];
+}
+
+template <int KS, int CH>
+__global__ void __launch_bounds__(256) k_entity_pull(PullArgs a) {
+    int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (n >= a.Ne) return;
+    bool cv[CH]; float4 acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { cv[c] = (lane + 32 * c) * 4 < a.dq; acc[c] = zero4(); }
+    int nseg = a.eh_count ? a.eh_count[n] : 0;
+    if (nseg == 0) {
+        pull_range<KS, CH>(a, __ldg(a.inc_off + n), __ldg(a.inc_off + n + 1), lane, cv, acc);
+    } else {
+        int s0 = a.eh_first[n];
+        for (int sg = s0; sg < s0 + nseg; ++sg)
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                if (cv[c]) {
+                    float4 v = ldg4(a.eh_part + (size_t)sg * a.dq + (lane + 32 * c) * 4);
+                    acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+                }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+        if (cv[c]) *reinterpret_cast<float4*>(a.gE + (size_t)n * a.dq + (lane + 32 * c) * 4) = acc[c];
+}
+
+// ==========================================================================================
+// K8  word-gradient pull + regulariser for the word block          NTN.java:411-430,437-438
+//     gWV[w] = (1/B) sum_{n : w in words(n)} gE[n]/len_n  + lambda*theta_w ;  reg += theta_w^2
+//     Sorted-segment pull over the inverse (word -> entity) CSR: deterministic, no float atomics.
+//     Hub words (e.g. "unknown") are pre-reduced in NTN_HUB_SEG segments by k_word_pull_hub.
+// ==========================================================================================
+struct WordArgs {
+    const float *gE, *len_bwd, *theta;
+    float* grad;
+    const int *w_off, *w_ent;
+    const int *wh_first, *wh_count, *wh_begin, *wh_end;
+    float* wh_part;
+    double* reg_part;
+    int Nw, dq, n_segs;
+    int64_t oWV;
+    float inv_B, lam;
+};
+
+template <int CH>
+__device__ __forceinline__ void word_range(const WordArgs& a, int j0, int j1, int lane, const bool cv[CH], float4 acc[CH]) {
+    for (int j = j0; j < j1; ++j) {
+        const int n = __ldg(a.w_ent + j);
+        const float len = __ldg(a.len_bwd + n);
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+            if (cv[c]) {
+                float4 v = ldg4(a.gE + (size_t)n * a.dq + (lane + 32 * c) * 4);
+                acc[c].x += v.x / len; acc[c].y += v.y / len; acc[c].z += v.z / len; acc[c].w += v.w / len;   // :420
+            }
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_word_pull_hub(WordArgs a) {
+    int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (seg >= a.n_segs) return;
+    bool cv[CH]; float4 acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { cv[c] = (lane + 32 * c) * 4 < a.dq; acc[c] = zero4(); }
+    word_range<CH>(a, a.wh_begin[seg], a.wh_end[seg], lane, cv, acc);
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+        if (cv[c]) *reinterpret_cast<float4*>(a.wh_part + (size_t)seg * a.dq + (lane + 32 * c) * 4) = acc[c];
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_word_pull(WordArgs a) {
+    __shared__ double s_reg[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + warp;
+    float reg = 0.f;
+    if (w < a.Nw) {
+        bool cv[CH]; float4 acc[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { cv[c] = (lane + 32 * c) * 4 < a.dq; acc[c] = zero4(); }
+        int nseg = a.wh_count ? a.wh_count[w] : 0;
+        if (nseg == 0) {
+            word_range<CH>(a, __ldg(a.w_off + w), __ldg(a.w_off + w + 1), lane, cv, acc);
+        } else {
+            int s0 = a.wh_first[w];
+            for (int sg = s0; sg < s0 + nseg; ++sg)
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                    if (cv[c]) {
+                        float4 v = ldg4(a.wh_part + (size_t)sg * a.dq + (lane + 32 * c) * 4);
+                        acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+                    }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+            if (cv[c]) {
+                size_t o = (size_t)a.oWV + (size_t)w * a.dq + (lane + 32 * c) * 4;
+                float4 th = ldg4(a.theta + o);
+                float4 g = make_float4(fmaf(a.lam, th.x, acc[c].x * a.inv_B), fmaf(a.lam, th.y, acc[c].y * a.inv_B),
+                                       fmaf(a.lam, th.z, acc[c].z * a.inv_B), fmaf(a.lam, th.w, acc[c].w * a.inv_B));
+                *reinterpret_cast<float4*>(a.grad + o) = g;          // :429,438
+                reg += dot4(th, th);                                 // :437
+            }
+    }
+    reg = warp_sum(reg);
+    if (lane == 0) s_reg[warp] = (double)reg;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += s_reg[i];
+        a.reg_part[blockIdx.x] = s;
+    }
+}
+
+// ==========================================================================================
+// K9  finalize the W, V, b, U blocks: fixed-order reduction of the dWaug split-K partials and of the
+//     tile partials, /batchSize, + lambda*theta, regulariser partial    NTN.java:398-401,433-438
+// ==========================================================================================
+struct FinArgs {
+    const float *theta, *dWpart, *tp_dU;
+    float* grad;
+    const int *relch_off, *reltile_off;
+    const uint8_t* side;
+    double* reg_part;      // [gridDim.x] slots after the word-pull slots
+    NtnDims dm;
+    float inv_B, lam;
+};
+
+__global__ void __launch_bounds__(256) k_finalize_small(FinArgs a) {
+    __shared__ double s_reg[8];
+    const NtnDims& dm = a.dm;
+    const int d = dm.d, k = dm.k, dq = dm.dq;
+    const int64_t per = (int64_t)dm.Kp * dm.Np;
+    const int64_t nW = per * dm.R, nU = (int64_t)dm.R * k;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float th2 = 0.f;
+    if (i < nW) {
+        int r = (int)(i / per);
+        int rem = (int)(i - (int64_t)r * per);
+        int p = rem / dm.Np, n = rem - p * dm.Np;
+        bool tail = a.side[r] != 0;
+        int64_t idx = -1;
+        if (n < k * dq) {
+            int s = n / dq, q = n - s * dq;
+            if (q < d) {
+                if (p < d) idx = dm.oW + (((int64_t)r * k + s) * d + (tail ? p : q)) * d + (tail ? q : p);
+                else if (p == d) idx = dm.oV + ((int64_t)r * 2 * d + (tail ? d + q : q)) * k + s;
+            }
+        } else if (n < k * dq + k) {
+            int s = n - k * dq;
+            if (p < d) idx = dm.oV + ((int64_t)r * 2 * d + (tail ? p : d + p)) * k + s;
+            else if (p == d) idx = dm.ob + (int64_t)r * k + s;
+        }
+        if (idx >= 0) {
+            float sum = 0.f;
+            for (int c = a.relch_off[r]; c < a.relch_off[r + 1]; ++c) sum += __ldg(a.dWpart + (size_t)c * per + rem);
+            float th = a.theta[idx];
+            a.grad[idx] = fmaf(a.lam, th, sum * a.inv_B);
+            th2 = th * th;
+        }
+    } else if (i < nW + nU) {
+        int j = (int)(i - nW);
+        int r = j / k, s = j - r * k;
+        float sum = 0.f;
+        for (int t = a.reltile_off[r]; t < a.reltile_off[r + 1]; ++t) sum += a.tp_dU[(size_t)t * k + s];
+        int64_t idx = dm.oU + j;
+        float th = a.theta[idx];
+        a.grad[idx] = fmaf(a.lam, th, sum * a.inv_B);
+        th2 = th * th;
+    } else if (i < nW + nU + (dm.oWVint - (dm.oU + nU))) {
+        a.grad[dm.oU + nU + (i - nW - nU)] = 0.f;                     // alignment padding before the word block
+    }
+    float s = warp_sum(th2);
+    if ((threadIdx.x & 31) == 0) s_reg[threadIdx.x >> 5] = (double)s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_reg[w];
+        a.reg_part[blockIdx.x] = t;
+    }
+}
+
+// single block: cost = sum(tile costs)/B + 0.5*lambda*sum(theta^2)      NTN.java:430,437
+__global__ void __launch_bounds__(256) k_final_reduce(const double* __restrict__ tp_cost, const int* __restrict__ tp_nact,
+                                                      int ntiles, const double* __restrict__ reg_part, int nreg,
+                                                      double inv_B, double half_lam, double* __restrict__ out) {
+    __shared__ double s_a[256], s_b[256], s_c[256];
+    double c = 0.0, n = 0.0, r = 0.0;
+    for (int i = threadIdx.x; i < ntiles; i += 256) { c += tp_cost[i]; n += (double)tp_nact[i]; }
+    for (int i = threadIdx.x; i < nreg; i += 256) r += reg_part[i];
+    s_a[threadIdx.x] = c; s_b[threadIdx.x] = n; s_c[threadIdx.x] = r;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_a[threadIdx.x] += s_a[threadIdx.x + o];
+            s_b[threadIdx.x] += s_b[threadIdx.x + o];
+            s_c[threadIdx.x] += s_c[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = s_a[0] * inv_B + half_lam * s_c[0];
+        out[1] = s_b[0];
+        out[2] = s_a[0] * inv_B;       // data term alone
+        out[3] = s_c[0];               // sum theta^2
+    }
+}
+
+// ==========================================================================================
+// layout conversion between the reference flattening (NTN.java:450-526; word block d x Nw) and the
+// internal one (word block Nw x dq).  32x32 shared-memory transposes, coalesced on both sides.
+// ==========================================================================================
+__global__ void __launch_bounds__(256) k_copy_small(const float* __restrict__ src, float* __restrict__ dst, int64_t n,
+                                                    int64_t pad_to) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+    else if (i < pad_to) dst[i] = 0.f;
+}
+// ref [d][Nw] -> int [Nw][dq]
+__global__ void __launch_bounds__(256) k_wv_to_internal(const float* __restrict__ src, float* __restrict__ dst, int d, int Nw, int dq) {
+    __shared__ float tile[32][33];
+    int w0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        int p = p0 + j, w = w0 + tx;
+        tile[j][tx] = (p < d && w < Nw) ? src[(size_t)p * Nw + w] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        int w = w0 + j, p = p0 + tx;
+        if (w < Nw && p < dq) dst[(size_t)w * dq + p] = tile[tx][j];
+    }
+}
+// int [Nw][dq] -> ref [d][Nw]
+__global__ void __launch_bounds__(256) k_wv_from_internal(const float* __restrict__ src, float* __restrict__ dst, int d, int Nw, int dq) {
+    __shared__ float tile[32][33];
+    int w0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        int w = w0 + j, p = p0 + tx;
+        tile[j][tx] = (w < Nw && p < dq) ? src[(size_t)w * dq + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        int p = p0 + j, w = w0 + tx;
+        if (p < d && w < Nw) dst[(size_t)p * Nw + w] = tile[tx][j];
+    }
+}
+
+// ==========================================================================================
+// eval-side scoring ("next" row N1)             NTN.calculateScoreOfaTripple, NTN.java:713-736
+// one warp per triple; FP64 accumulation is not needed: the reference is FP32.
+// ==========================================================================================
+template <int ACT>
+__global__ void __launch_bounds__(256) k_score_eval(const float* __restrict__ theta, const float* __restrict__ E,
+                                                    const int* __restrict__ e1, const int* __restrict__ rel,
+                                                    const int* __restrict__ e2, int64_t n, int mode,
+                                                    double* __restrict__ out, NtnDims dm) {
+    int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (j >= n) return;
+    const int d = dm.d, k = dm.k;
+    const int r = rel[j];
+    const float* a = E + (size_t)e1[j] * dm.Kp;
+    const float* c = E + (size_t)e2[j] * dm.Kp;
+    float total = 0.f;
+    for (int s = 0; s < k; ++s) {
+        const float* W = theta + dm.oW + ((int64_t)r * k + s) * d * d;
+        const float* V = theta + dm.oV + (int64_t)r * 2 * d * k;
+        float bil = 0.f, lin = 0.f;
+        for (int p = lane; p < d; p += 32) {
+            float wc = 0.f;
+            for (int q = 0; q < d; ++q) wc = fmaf(W[(size_t)p * d + q], c[q], wc);    // :727
+            bil = fmaf(a[p], wc, bil);                                                // :728
+            lin = fmaf(V[p * k + s], a[p], lin);                                      // :729
+            lin = fmaf(V[(d + p) * k + s], c[p], lin);
+        }
+        bil = warp_sum(bil); lin = warp_sum(lin);
+        float u = theta[dm.oU + (int64_t)r * k + s], b = theta[dm.ob + (int64_t)r * k + s];
+        if (mode == NTN_SCORE_REFERENCE_EVAL) total += u * bil + lin + b;             // :730 (no activation)
+        else total += u * act_fn<ACT>(bil + lin + b);
+    }
+    if (lane == 0) out[j] = (double)total;
+}
+
+// ==========================================================================================
+// launchers
+// ==========================================================================================
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+void ntn_launch_entity_build(ntn_handle* h, const float* wvt) {
+    const NtnDims& dm = h->dm;
+    k_entity_build<<<cdiv((int64_t)dm.Ne * 32, 256), 256, 0, h->stream>>>(wvt, h->w.fwd_off, h->w.fwd_idx, h->E, dm.Ne,
+                                                                          dm.d, dm.dq, dm.Kp);
+    h->launches++;
+}
+
+void ntn_launch_w_prep(ntn_handle* h, const float* theta) {
+    const NtnDims& dm = h->dm;
+    int64_t n = (int64_t)dm.R * dm.Kp * dm.Np;
+    k_w_prep<<<cdiv(n, 256), 256, 0, h->stream>>>(theta, h->side, h->Waug, dm);
+    h->launches++;
+}
+
+static GemmTables tile_tables(ntn_handle* h) {
+    return GemmTables{h->b.t_rel, h->b.t_u0, h->b.t_n, h->b.u_e1, h->b.u_e2, h->side};
+}
+
+void ntn_launch_gemm_fwd_simt(ntn_handle* h) {
+    const NtnDims& dm = h->dm;
+    if (h->b.ntiles == 0) return;
+    dim3 g(h->b.ntiles * 2, cdiv(dm.Np, GBN));
+    k_gemm_fwd_simt<<<g, 256, 0, h->stream>>>(tile_tables(h), h->E, h->Waug, h->b.T, dm.Kp, dm.Np);
+    h->launches++;
+}
+
+void ntn_launch_gemm_ge_simt(ntn_handle* h) {
+    const NtnDims& dm = h->dm;
+    if (h->b.ntiles == 0) return;
+    dim3 g(h->b.ntiles * 2, cdiv(dm.Kp, GBN));
+    k_gemm_ge_simt<<<g, 256, 0, h->stream>>>(tile_tables(h), h->b.M, h->Waug, h->b.GA, dm.Kp, dm.Np);
+    h->launches++;
+}
+
+void ntn_launch_gemm_dw_simt(ntn_handle* h) {
+    const NtnDims& dm = h->dm;
+    if (h->b.nchunks == 0) return;
+    GemmTables tb{h->b.ch_rel, h->b.ch_u0, h->b.ch_n, h->b.u_e1, h->b.u_e2, h->side};
+    dim3 g(h->b.nchunks, cdiv(dm.Kp, GBM) * cdiv(dm.Np, GBN));
+    k_gemm_dw_simt<<<g, 256, 0, h->stream>>>(tb, h->E, h->b.M, h->b.dWpart, dm.Kp, dm.Np);
+    h->launches++;
+}
+
+#define DISPATCH_KS(KSv, ...)                                              \
+    switch (KSv) {                                                         \
+        case 1: { constexpr int KS = 1; __VA_ARGS__; } break;              \
+        case 2: { constexpr int KS = 2; __VA_ARGS__; } break;              \
+        case 3: { constexpr int KS = 3; __VA_ARGS__; } break;              \
+        case 4: { constexpr int KS = 4; __VA_ARGS__; } break;              \
+        case 5: { constexpr int KS = 5; __VA_ARGS__; } break;              \
+        case 6: { constexpr int KS = 6; __VA_ARGS__; } break;              \
+        case 7: { constexpr int KS = 7; __VA_ARGS__; } break;              \
+        default: { constexpr int KS = 8; __VA_ARGS__; } break;             \
+    }
+#define DISPATCH_CH(CHv, ...)                                              \
+    if ((CHv) <= 1) { constexpr int CH = 1; __VA_ARGS__; } else { constexpr int CH = 2; __VA_ARGS__; }
+
+void ntn_launch_score(ntn_handle* h, const float* theta) {
+    const NtnDims& dm = h->dm;
+    if (h->b.ntiles == 0) return;
+    ScoreArgs a{theta, h->E, h->b.T, h->b.M, h->b.acoef, h->b.ccoef, h->b.t_rel, h->b.t_u0, h->b.t_n,
+                h->b.u_e1, h->b.u_e2, h->b.c_off, h->b.c_e3, h->side, h->b.tp_cost, h->b.tp_nact, h->b.tp_dU,
+                dm.d, dm.dq, dm.Kp, dm.Np, dm.oU};
+    int ch = cdiv(dm.dq / 4, 32);
+    const bool tanh_act = h->cfg.activation == NTN_ACT_TANH;
+    DISPATCH_KS(dm.k, DISPATCH_CH(ch, {
+        if (tanh_act) k_score<KS, CH, NTN_ACT_TANH><<<h->b.ntiles, 256, 0, h->stream>>>(a);
+        else k_score<KS, CH, NTN_ACT_SIGMOID><<<h->b.ntiles, 256, 0, h->stream>>>(a);
+    }));
+    h->launches++;
+}
+
+void ntn_launch_entity_pull(ntn_handle* h) {
+    const NtnDims& dm = h->dm;
+    const DeviceBatch& b = h->b;
+    PullArgs a{b.T, b.GA, b.acoef, b.ccoef, b.u_rel, b.inc_off, b.inc_u, b.inc_code, h->side, h->gE,
+               b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
+               b.eh_ent, b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.n_ent_hub_segs};
+    int ch = cdiv(dm.dq / 4, 32);
+    DISPATCH_KS(dm.k, DISPATCH_CH(ch, {
+        if (b.n_ent_hub_segs) {
+            k_entity_pull_hub<KS, CH><<<cdiv((int64_t)b.n_ent_hub_segs * 32, 256), 256, 0, h->stream>>>(a);
+            h->launches++;
+        }
+        k_entity_pull<KS, CH><<<cdiv((int64_t)dm.Ne * 32, 256), 256, 0, h->stream>>>(a);
+    }));
+    h->launches++;
+}
+
+static int word_pull_blocks(const NtnDims& dm) { return cdiv(dm.Nw, 8); }
+
+void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad) {
+    const NtnDims& dm = h->dm;
+    const DeviceWords& w = h->w;
+    WordArgs a{h->gE, w.len_bwd, theta, grad, w.w_off, w.w_ent,
+               w.n_hub_segs ? w.wh_first : nullptr, w.n_hub_segs ? w.wh_count : nullptr, w.wh_begin, w.wh_end,
+               w.wh_part, h->reg_part, dm.Nw, dm.dq, w.n_hub_segs, dm.oWVint,
+               1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale};
+    int ch = cdiv(dm.dq / 4, 32);
+    DISPATCH_CH(ch, {
+        if (w.n_hub_segs) {
+            k_word_pull_hub<CH><<<cdiv((int64_t)w.n_hub_segs * 32, 256), 256, 0, h->stream>>>(a);
+            h->launches++;
+        }
+        k_word_pull<CH><<<word_pull_blocks(dm), 256, 0, h->stream>>>(a);
+    });
+    h->launches++;
+}
+
+int ntn_reg_part_count(const NtnDims& dm) {
+    int64_t nsmall = (int64_t)dm.R * dm.Kp * dm.Np + (int64_t)dm.R * dm.k + 4;
+    return word_pull_blocks(dm) + cdiv(nsmall, 256);
+}
+
+void ntn_launch_finalize(ntn_handle* h, const float* theta, float* grad) {
+    const NtnDims& dm = h->dm;
+    const DeviceBatch& b = h->b;
+    int64_t nsmall = (int64_t)dm.R * dm.Kp * dm.Np + (int64_t)dm.R * dm.k + 4;
+    int nb = cdiv(nsmall, 256);
+    int wb = word_pull_blocks(dm);
+    FinArgs a{theta, b.dWpart, b.tp_dU, grad, b.relch_off, b.reltile_off, h->side, h->reg_part + wb, dm,
+              1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale};
+    k_finalize_small<<<nb, 256, 0, h->stream>>>(a);
+    double lam = (double)h->cfg.lambda * (double)h->cfg.reg_scale;
+    k_final_reduce<<<1, 256, 0, h->stream>>>(b.tp_cost, b.tp_nact, b.ntiles, h->reg_part, wb + nb,
+                                             1.0 / (double)h->cfg.batch_divisor, 0.5 * lam, h->d_out);
+    h->launches += 2;
+}
+
+void ntn_launch_to_internal(ntn_handle* h, const float* d_ref, float* d_int) {
+    const NtnDims& dm = h->dm;
+    k_copy_small<<<cdiv(dm.oWVint, 256), 256, 0, h->stream>>>(d_ref, d_int, dm.oWVref, dm.oWVint);
+    dim3 g(cdiv(dm.Nw, 32), cdiv(dm.dq, 32));
+    k_wv_to_internal<<<g, 256, 0, h->stream>>>(d_ref + dm.oWVref, d_int + dm.oWVint, dm.d, dm.Nw, dm.dq);
+    h->launches += 2;
+}
+
+void ntn_launch_from_internal(ntn_handle* h, const float* d_int, float* d_ref) {
+    const NtnDims& dm = h->dm;
+    k_copy_small<<<cdiv(dm.oWVref, 256), 256, 0, h->stream>>>(d_int, d_ref, dm.oWVref, dm.oWVref);
+    dim3 g(cdiv(dm.Nw, 32), cdiv(dm.dq, 32));
+    k_wv_from_internal<<<g, 256, 0, h->stream>>>(d_int + dm.oWVint, d_ref + dm.oWVref, dm.d, dm.Nw, dm.dq);
+    h->launches += 2;
+}
+
+void ntn_launch_transpose_wv_host_layout(ntn_handle* h, const float* d_wv_ref, float* d_wvt) {
+    const NtnDims& dm = h->dm;
+    dim3 g(cdiv(dm.Nw, 32), cdiv(dm.dq, 32));
+    k_wv_to_internal<<<g, 256, 0, h->stream>>>(d_wv_ref, d_wvt, dm.d, dm.Nw, dm.dq);
+}
+
+void ntn_launch_score_eval(ntn_handle* h, const float* theta, const int* e1, const int* rel, const int* e2, int64_t n,
+                           int mode, double* out) {
+    if (n == 0) return;
+    if (h->cfg.activation == NTN_ACT_TANH)
+        k_score_eval<NTN_ACT_TANH><<<cdiv(n * 32, 256), 256, 0, h->stream>>>(theta, h->E, e1, rel, e2, n, mode, out, h->dm);
+    else
+        k_score_eval<NTN_ACT_SIGMOID><<<cdiv(n * 32, 256), 256, 0, h->stream>>>(theta, h->E, e1, rel, e2, n, mode, out, h->dm);
+}
