@@ -146,7 +146,8 @@ int ntn_score(ntn_handle* h, const double* theta, int64_t n,
 /* Kernel launches issued by the last ntn_eval* call, and which contraction path it took. */
 int ntn_last_launch_count(const ntn_handle* h);
 int ntn_active_gemm_path(const ntn_handle* h);
-/* Per-phase device times of the last ntn_eval* (ms), filled only after ntn_set_profiling(h,1).
+/* Mean per-phase device times (ms, CUDA events on the handle's stream) over the evaluations issued
+ * since ntn_set_profiling(h, 1), which also resets the accumulators.
  * names: entity_build, w_prep, gemm_fwd, score, gemm_dw, gemm_ge, entity_pull, word_pull, finalize */
 int ntn_set_profiling(ntn_handle* h, int on);
 int ntn_last_phase_ms(ntn_handle* h, float* ms /* NTN_NUM_PHASES */);

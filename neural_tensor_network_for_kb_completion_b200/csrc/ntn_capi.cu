@@ -117,12 +117,14 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
     CKC(cudaMalloc((void**)&h->gE, (size_t)dm.Ne * dm.dq * sizeof(float)));
     CKC(cudaMalloc((void**)&h->Waug, (size_t)dm.R * dm.Kp * dm.Np * sizeof(float)));
     CKC(cudaMalloc((void**)&h->side, dm.R));
-    CKC(cudaMallocHost((void**)&h->h_side, dm.R));
+    CKC(cudaMallocHost((void**)&h->h_side, (size_t)dm.R * NTN_RING));
+    for (int i = 0; i < NTN_RING; ++i) CKC(cudaEventCreateWithFlags(&h->side_ev[i], cudaEventDisableTiming));
     h->n_reg_part = ntn_reg_part_count(dm);
     CKC(cudaMalloc((void**)&h->reg_part, (size_t)h->n_reg_part * sizeof(double)));
     CKC(cudaMalloc((void**)&h->d_out, 4 * sizeof(double)));
     CKC(cudaMallocHost((void**)&h->h_out, 4 * sizeof(double)));
-    for (int i = 0; i <= NTN_NUM_PHASES; ++i) CKC(cudaEventCreate(&h->ev[i]));
+    for (int s = 0; s < NTN_RING; ++s)
+        for (int i = 0; i <= NTN_NUM_PHASES; ++i) CKC(cudaEventCreate(&h->ev[s][i]));
 #undef CKC
     *out = h;
     return NTN_OK;
@@ -154,7 +156,10 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     if (h->h_side) cudaFreeHost(h->h_side);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_stage) cudaFreeHost(h->h_stage);
-    for (int i = 0; i <= NTN_NUM_PHASES; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int s = 0; s < NTN_RING; ++s) {
+        if (h->side_ev[s]) cudaEventDestroy(h->side_ev[s]);
+        for (int i = 0; i <= NTN_NUM_PHASES; ++i) if (h->ev[s][i]) cudaEventDestroy(h->ev[s][i]);
+    }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -170,7 +175,25 @@ extern "C" int ntn_set_stream(ntn_handle* h, void* s) {
     return NTN_OK;
 }
 extern "C" void* ntn_get_stream(ntn_handle* h) { return h ? (void*)h->stream : nullptr; }
-extern "C" int ntn_set_profiling(ntn_handle* h, int on) { if (!h) return NTN_EINVAL; h->profiling = on != 0; return NTN_OK; }
+// fold the event pairs of ring slot s into the per-phase accumulators (waits for that evaluation)
+static void drain_profile_slot(ntn_handle* h, int s) {
+    if (!h->ev_pending[s]) return;
+    cudaEventSynchronize(h->ev[s][NTN_NUM_PHASES]);
+    for (int i = 0; i < NTN_NUM_PHASES; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[s][i], h->ev[s][i + 1]) == cudaSuccess) h->phase_acc[i] += ms;
+    }
+    h->phase_n++;
+    h->ev_pending[s] = false;
+}
+extern "C" int ntn_set_profiling(ntn_handle* h, int on) {
+    if (!h) return NTN_EINVAL;
+    for (int s = 0; s < NTN_RING; ++s) drain_profile_slot(h, s);
+    h->profiling = on != 0;
+    for (int i = 0; i < NTN_NUM_PHASES; ++i) h->phase_acc[i] = 0.0;
+    h->phase_n = 0;
+    return NTN_OK;
+}
 
 // Split the lists longer than NTN_HUB_SEG into segments (hub words like "unknown", hub entities).
 static void build_hub_segments(const std::vector<int>& off, int nrows, std::vector<int>& seg_row,
@@ -373,13 +396,17 @@ static int eval_internal(ntn_handle* h, const float* d_theta, const uint8_t* cor
     }
     h->launches = 0;
     const bool prof = h->profiling;
+    const int slot = h->ring_pos;
+    h->ring_pos = (slot + 1) % NTN_RING;
     int pe = 0;
-    auto mark = [&]() { if (prof) cudaEventRecord(h->ev[pe++], h->stream); };
-    // h_side is reused across calls: make sure the previous evaluation has consumed it
-    // (it has if the caller synchronised; otherwise this is a no-op wait on our own stream)
-    CK(cudaStreamSynchronize(h->stream));
-    for (int r = 0; r < dm.R; ++r) h->h_side[r] = corrupt_side[r] ? 1 : 0;
-    CK(cudaMemcpyAsync(h->side, h->h_side, dm.R, cudaMemcpyHostToDevice, h->stream));
+    if (prof) drain_profile_slot(h, slot);
+    auto mark = [&]() { if (prof) cudaEventRecord(h->ev[slot][pe++], h->stream); };
+    // pinned ring slot: wait only for the evaluation that used this slot NTN_RING calls ago
+    CK(cudaEventSynchronize(h->side_ev[slot]));
+    uint8_t* hs = h->h_side + (size_t)slot * dm.R;
+    for (int r = 0; r < dm.R; ++r) hs[r] = corrupt_side[r] ? 1 : 0;
+    CK(cudaMemcpyAsync(h->side, hs, dm.R, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->side_ev[slot], h->stream));
     const bool tc = h->gemm_path_active == NTN_GEMM_TCGEN05 && h->b.ntiles > 0;
     int rc;
     mark(); ntn_launch_entity_build(h, wvt);                               // NTN.java:103
@@ -396,6 +423,7 @@ static int eval_internal(ntn_handle* h, const float* d_theta, const uint8_t* cor
     mark(); ntn_launch_word_pull(h, d_theta, d_grad);                      // :411-430
     mark(); ntn_launch_finalize(h, d_theta, d_grad);                       // :398-401,433-438
     mark();
+    if (prof) h->ev_pending[slot] = true;
     CK(cudaMemcpyAsync(h->h_out, h->d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaGetLastError());
     return NTN_OK;
@@ -406,14 +434,13 @@ extern "C" int ntn_last_cost(ntn_handle* h, double* cost, int64_t* n_active) {
     CK(cudaStreamSynchronize(h->stream));
     if (cost) *cost = h->h_out[0];
     if (n_active) *n_active = (int64_t)llround(h->h_out[1]);
-    if (h->profiling)
-        for (int i = 0; i < NTN_NUM_PHASES; ++i) cudaEventElapsedTime(&h->phase_ms[i], h->ev[i], h->ev[i + 1]);
     return NTN_OK;
 }
 
 extern "C" int ntn_last_phase_ms(ntn_handle* h, float* ms) {
     if (!h || !ms) return NTN_EINVAL;
-    for (int i = 0; i < NTN_NUM_PHASES; ++i) ms[i] = h->phase_ms[i];
+    for (int s = 0; s < NTN_RING; ++s) drain_profile_slot(h, s);
+    for (int i = 0; i < NTN_NUM_PHASES; ++i) ms[i] = h->phase_n ? (float)(h->phase_acc[i] / h->phase_n) : 0.f;
     return NTN_OK;
 }
 

@@ -31,6 +31,7 @@ struct NtnDims {
 #define NTN_TILE_ROWS   128      // unique triples per score tile (one relation per tile)
 #define NTN_CHUNK_ROWS  512      // unique triples per dW split-K chunk (one relation per chunk)
 #define NTN_HUB_SEG     256      // incident-list segment length for hub words / hub entities
+#define NTN_RING        8        // in-flight evaluations the host may enqueue without synchronising
 
 struct DeviceBatch {
     int64_t N = 0;               // columns
@@ -93,7 +94,9 @@ struct ntn_handle {
     float *gE = nullptr;          // Ne x dq
     float *Waug = nullptr;        // R x Kp x Np   (row p, column n)
     uint8_t *side = nullptr;      // R (device)
-    uint8_t *h_side = nullptr;    // R (pinned)
+    uint8_t *h_side = nullptr;    // NTN_RING x R (pinned ring, so evaluations can be enqueued back to back)
+    cudaEvent_t side_ev[NTN_RING] = {};
+    int ring_pos = 0;
     double *reg_part = nullptr;   // partial sums of theta^2
     int n_reg_part = 0;
     // results
@@ -106,8 +109,10 @@ struct ntn_handle {
     int launches = 0;
     int gemm_path_active = NTN_GEMM_SIMT;
     bool profiling = false;
-    cudaEvent_t ev[NTN_NUM_PHASES + 1] = {};
-    float phase_ms[NTN_NUM_PHASES] = {};
+    cudaEvent_t ev[NTN_RING][NTN_NUM_PHASES + 1] = {};
+    bool ev_pending[NTN_RING] = {};
+    double phase_acc[NTN_NUM_PHASES] = {};
+    int phase_n = 0;
     void *tc = nullptr;           // tcgen05 path state (gemm_tcgen05.cu)
 };
 
