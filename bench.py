@@ -211,7 +211,8 @@ def main():
     else:
         torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # everything (kernels, NCCL, timing events) on this stream
+    torch.cuda.set_stream(stream)
 
     kb = build_problem(world)
     hbm_peak, tf_peak, peak_kind = peaks()

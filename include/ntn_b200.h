@@ -97,7 +97,8 @@ int ntn_set_frozen_wv(ntn_handle* h, const float* wv /* d*Nw */);
 
 /* The batch job (DataFactory.generateNewTrainingBatchJob, DataFactory.java:116-136): n columns
  * (e1, rel, e2, e3_corrupt) in batch order.  Indices are validated.  Columns sharing
- * (e1, rel, e2) are grouped internally; results do not depend on column order. */
+ * (e1, rel, e2) are grouped internally; results depend on column order only through FP32
+ * summation order. */
 int ntn_set_batch(ntn_handle* h, int64_t n,
                   const int32_t* e1, const int32_t* rel, const int32_t* e2, const int32_t* e3);
 
@@ -132,8 +133,10 @@ int ntn_from_internal_dev(ntn_handle* h, const float* d_int, float* d_ref);
 int ntn_upload_theta(ntn_handle* h, const double* theta, float* d_int);
 int ntn_download_theta(ntn_handle* h, const float* d_int, double* theta);
 
-/* Use the caller's CUDA stream (a cudaStream_t cast to void*; NULL = the handle's own). */
+/* Run on the caller's CUDA stream (a cudaStream_t cast to void*; as in CUDA, NULL is the legacy
+ * default stream).  ntn_reset_stream goes back to the handle's own non-blocking stream. */
 int ntn_set_stream(ntn_handle* h, void* cuda_stream);
+int ntn_reset_stream(ntn_handle* h);
 void* ntn_get_stream(ntn_handle* h);
 
 /* ---- eval-side scoring ("next" row N1) -------------------------------------------------- */

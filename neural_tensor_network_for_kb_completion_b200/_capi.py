@@ -56,6 +56,7 @@ SYMBOLS = {
     "ntn_upload_theta": (C.c_int, [_P, _P, _P]),
     "ntn_download_theta": (C.c_int, [_P, _P, _P]),
     "ntn_set_stream": (C.c_int, [_P, _P]),
+    "ntn_reset_stream": (C.c_int, [_P]),
     "ntn_get_stream": (_P, [_P]),
     "ntn_score": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, _P]),
     "ntn_last_launch_count": (C.c_int, [_P]),
@@ -198,8 +199,12 @@ class Handle:
         self._ck(self.lib.ntn_download_theta(self.h, d_int, _ptr(out)))
         return out
 
-    def set_stream(self, cuda_stream: int | None):
-        self._ck(self.lib.ntn_set_stream(self.h, cuda_stream))
+    def set_stream(self, cuda_stream: int):
+        """Run on this cudaStream_t (0 = CUDA's legacy default stream, e.g. torch's default)."""
+        self._ck(self.lib.ntn_set_stream(self.h, cuda_stream or None))
+
+    def reset_stream(self):
+        self._ck(self.lib.ntn_reset_stream(self.h))
 
     def score(self, theta, e1, rel, e2, mode="reference_eval"):
         theta = np.ascontiguousarray(theta, dtype=np.float64)

@@ -9,7 +9,8 @@
 
 #include "ntn_internal.h"
 
-int ntn_reg_part_count(const NtnDims& dm);                    // ntn_kernels.cu
+int ntn_small_blocks(const NtnDims& dm);                       // ntn_kernels.cu
+int ntn_word_blocks(const NtnDims& dm);
 int ntn_tc_supported(const ntn_handle* h);                     // gemm_tcgen05.cu
 int ntn_tc_prepare_batch(ntn_handle* h);
 void ntn_tc_release(ntn_handle* h);
@@ -111,6 +112,9 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
         return bail(NTN_ECUDA);
     }
     CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->stream = h->own_stream;
     const NtnDims& dm = h->dm;
     CKC(cudaMalloc((void**)&h->E, (size_t)dm.Ne * dm.Kp * sizeof(float)));
@@ -119,7 +123,7 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
     CKC(cudaMalloc((void**)&h->side, dm.R));
     CKC(cudaMallocHost((void**)&h->h_side, (size_t)dm.R * NTN_RING));
     for (int i = 0; i < NTN_RING; ++i) CKC(cudaEventCreateWithFlags(&h->side_ev[i], cudaEventDisableTiming));
-    h->n_reg_part = ntn_reg_part_count(dm);
+    h->n_reg_part = ntn_word_blocks(dm) + dm.Nw + ntn_small_blocks(dm);   // word blocks | hub words (<= Nw) | small blocks
     CKC(cudaMalloc((void**)&h->reg_part, (size_t)h->n_reg_part * sizeof(double)));
     CKC(cudaMalloc((void**)&h->d_out, 4 * sizeof(double)));
     CKC(cudaMallocHost((void**)&h->h_out, 4 * sizeof(double)));
@@ -132,10 +136,11 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
 
 static void free_batch(DeviceBatch& b) {
     dev_free(b.u_e1); dev_free(b.u_e2); dev_free(b.u_rel); dev_free(b.c_off); dev_free(b.c_e3);
+    dev_free(b.st_rel); dev_free(b.st_u0); dev_free(b.st_n); dev_free(b.rels_off);
     dev_free(b.t_rel); dev_free(b.t_u0); dev_free(b.t_n); dev_free(b.ch_rel); dev_free(b.ch_u0); dev_free(b.ch_n);
-    dev_free(b.relch_off); dev_free(b.reltile_off); dev_free(b.inc_off); dev_free(b.inc_u); dev_free(b.inc_code);
+    dev_free(b.relch_off); dev_free(b.reltile_off); dev_free(b.inc_off); dev_free(b.inc);
     dev_free(b.eh_ent); dev_free(b.eh_begin); dev_free(b.eh_end); dev_free(b.eh_first); dev_free(b.eh_count);
-    dev_free(b.T); dev_free(b.M); dev_free(b.GA); dev_free(b.acoef); dev_free(b.ccoef); dev_free(b.dWpart);
+    dev_free(b.T); dev_free(b.M); dev_free(b.GA); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.dWpart);
     dev_free(b.tp_cost); dev_free(b.tp_nact); dev_free(b.tp_dU); dev_free(b.eh_part);
     b = DeviceBatch();
 }
@@ -149,7 +154,7 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     DeviceWords& w = h->w;
     dev_free(w.fwd_off); dev_free(w.fwd_idx); dev_free(w.w_off); dev_free(w.w_ent); dev_free(w.len_bwd);
     dev_free(w.wh_word); dev_free(w.wh_begin); dev_free(w.wh_end); dev_free(w.wh_first); dev_free(w.wh_count);
-    dev_free(w.wh_part);
+    dev_free(w.wh_part); dev_free(w.hub_words);
     dev_free(h->wv_frozen); dev_free(h->E); dev_free(h->gE); dev_free(h->Waug); dev_free(h->side);
     dev_free(h->reg_part); dev_free(h->d_out); dev_free(h->d_ref_theta); dev_free(h->d_ref_grad);
     dev_free(h->d_int_theta); dev_free(h->d_int_grad);
@@ -160,6 +165,9 @@ extern "C" void ntn_destroy(ntn_handle* h) {
         if (h->side_ev[s]) cudaEventDestroy(h->side_ev[s]);
         for (int i = 0; i <= NTN_NUM_PHASES; ++i) if (h->ev[s][i]) cudaEventDestroy(h->ev[s][i]);
     }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -171,7 +179,14 @@ extern "C" int ntn_active_gemm_path(const ntn_handle* h) { return h ? h->gemm_pa
 
 extern "C" int ntn_set_stream(ntn_handle* h, void* s) {
     if (!h) return NTN_EINVAL;
-    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    cudaStreamSynchronize(h->stream);
+    h->stream = (cudaStream_t)s;
+    return NTN_OK;
+}
+extern "C" int ntn_reset_stream(ntn_handle* h) {
+    if (!h) return NTN_EINVAL;
+    cudaStreamSynchronize(h->stream);
+    h->stream = h->own_stream;
     return NTN_OK;
 }
 extern "C" void* ntn_get_stream(ntn_handle* h) { return h ? (void*)h->stream : nullptr; }
@@ -249,12 +264,16 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
     std::vector<int> sr, sb, se, first, count;
     build_hub_segments(woff, dm.Nw, sr, sb, se, first, count);
     w.n_hub_segs = (int)sr.size();
+    std::vector<int> hub_words;
+    for (int i = 0; i < dm.Nw; ++i) if (count[i] > 0) hub_words.push_back(i);
+    w.n_hub_words = (int)hub_words.size();
     int rc;
     if ((rc = dev_upload(h, &w.fwd_off, vfo)) || (rc = dev_upload(h, &w.fwd_idx, vfi)) ||
         (rc = dev_upload(h, &w.w_off, woff)) || (rc = dev_upload(h, &w.w_ent, went)) ||
         (rc = dev_upload(h, &w.len_bwd, lb)) || (rc = dev_upload(h, &w.wh_word, sr)) ||
         (rc = dev_upload(h, &w.wh_begin, sb)) || (rc = dev_upload(h, &w.wh_end, se)) ||
         (rc = dev_upload(h, &w.wh_first, first)) || (rc = dev_upload(h, &w.wh_count, count)) ||
+        (rc = dev_upload(h, &w.hub_words, hub_words)) ||
         (rc = dev_alloc(h, &w.wh_part, (size_t)w.n_hub_segs * dm.dq)))
         return rc;
     CK(cudaStreamSynchronize(h->stream));     // host vectors go out of scope
@@ -317,6 +336,7 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
     for (int u = 0; u < Nu; ++u) rel_off[u_rel[u] + 1]++;
     for (int r = 0; r < dm.R; ++r) rel_off[r + 1] += rel_off[r];
     std::vector<int> t_rel, t_u0, t_n, ch_rel, ch_u0, ch_n, relch_off(dm.R + 1, 0), reltile_off(dm.R + 1, 0);
+    std::vector<int> st_rel, st_u0, st_n, rels_off(dm.R + 1, 0);
     for (int r = 0; r < dm.R; ++r) {
         for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += NTN_TILE_ROWS) {
             t_rel.push_back(r); t_u0.push_back(u0); t_n.push_back(std::min(NTN_TILE_ROWS, rel_off[r + 1] - u0));
@@ -324,20 +344,25 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
         for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += NTN_CHUNK_ROWS) {
             ch_rel.push_back(r); ch_u0.push_back(u0); ch_n.push_back(std::min(NTN_CHUNK_ROWS, rel_off[r + 1] - u0));
         }
+        for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += NTN_SCORE_ROWS) {
+            st_rel.push_back(r); st_u0.push_back(u0); st_n.push_back(std::min(NTN_SCORE_ROWS, rel_off[r + 1] - u0));
+        }
+        rels_off[r + 1] = (int)st_rel.size();
         reltile_off[r + 1] = (int)t_rel.size();
         relch_off[r + 1] = (int)ch_rel.size();
     }
     // entity -> incidents: (e1 role, e2 role, corrupt columns), stable counting sort by entity
     int n_inc = 2 * Nu + (int)n;
-    std::vector<int> inc_off(dm.Ne + 1, 0), inc_u(n_inc), inc_code(n_inc);
+    std::vector<int> inc_off(dm.Ne + 1, 0);
+    std::vector<int4> inc(n_inc);
     for (int u = 0; u < Nu; ++u) { inc_off[u_e1[u] + 1]++; inc_off[u_e2[u] + 1]++; }
     for (int64_t c = 0; c < n; ++c) inc_off[c_e3[c] + 1]++;
     for (int e = 0; e < dm.Ne; ++e) inc_off[e + 1] += inc_off[e];
     {
         std::vector<int> cur(inc_off.begin(), inc_off.end() - 1);
-        for (int u = 0; u < Nu; ++u) { int p = cur[u_e1[u]]++; inc_u[p] = u; inc_code[p] = -1; }
-        for (int u = 0; u < Nu; ++u) { int p = cur[u_e2[u]]++; inc_u[p] = u; inc_code[p] = -2; }
-        for (int64_t c = 0; c < n; ++c) { int p = cur[c_e3[c]]++; inc_u[p] = col_u[c]; inc_code[p] = (int)c; }
+        for (int u = 0; u < Nu; ++u) inc[cur[u_e1[u]]++] = make_int4(u, u, 0, u_rel[u]);
+        for (int u = 0; u < Nu; ++u) inc[cur[u_e2[u]]++] = make_int4(u, u, 1, u_rel[u]);
+        for (int64_t c = 0; c < n; ++c) inc[cur[c_e3[c]]++] = make_int4(col_u[c], Nu + (int)c, 2, u_rel[col_u[c]]);
     }
     std::vector<int> sr, sb, se, first, count;
     build_hub_segments(inc_off, dm.Ne, sr, sb, se, first, count);
@@ -346,25 +371,28 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
     free_batch(h->b);
     DeviceBatch& b = h->b;
     b.N = n; b.Nu = Nu; b.ntiles = (int)t_rel.size(); b.nchunks = (int)ch_rel.size(); b.n_inc = n_inc;
+    b.nstiles = (int)st_rel.size();
     b.n_ent_hub_segs = (int)sr.size();
     int rc;
     if ((rc = dev_upload(h, &b.u_e1, u_e1)) || (rc = dev_upload(h, &b.u_e2, u_e2)) || (rc = dev_upload(h, &b.u_rel, u_rel)) ||
         (rc = dev_upload(h, &b.c_off, c_off)) || (rc = dev_upload(h, &b.c_e3, c_e3)) ||
         (rc = dev_upload(h, &b.t_rel, t_rel)) || (rc = dev_upload(h, &b.t_u0, t_u0)) || (rc = dev_upload(h, &b.t_n, t_n)) ||
+        (rc = dev_upload(h, &b.st_rel, st_rel)) || (rc = dev_upload(h, &b.st_u0, st_u0)) || (rc = dev_upload(h, &b.st_n, st_n)) ||
+        (rc = dev_upload(h, &b.rels_off, rels_off)) ||
         (rc = dev_upload(h, &b.ch_rel, ch_rel)) || (rc = dev_upload(h, &b.ch_u0, ch_u0)) || (rc = dev_upload(h, &b.ch_n, ch_n)) ||
         (rc = dev_upload(h, &b.relch_off, relch_off)) || (rc = dev_upload(h, &b.reltile_off, reltile_off)) ||
-        (rc = dev_upload(h, &b.inc_off, inc_off)) || (rc = dev_upload(h, &b.inc_u, inc_u)) ||
-        (rc = dev_upload(h, &b.inc_code, inc_code)) || (rc = dev_upload(h, &b.eh_ent, sr)) ||
+        (rc = dev_upload(h, &b.inc_off, inc_off)) || (rc = dev_upload(h, &b.inc, inc)) ||
+        (rc = dev_upload(h, &b.eh_ent, sr)) ||
         (rc = dev_upload(h, &b.eh_begin, sb)) || (rc = dev_upload(h, &b.eh_end, se)) ||
         (rc = dev_upload(h, &b.eh_first, first)) || (rc = dev_upload(h, &b.eh_count, count)) ||
         (rc = dev_alloc(h, &b.T, (size_t)Nu * dm.Np)) || (rc = dev_alloc(h, &b.M, (size_t)Nu * dm.Np)) ||
-        (rc = dev_alloc(h, &b.GA, (size_t)Nu * dm.Kp)) || (rc = dev_alloc(h, &b.acoef, (size_t)Nu * dm.k)) ||
-        (rc = dev_alloc(h, &b.ccoef, (size_t)n * dm.k)) ||
+        (rc = dev_alloc(h, &b.GA, (size_t)Nu * dm.Kp)) || (rc = dev_alloc(h, &b.acoef, ((size_t)Nu + (size_t)n) * dm.k)) ||
         (rc = dev_alloc(h, &b.dWpart, (size_t)b.nchunks * dm.Kp * dm.Np)) ||
-        (rc = dev_alloc(h, &b.tp_cost, (size_t)b.ntiles)) || (rc = dev_alloc(h, &b.tp_nact, (size_t)b.ntiles)) ||
-        (rc = dev_alloc(h, &b.tp_dU, (size_t)b.ntiles * dm.k)) ||
+        (rc = dev_alloc(h, &b.tp_cost, (size_t)b.nstiles)) || (rc = dev_alloc(h, &b.tp_nact, (size_t)b.nstiles)) ||
+        (rc = dev_alloc(h, &b.tp_dU, (size_t)b.nstiles * dm.k)) ||
         (rc = dev_alloc(h, &b.eh_part, (size_t)b.n_ent_hub_segs * dm.dq)))
         return rc;
+    b.ccoef = b.acoef + (size_t)Nu * dm.k;
     CK(cudaStreamSynchronize(h->stream));
     // contraction path for this batch
     h->gemm_path_active = NTN_GEMM_SIMT;

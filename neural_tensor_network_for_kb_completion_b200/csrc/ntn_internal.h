@@ -28,29 +28,31 @@ struct NtnDims {
     int64_t Pint;
 };
 
-#define NTN_TILE_ROWS   128      // unique triples per score tile (one relation per tile)
+#define NTN_TILE_ROWS   128      // unique triples per contraction tile (one relation per tile)
 #define NTN_CHUNK_ROWS  512      // unique triples per dW split-K chunk (one relation per chunk)
-#define NTN_HUB_SEG     256      // incident-list segment length for hub words / hub entities
+#define NTN_SCORE_ROWS  32       // unique triples per score tile (8 warps x 4)
+#define NTN_HUB_SEG     32       // incident-list segment length for hub words / hub entities
 #define NTN_RING        8        // in-flight evaluations the host may enqueue without synchronising
 
 struct DeviceBatch {
     int64_t N = 0;               // columns
     int Nu = 0;                  // unique (rel, e1, e2)
-    int ntiles = 0, nchunks = 0;
+    int ntiles = 0, nchunks = 0, nstiles = 0;
     int n_inc = 0;               // incidents = 2*Nu + N
     int n_ent_hub_segs = 0;
     // unique triples, sorted by (rel, e1, e2)
     int *u_e1 = nullptr, *u_e2 = nullptr, *u_rel = nullptr;
     int *c_off = nullptr;        // Nu+1: corrupt columns of each unique triple
     int *c_e3 = nullptr;         // N
-    int *t_rel = nullptr, *t_u0 = nullptr, *t_n = nullptr;        // score tiles
+    int *t_rel = nullptr, *t_u0 = nullptr, *t_n = nullptr;        // contraction tiles
+    int *st_rel = nullptr, *st_u0 = nullptr, *st_n = nullptr;     // score tiles
+    int *rels_off = nullptr;     // R+1: score-tile range per relation
     int *ch_rel = nullptr, *ch_u0 = nullptr, *ch_n = nullptr;     // dW chunks
     int *relch_off = nullptr;    // R+1: chunk range per relation
     int *reltile_off = nullptr;  // R+1: tile range per relation
     // entity -> incidents (pull lists), sorted by (entity, code, u)
     int *inc_off = nullptr;      // Ne+1
-    int *inc_u = nullptr;        // unique triple of the incident
-    int *inc_code = nullptr;     // -1: entity is e1 of u, -2: e2 of u, >=0: corrupt column id
+    int4 *inc = nullptr;         // {unique triple, coefficient row, role (0 e1, 1 e2, 2 e3), relation}
     // hub entities (incident list longer than NTN_HUB_SEG): segments + partial rows
     int *eh_ent = nullptr, *eh_begin = nullptr, *eh_end = nullptr;   // per segment
     int *eh_first = nullptr;     // Ne: first segment id of a hub entity, -1 otherwise
@@ -59,8 +61,8 @@ struct DeviceBatch {
     float *T = nullptr;          // Nu x Np   T' = [E_anchor | 1] * Waug
     float *M = nullptr;          // Nu x Np   backward coefficients folded with the gathered rows
     float *GA = nullptr;         // Nu x Kp   anchor-entity gradient rows
-    float *acoef = nullptr;      // Nu x k    a_{u,s}
-    float *ccoef = nullptr;      // N  x k    c_{col,s}
+    float *acoef = nullptr;      // (Nu + N) x k : a_{u,s} rows, then c_{col,s} rows (one allocation)
+    float *ccoef = nullptr;      // = acoef + Nu*k
     float *dWpart = nullptr;     // nchunks x Kp x Np
     double *tp_cost = nullptr;   // ntiles
     int *tp_nact = nullptr;      // ntiles
@@ -74,7 +76,8 @@ struct DeviceWords {
     int *fwd_off = nullptr, *fwd_idx = nullptr;    // entity -> forward words
     int *w_off = nullptr, *w_ent = nullptr;        // word -> entities of the backward lists (inverse CSR)
     float *len_bwd = nullptr;                      // Ne, as float
-    int n_hub_segs = 0;
+    int n_hub_segs = 0, n_hub_words = 0;
+    int *hub_words = nullptr;                      // ids of the hub words
     int *wh_word = nullptr, *wh_begin = nullptr, *wh_end = nullptr;
     int *wh_first = nullptr, *wh_count = nullptr;  // Nw
     float *wh_part = nullptr;                      // n_hub_segs x dq
@@ -86,6 +89,8 @@ struct ntn_handle {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // forked branch (hub words), joined before the final reduce
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     DeviceWords w;
     DeviceBatch b;

