@@ -157,6 +157,10 @@ int ntn_last_phase_ms(ntn_handle* h, float* ms /* NTN_NUM_PHASES */);
 #define NTN_NUM_PHASES 9
 const char* ntn_phase_name(int i);
 
+/* Test hook: copy an FP32 intermediate of the last evaluation ("T", "M", "GA", "dWpart", "E", "gE")
+ * to the host; returns its element count (call with out == NULL to size the buffer), -1 if unknown. */
+int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, int64_t cap);
+
 const char* ntn_version(void);
 
 #ifdef __cplusplus

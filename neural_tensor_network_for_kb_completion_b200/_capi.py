@@ -64,6 +64,7 @@ SYMBOLS = {
     "ntn_set_profiling": (C.c_int, [_P, C.c_int]),
     "ntn_last_phase_ms": (C.c_int, [_P, _P]),
     "ntn_phase_name": (C.c_char_p, [C.c_int]),
+    "ntn_debug_fetch": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64]),
     "ntn_version": (C.c_char_p, []),
 }
 
@@ -212,6 +213,14 @@ class Handle:
         out = np.empty(len(e1), np.float64)
         m = {"reference_eval": SCORE_REFERENCE_EVAL, "train": SCORE_TRAIN}[mode]
         self._ck(self.lib.ntn_score(self.h, _ptr(theta), len(e1), _ptr(e1), _ptr(rel), _ptr(e2), m, _ptr(out)))
+        return out
+
+    def debug_fetch(self, name):
+        n = self.lib.ntn_debug_fetch(self.h, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, np.float32)
+        self.lib.ntn_debug_fetch(self.h, name.encode(), _ptr(out), n)
         return out
 
     # ---- introspection ----

@@ -1,11 +1,475 @@
-// tcgen05/TMEM + TMA contractions (3xTF32).  Placeholder until the kernels land: reports the
-// path as unsupported so that NTN_GEMM_AUTO uses the SIMT kernels and NTN_GEMM_TCGEN05 fails loudly.
+// tcgen05 / TMEM contractions of the NTN path with a 3xTF32 split (FP32-level accuracy on the
+// 5th-generation tensor cores).  Three grouped GEMMs per evaluation:
+//
+//   fwd  T'[u, n]      = sum_p  [E_anchor(u) | 1][p] * Waug_r[p, n]        NTN.java:163-197
+//   dw   dWaug_r[p, n] = sum_u  [E_anchor(u) | 1][p] * M[u, n]  (split-K)  NTN.java:301-349
+//   ge   GA[u, p]      = sum_n  M[u, n] * Waug_r[p, n]                     NTN.java:352-388
+//
+// One CTA = one 128-row accumulator tile in TMEM (tcgen05.alloc), N <= 160 columns.
+//   warps 0-3  producers: gather / load FP32 operand rows, split x = hi + lo (hi = rna-tf32(x),
+//              lo = rna-tf32(x - hi)), store both into 128B-swizzled UMMA shared-memory tiles,
+//              fence.proxy.async, arrive on the stage's "full" mbarrier; afterwards the same warps
+//              run the epilogue (tcgen05.ld -> registers -> global).
+//   warp  4    TMEM allocation + the single-thread MMA issuer: per k-step of 8 it issues
+//              tcgen05.mma kind::tf32  hi*hi, lo*hi, hi*lo  into the same FP32 accumulator, then
+//              tcgen05.commit releases the stage ("empty" mbarrier) / signals the epilogue.
+// fwd and ge use K-major operands (row = M/N index, 128 bytes of K per row, SWIZZLE_128B);
+// dw contracts over the row index of both operands, so both are MN-major swizzled tiles.
+// The weight operand is read from pre-split hi/lo arrays written once per evaluation by
+// k_tc_w_prep (via TMA when NTN_TC_TMA is enabled).
+#include <cuda.h>
+#include <stdio.h>
+
 #include "ntn_internal.h"
 
-int ntn_tc_supported(const ntn_handle*) { return 0; }
-int ntn_tc_prepare_batch(ntn_handle*) { return NTN_EUNSUP; }
-void ntn_tc_release(ntn_handle*) {}
-int ntn_tc_w_prep(ntn_handle*, const float*) { return NTN_EUNSUP; }
-int ntn_tc_gemm_fwd(ntn_handle*) { return NTN_EUNSUP; }
-int ntn_tc_gemm_dw(ntn_handle*) { return NTN_EUNSUP; }
-int ntn_tc_gemm_ge(ntn_handle*) { return NTN_EUNSUP; }
+#define TC_STAGES 3
+#define TC_BK 32                  // floats of K per stage (= one 128-byte swizzle row)
+#define TC_NCH 160                // accumulator columns per CTA
+#define TC_A_BYTES (128 * 128)    // one split of the A tile per stage
+#define TC_B_BYTES (TC_NCH * 128) // one split of the B tile per stage
+#define TC_STAGE_BYTES (2 * TC_A_BYTES + 2 * TC_B_BYTES)
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define TC_TMEM_COLS 256
+#define TC_SPIN_LIMIT (1u << 22)
+
+struct TcState {
+    float *WT_hi = nullptr, *WT_lo = nullptr;   // [R][Np][KpP]   Waug^T, K(=p)-major rows      (fwd B)
+    float *W_hi = nullptr, *W_lo = nullptr;     // [R][KpN][NpP]  Waug,   K(=n)-major rows      (ge  B)
+    int KpP = 0, KpN = 0, NpP = 0;
+    int* err = nullptr;                         // device flag: a bounded wait expired
+    bool attr_set = false;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must not hang the GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+    for (uint32_t i = 0; i < TC_SPIN_LIMIT; ++i)
+        if (mbar_try_wait(bar, parity)) return true;
+    atomicExch(err, 1);
+    return false;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], TF32 inputs, FP32 accumulate, single-CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
+    auto sp = [](float v, float& h, float& l) {
+        uint32_t hb, lb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+        h = __uint_as_float(hb);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - h));
+        l = __uint_as_float(lb);
+    };
+    sp(x.x, hi.x, lo.x); sp(x.y, hi.y, lo.y); sp(x.z, hi.z, lo.z); sp(x.w, hi.w, lo.w);
+}
+__device__ __forceinline__ float4 ldg4g(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void sts4(uint8_t* base, uint32_t off, const float4& v) { *reinterpret_cast<float4*>(base + off) = v; }
+
+// ------------------------------------------------------------------------------------------
+struct TcArgs {
+    const int *t_rel, *t_u0, *t_n;     // tile table (fwd/ge: <=128 rows) or chunk table (dw: <=512 rows)
+    const int *u_e1, *u_e2;
+    const uint8_t* side;
+    const float *E, *M;
+    const float *WT_hi, *WT_lo, *W_hi, *W_lo;
+    float *T, *GA, *dWpart;
+    int Kp, Np, KpP, KpN, NpP;
+    int* err;
+};
+
+enum { TC_FWD = 0, TC_DW = 1, TC_GE = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready; then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+    const uint32_t acc_bar = bar0 + 8u * (2 * TC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x;
+    const int r = a.t_rel[item], u0 = a.t_u0[item], rows = a.t_n[item];
+    const bool tail = a.side[r] != 0;
+
+    // problem geometry of this CTA
+    int n0, nlen, m0 = 0, kext;
+    if (MODE == TC_GE) { n0 = blockIdx.y * TC_NCH; nlen = min(TC_NCH, a.KpN - n0); kext = a.Np; }
+    else { n0 = blockIdx.y * TC_NCH; nlen = min(TC_NCH, a.Np - n0); kext = (MODE == TC_FWD) ? a.Kp : rows; }
+    if (MODE == TC_DW) m0 = blockIdx.z * 128;
+    const int nkb = (kext + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ================================ producers ================================
+        const int t = threadIdx.x;                       // 0..127
+        const int j = t & 7;                             // 16-byte chunk inside a 128-byte swizzle row
+        const int rsub = t >> 3;                         // 0..15
+        int anchor[8];                                   // fwd: gathered entity of this thread's 8 rows; dw: per k-block
+        if (MODE == TC_FWD) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int row = rsub + 16 * i;
+                anchor[i] = (row < rows) ? (tail ? __ldg(a.u_e1 + u0 + row) : __ldg(a.u_e2 + u0 + row)) : -1;
+            }
+        }
+        const float* Bhi = (MODE == TC_FWD) ? a.WT_hi + (size_t)r * a.Np * a.KpP
+                          : (MODE == TC_GE) ? a.W_hi + (size_t)r * a.KpN * a.NpP : nullptr;
+        const float* Blo = (MODE == TC_FWD) ? a.WT_lo + (size_t)r * a.Np * a.KpP
+                          : (MODE == TC_GE) ? a.W_lo + (size_t)r * a.KpN * a.NpP : nullptr;
+        const int ldb = (MODE == TC_FWD) ? a.KpP : a.NpP;
+        bool alive = true;
+        for (int kb = 0; kb < nkb && alive; ++kb) {
+            const int s = kb % TC_STAGES;
+            const uint32_t ph = (kb / TC_STAGES) & 1;
+            alive = mbar_wait(empty_bar(s), ph ^ 1, a.err);
+            uint8_t* sA_hi = smem + s * TC_STAGE_BYTES;
+            uint8_t* sA_lo = sA_hi + TC_A_BYTES;
+            uint8_t* sB_hi = sA_lo + TC_A_BYTES;
+            uint8_t* sB_lo = sB_hi + TC_B_BYTES;
+            const int k0 = kb * TC_BK;
+            if (MODE == TC_FWD || MODE == TC_GE) {
+                // ---- A: K-major, 128 rows x 128 bytes, chunk j of row `row` at row*128 + ((j ^ (row&7))<<4)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = rsub + 16 * i;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int kk = k0 + j * 4;
+                    if (MODE == TC_FWD) { if (anchor[i] >= 0 && kk < a.Kp) x = ldg4g(a.E + (size_t)anchor[i] * a.Kp + kk); }
+                    else { if (row < rows && kk < a.Np) x = ldg4g(a.M + (size_t)(u0 + row) * a.Np + kk); }
+                    float4 hi, lo;
+                    split_tf32(x, hi, lo);
+                    const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+                    sts4(sA_hi, off, hi); sts4(sA_lo, off, lo);
+                }
+                // ---- B: K-major, nlen rows (n resp. p) x 128 bytes, from the pre-split weight arrays
+                for (int row = rsub; row < nlen; row += 16) {
+                    const size_t g = (size_t)(n0 + row) * ldb + k0 + j * 4;
+                    const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+                    sts4(sB_hi, off, ldg4g(Bhi + g)); sts4(sB_lo, off, ldg4g(Blo + g));
+                }
+            } else {
+                // ---- dw: both operands MN-major.  Tile = [mn-atom (32 floats)][k-group (8 rows)][8 rows][128 B];
+                //      row u_local of the k-block: k-group u_local>>3, row u_local&7.
+#pragma unroll
+                for (int i2 = 0; i2 < 2; ++i2) {
+                    const int ul = rsub + 16 * i2;
+                    const int u = k0 + ul;
+                    const int an = (u < rows) ? (tail ? __ldg(a.u_e1 + u0 + u) : __ldg(a.u_e2 + u0 + u)) : -1;
+                    const uint32_t rowoff = (ul >> 3) * 1024 + (ul & 7) * 128 + ((j ^ (ul & 7)) << 4);
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {                                  // A: p = m0 + mi*32 + j*4
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int p = m0 + mi * 32 + j * 4;
+                        if (an >= 0 && p < a.Kp) x = ldg4g(a.E + (size_t)an * a.Kp + p);
+                        float4 hi, lo;
+                        split_tf32(x, hi, lo);
+                        sts4(sA_hi, mi * 4096 + rowoff, hi); sts4(sA_lo, mi * 4096 + rowoff, lo);
+                    }
+                    for (int ni = 0; ni * 32 < nlen; ++ni) {                          // B: n = n0 + ni*32 + j*4
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int n = ni * 32 + j * 4;
+                        if (an >= 0 && n < nlen) x = ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + n);
+                        float4 hi, lo;
+                        split_tf32(x, hi, lo);
+                        sts4(sB_hi, ni * 4096 + rowoff, hi); sts4(sB_lo, ni * 4096 + rowoff, lo);
+                    }
+                }
+            }
+            fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(full_bar(s));
+        }
+        // ================================ epilogue ================================
+        if (alive) alive = mbar_wait(acc_bar, 0, a.err);
+        tc_fence_after();
+        if (alive) {
+            const int row = warp * 32 + lane;            // TMEM lane = accumulator row
+            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < nlen; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + c0, v);
+                if (MODE == TC_FWD) {
+                    if (row < rows) {
+                        float* dst = a.T + (size_t)(u0 + row) * a.Np + n0 + c0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                } else if (MODE == TC_GE) {
+                    if (row < rows) {
+                        float* dst = a.GA + (size_t)(u0 + row) * a.Kp + n0 + c0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (n0 + c0 + 4 * q < a.Kp) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                } else {
+                    // partial stored transposed, [n][p]: lanes = consecutive p -> coalesced
+                    const int p = m0 + row;
+                    if (p < a.Kp) {
+                        float* dst = a.dWpart + (size_t)item * a.Kp * a.Np + (size_t)(n0 + c0) * a.Kp + p;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) dst[(size_t)q * a.Kp] = v[q];
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc = make_idesc(nlen, MODE == TC_DW, MODE == TC_DW);
+        bool alive = true;
+        for (int kb = 0; kb < nkb && alive; ++kb) {
+            const int s = kb % TC_STAGES;
+            const uint32_t ph = (kb / TC_STAGES) & 1;
+            alive = mbar_wait(full_bar(s), ph, a.err);
+            tc_fence_after();
+            if (lane == 0 && alive) {
+                const uint32_t sA_hi = smem_u32(smem + s * TC_STAGE_BYTES);
+                const uint32_t sA_lo = sA_hi + TC_A_BYTES, sB_hi = sA_lo + TC_A_BYTES, sB_lo = sB_hi + TC_B_BYTES;
+                const int kleft = kext - kb * TC_BK;
+                const int nks = (kleft >= TC_BK) ? 4 : (kleft + 7) / 8;
+                for (int ks = 0; ks < nks; ++ks) {
+                    uint64_t dAh, dAl, dBh, dBl;
+                    if (MODE == TC_DW) {             // MN-major: k-step = one 8-row group (1024 B); atoms 4096 B apart
+                        dAh = make_desc(sA_hi + ks * 1024, 4096, 1024); dAl = make_desc(sA_lo + ks * 1024, 4096, 1024);
+                        dBh = make_desc(sB_hi + ks * 1024, 4096, 1024); dBl = make_desc(sB_lo + ks * 1024, 4096, 1024);
+                    } else {                         // K-major: k-step = 32 bytes inside the swizzle row; 8-row groups 1024 B apart
+                        dAh = make_desc(sA_hi + ks * 32, 16, 1024); dAl = make_desc(sA_lo + ks * 32, 16, 1024);
+                        dBh = make_desc(sB_hi + ks * 32, 16, 1024); dBl = make_desc(sB_lo + ks * 32, 16, 1024);
+                    }
+                    const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                    umma_tf32(tmem_base, dAl, dBh, idesc, first);      // small terms first
+                    umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
+                    umma_tf32(tmem_base, dAh, dBh, idesc, 1u);
+                }
+                umma_commit(empty_bar(s));                              // stage free once these MMAs have read it
+                if (kb == nkb - 1) umma_commit(acc_bar);                // accumulator complete
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, TC_TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-evaluation weight preparation: Waug_r (see k_w_prep in ntn_kernels.cu) pre-split into tf32
+// hi/lo, in the two K-major layouts the kernels above read.  Padding rows/columns are zero.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float waug_at(const float* theta, const NtnDims& dm, int r, bool tail, int p, int n) {
+    const int d = dm.d, k = dm.k, dq = dm.dq;
+    if (p > d || n >= k * dq + k) return 0.f;
+    const float* W = theta + dm.oW + (int64_t)r * k * d * d;
+    const float* V = theta + dm.oV + (int64_t)r * 2 * d * k;
+    if (n < k * dq) {
+        int s = n / dq, q = n - s * dq;
+        if (q >= d) return 0.f;
+        if (p < d) return tail ? W[((int64_t)s * d + p) * d + q] : W[((int64_t)s * d + q) * d + p];
+        return tail ? V[(d + q) * k + s] : V[q * k + s];
+    }
+    int s = n - k * dq;
+    if (p < d) return tail ? V[p * k + s] : V[(d + p) * k + s];
+    return theta[dm.ob + (int64_t)r * k + s];
+}
+__device__ __forceinline__ void split1(float v, float& h, float& l) {
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    h = __uint_as_float(hb);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - h));
+    l = __uint_as_float(lb);
+}
+__global__ void __launch_bounds__(256) k_tc_w_prep(const float* __restrict__ theta, const uint8_t* __restrict__ side,
+                                                   float* WT_hi, float* WT_lo, float* W_hi, float* W_lo, NtnDims dm,
+                                                   int KpP, int KpN, int NpP) {
+    const int64_t nA = (int64_t)dm.R * dm.Np * KpP, nB = (int64_t)dm.R * KpN * NpP;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nA) {
+        int r = (int)(i / ((int64_t)dm.Np * KpP));
+        int rem = (int)(i - (int64_t)r * dm.Np * KpP);
+        int n = rem / KpP, p = rem - n * KpP;
+        float h, l;
+        split1(waug_at(theta, dm, r, side[r] != 0, p, n), h, l);
+        WT_hi[i] = h; WT_lo[i] = l;
+    } else if (i < nA + nB) {
+        i -= nA;
+        int r = (int)(i / ((int64_t)KpN * NpP));
+        int rem = (int)(i - (int64_t)r * KpN * NpP);
+        int p = rem / NpP, n = rem - p * NpP;
+        float h, l;
+        split1(waug_at(theta, dm, r, side[r] != 0, p, n), h, l);
+        W_hi[i] = h; W_lo[i] = l;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline int rup(int a, int b) { return (a + b - 1) / b * b; }
+static inline int cdivi(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+int ntn_tc_supported(const ntn_handle* h) {
+    (void)h;
+    return 1;
+}
+
+static TcArgs tc_args(ntn_handle* h, bool chunks) {
+    TcState* st = (TcState*)h->tc;
+    const DeviceBatch& b = h->b;
+    TcArgs a{};
+    a.t_rel = chunks ? b.ch_rel : b.t_rel; a.t_u0 = chunks ? b.ch_u0 : b.t_u0; a.t_n = chunks ? b.ch_n : b.t_n;
+    a.u_e1 = b.u_e1; a.u_e2 = b.u_e2; a.side = h->side; a.E = h->E; a.M = b.M;
+    a.WT_hi = st->WT_hi; a.WT_lo = st->WT_lo; a.W_hi = st->W_hi; a.W_lo = st->W_lo;
+    a.T = b.T; a.GA = b.GA; a.dWpart = b.dWpart;
+    a.Kp = h->dm.Kp; a.Np = h->dm.Np; a.KpP = st->KpP; a.KpN = st->KpN; a.NpP = st->NpP;
+    a.err = st->err;
+    return a;
+}
+
+int ntn_tc_prepare_batch(ntn_handle* h) {
+    const NtnDims& dm = h->dm;
+    if (!h->tc) {
+        TcState* st = new TcState();
+        h->tc = st;
+        st->KpP = rup(dm.Kp, TC_BK); st->KpN = rup(dm.Kp, 16); st->NpP = rup(dm.Np, TC_BK);
+        size_t nA = (size_t)dm.R * dm.Np * st->KpP, nB = (size_t)dm.R * st->KpN * st->NpP;
+        cudaError_t e;
+        if ((e = cudaMalloc((void**)&st->WT_hi, nA * 4)) || (e = cudaMalloc((void**)&st->WT_lo, nA * 4)) ||
+            (e = cudaMalloc((void**)&st->W_hi, nB * 4)) || (e = cudaMalloc((void**)&st->W_lo, nB * 4)) ||
+            (e = cudaMalloc((void**)&st->err, 4)) || (e = cudaMemset(st->err, 0, 4))) {
+            h->err = std::string("tcgen05 state: ") + cudaGetErrorString(e);
+            return NTN_ECUDA;
+        }
+        if ((e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES))) {
+            h->err = std::string("tcgen05 smem attribute: ") + cudaGetErrorString(e);
+            return NTN_ECUDA;
+        }
+    }
+    return NTN_OK;
+}
+
+void ntn_tc_release(ntn_handle* h) {
+    TcState* st = (TcState*)h->tc;
+    if (!st) return;
+    cudaFree(st->WT_hi); cudaFree(st->WT_lo); cudaFree(st->W_hi); cudaFree(st->W_lo); cudaFree(st->err);
+    delete st;
+    h->tc = nullptr;
+}
+
+int ntn_tc_w_prep(ntn_handle* h, const float* theta) {
+    TcState* st = (TcState*)h->tc;
+    const NtnDims& dm = h->dm;
+    int64_t n = (int64_t)dm.R * dm.Np * st->KpP + (int64_t)dm.R * st->KpN * st->NpP;
+    k_tc_w_prep<<<cdivi(n, 256), 256, 0, h->stream>>>(theta, h->side, st->WT_hi, st->WT_lo, st->W_hi, st->W_lo, dm,
+                                                      st->KpP, st->KpN, st->NpP);
+    h->launches++;
+    return NTN_OK;
+}
+
+int ntn_tc_gemm_fwd(ntn_handle* h) {
+    TcArgs a = tc_args(h, false);
+    dim3 g(h->b.ntiles, cdivi(h->dm.Np, TC_NCH));
+    k_tc_gemm<TC_FWD><<<g, 160, TC_SMEM_BYTES, h->stream>>>(a);
+    h->launches++;
+    return NTN_OK;
+}
+
+int ntn_tc_gemm_dw(ntn_handle* h) {
+    TcArgs a = tc_args(h, true);
+    dim3 g(h->b.nchunks, cdivi(h->dm.Np, TC_NCH), cdivi(h->dm.Kp, 128));
+    k_tc_gemm<TC_DW><<<g, 160, TC_SMEM_BYTES, h->stream>>>(a);
+    h->launches++;
+    return NTN_OK;
+}
+
+int ntn_tc_gemm_ge(ntn_handle* h) {
+    TcArgs a = tc_args(h, false);
+    TcState* st = (TcState*)h->tc;
+    dim3 g(h->b.ntiles, cdivi(st->KpN, TC_NCH));
+    k_tc_gemm<TC_GE><<<g, 160, TC_SMEM_BYTES, h->stream>>>(a);
+    h->launches++;
+    return NTN_OK;
+}
+
+int ntn_tc_check_error(ntn_handle* h) {
+    TcState* st = (TcState*)h->tc;
+    if (!st) return 0;
+    int v = 0;
+    cudaMemcpy(&v, st->err, 4, cudaMemcpyDeviceToHost);
+    return v;
+}

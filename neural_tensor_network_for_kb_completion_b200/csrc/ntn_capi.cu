@@ -18,6 +18,7 @@ int ntn_tc_w_prep(ntn_handle* h, const float* theta);
 int ntn_tc_gemm_fwd(ntn_handle* h);
 int ntn_tc_gemm_dw(ntn_handle* h);
 int ntn_tc_gemm_ge(ntn_handle* h);
+int ntn_tc_check_error(ntn_handle* h);
 
 static thread_local std::string g_create_err;
 
@@ -462,6 +463,8 @@ extern "C" int ntn_last_cost(ntn_handle* h, double* cost, int64_t* n_active) {
     CK(cudaStreamSynchronize(h->stream));
     if (cost) *cost = h->h_out[0];
     if (n_active) *n_active = (int64_t)llround(h->h_out[1]);
+    if (h->gemm_path_active == NTN_GEMM_TCGEN05 && ntn_tc_check_error(h))
+        FAIL(NTN_ECUDA, "tcgen05 pipeline: a bounded mbarrier wait expired (results invalid)");
     return NTN_OK;
 }
 
@@ -585,6 +588,26 @@ extern "C" int ntn_download_theta(ntn_handle* h, const float* d_int, double* the
     CK(cudaStreamSynchronize(h->stream));
     convert_parallel(h->h_stage, theta, dm.P);
     return NTN_OK;
+}
+
+// test hook: copy an intermediate of the last evaluation to the host (T, M, GA: FP32; returns count)
+extern "C" int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, int64_t cap) {
+    if (!h || !name) return -1;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    const NtnDims& dm = h->dm;
+    const DeviceBatch& b = h->b;
+    const float* src = nullptr; int64_t n = 0;
+    std::string s(name);
+    if (s == "T") { src = b.T; n = (int64_t)b.Nu * dm.Np; }
+    else if (s == "M") { src = b.M; n = (int64_t)b.Nu * dm.Np; }
+    else if (s == "GA") { src = b.GA; n = (int64_t)b.Nu * dm.Kp; }
+    else if (s == "dWpart") { src = b.dWpart; n = (int64_t)b.nchunks * dm.Kp * dm.Np; }
+    else if (s == "E") { src = h->E; n = (int64_t)dm.Ne * dm.Kp; }
+    else if (s == "gE") { src = h->gE; n = (int64_t)dm.Ne * dm.dq; }
+    else return -1;
+    if (out && cap >= n && n > 0) cudaMemcpy(out, src, n * sizeof(float), cudaMemcpyDeviceToHost);
+    return n;
 }
 
 extern "C" int ntn_score(ntn_handle* h, const double* theta, int64_t n, const int32_t* e1, const int32_t* rel,

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) k_gemm_ge_simt(GemmTables tb, const float
     }
 }
 
-// dWaug split-K partial: part[chunk][p][n] = sum_{u in chunk} E[anchor(u)][p] * M[u][n]   (NTN.java:301-349)
+// dWaug split-K partial: part[chunk][n][p] = sum_{u in chunk} E[anchor(u)][p] * M[u][n]   (NTN.java:301-349)
 // grid.x = chunks, grid.y = ceil(Kp/64) * ceil(Np/64)
 __global__ void __launch_bounds__(256) k_gemm_dw_simt(GemmTables tb, const float* __restrict__ E,
                                                       const float* __restrict__ M, float* __restrict__ part,
@@ -258,13 +258,14 @@ __global__ void __launch_bounds__(256) k_gemm_dw_simt(GemmTables tb, const float
         gemm_compute_tile(As, Bs, acc, ty, tx);
         __syncthreads();
     }
+    // stored transposed, [chunk][n][p] (p contiguous): the layout the tcgen05 epilogue writes coalesced
     float* C = part + (size_t)ch * Kp * Np;
+    const int m = m0 + ty * 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int m = m0 + ty * 4 + i;
-        if (m < Kp && n0 + tx * 4 < Np)
-            *reinterpret_cast<float4*>(C + (size_t)m * Np + n0 + tx * 4) =
-                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    for (int j = 0; j < 4; ++j) {
+        int n = n0 + tx * 4 + j;
+        if (n < Np && m < Kp)
+            *reinterpret_cast<float4*>(C + (size_t)n * Kp + m) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
     }
 }
 
@@ -695,7 +696,7 @@ __global__ void __launch_bounds__(256) k_finalize_small(FinArgs a) {
     if (i < nW) {
         int r = (int)(i / per);
         int rem = (int)(i - (int64_t)r * per);
-        int p = rem / dm.Np, n = rem - p * dm.Np;
+        int n = rem / dm.Kp, p = rem - n * dm.Kp;                      // partials are [n][p], p contiguous
         bool tail = a.side[r] != 0;
         int64_t idx = -1;
         if (n < k * dq) {

@@ -260,3 +260,27 @@ def test_errors_are_reported_not_fatal():
         h.set_entity_words(p.fwd_off, p.fwd_idx, p.bwd_off, p.bwd_idx, lb)
     assert ei.value.code == _capi.NTN_EINVAL
     h.close()
+
+
+@pytest.mark.parametrize("shape", [
+    dict(Ne=500, R=11, T=3000, Nw=400, d=100, k=3, batch=2000, corrupt=10),
+    dict(Ne=300, R=4, T=500, Nw=200, d=20, k=3, batch=400, corrupt=5),
+    dict(Ne=150, R=5, T=400, Nw=80, d=132, k=8, batch=300, corrupt=3),
+])
+def test_tcgen05_contractions_match_simt_intermediates(shape):
+    """The three tcgen05/TMEM 3xTF32 contractions against the FP32 CUDA-core kernels on the same
+    inputs: T' (forward), GA (anchor-entity gradient), dWaug split-K partials."""
+    kb, p, batch, side, theta0 = small_problem(**shape, seed=1)
+    theta = f32(spread(perturbed(theta0, 0.05), p, u=4.0, w=10.0, wv=3.0))
+    out = {}
+    for path in ("simt", "tcgen05"):
+        h = make_handle(p, "theta", path)
+        h.set_batch(*batch)
+        h.eval(theta, side)
+        assert h.gemm_path == path
+        out[path] = {n: h.debug_fetch(n) for n in ("T", "M", "GA", "dWpart")}
+        h.close()
+    for name in ("T", "M", "GA", "dWpart"):
+        a, b = out["simt"][name], out["tcgen05"][name]
+        scale = np.abs(a).max()
+        assert np.abs(a - b).max() <= 2e-6 * scale + 1e-7, (name, float(np.abs(a - b).max()), float(scale))
