@@ -13,8 +13,8 @@
 //   warp  4    TMEM allocation + the single-thread MMA issuer: per k-step of 8 it issues
 //              tcgen05.mma kind::tf32  hi*hi, lo*hi, hi*lo  into the same FP32 accumulator, then
 //              tcgen05.commit releases the stage ("empty" mbarrier) / signals the epilogue.
-// fwd and ge use K-major operands (row = M/N index, 128 bytes of K per row, SWIZZLE_128B);
-// dw contracts over the row index of both operands, so both are MN-major swizzled tiles.
+// All operands are K-major SWIZZLE_128B tiles (row = M/N index, 128 bytes of K per row).  dw contracts
+// over the ROW index of both of its operands, so its producers transpose while they store.
 // The weight operand is read from pre-split hi/lo arrays written once per evaluation by
 // k_tc_w_prep (via TMA when NTN_TC_TMA is enabled).
 #include <cuda.h>
@@ -223,30 +223,38 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                     sts4(sB_hi, off, ldg4g(Bhi + g)); sts4(sB_lo, off, ldg4g(Blo + g));
                 }
             } else {
-                // ---- dw: both operands MN-major.  Tile = [mn-atom (32 floats)][k-group (8 rows)][8 rows][128 B];
-                //      row u_local of the k-block: k-group u_local>>3, row u_local&7.
+                // ---- dw: the contraction runs over the ROW index u of both operands, so the producers
+                //      transpose while storing: lane = u row of this k-block (K index), warps stride over the
+                //      16-byte column chunks.  For a fixed chunk and component the 32 lanes hit 32 different
+                //      banks (8 swizzled k-chunks x 4 words), so the 4-byte stores are conflict-free.
+                const int ul = lane, u = k0 + ul;
+                const int an = (u < rows) ? (tail ? __ldg(a.u_e1 + u0 + u) : __ldg(a.u_e2 + u0 + u)) : -1;
+                const uint32_t kc = ul >> 2, ke = (ul & 3) * 4;
+                for (int c = warp; c < 32; c += 4) {                                  // A rows: p = m0 + 4c + e
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int p = m0 + 4 * c;
+                    if (an >= 0 && p < a.Kp) x = ldg4g(a.E + (size_t)an * a.Kp + p);
+                    float4 hi, lo;
+                    split_tf32(x, hi, lo);
+                    const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
-                for (int i2 = 0; i2 < 2; ++i2) {
-                    const int ul = rsub + 16 * i2;
-                    const int u = k0 + ul;
-                    const int an = (u < rows) ? (tail ? __ldg(a.u_e1 + u0 + u) : __ldg(a.u_e2 + u0 + u)) : -1;
-                    const uint32_t rowoff = (ul >> 3) * 1024 + (ul & 7) * 128 + ((j ^ (ul & 7)) << 4);
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) {                                  // A: p = m0 + mi*32 + j*4
-                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const int p = m0 + mi * 32 + j * 4;
-                        if (an >= 0 && p < a.Kp) x = ldg4g(a.E + (size_t)an * a.Kp + p);
-                        float4 hi, lo;
-                        split_tf32(x, hi, lo);
-                        sts4(sA_hi, mi * 4096 + rowoff, hi); sts4(sA_lo, mi * 4096 + rowoff, lo);
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t row = 4 * c + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
+                        *reinterpret_cast<float*>(sA_hi + off) = hv[e];
+                        *reinterpret_cast<float*>(sA_lo + off) = lv[e];
                     }
-                    for (int ni = 0; ni * 32 < nlen; ++ni) {                          // B: n = n0 + ni*32 + j*4
-                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const int n = ni * 32 + j * 4;
-                        if (an >= 0 && n < nlen) x = ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + n);
-                        float4 hi, lo;
-                        split_tf32(x, hi, lo);
-                        sts4(sB_hi, ni * 4096 + rowoff, hi); sts4(sB_lo, ni * 4096 + rowoff, lo);
+                }
+                for (int c = warp; 4 * c < nlen; c += 4) {                            // B rows: n = n0 + 4c + e
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (an >= 0) x = ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + 4 * c);
+                    float4 hi, lo;
+                    split_tf32(x, hi, lo);
+                    const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t row = 4 * c + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
+                        *reinterpret_cast<float*>(sB_hi + off) = hv[e];
+                        *reinterpret_cast<float*>(sB_lo + off) = lv[e];
                     }
                 }
             }
@@ -289,7 +297,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
         tc_fence_before();
     } else {
         // ================================ MMA issuer ================================
-        const uint32_t idesc = make_idesc(nlen, MODE == TC_DW, MODE == TC_DW);
+        const uint32_t idesc = make_idesc(nlen, 0, 0);
         bool alive = true;
         for (int kb = 0; kb < nkb && alive; ++kb) {
             const int s = kb % TC_STAGES;
@@ -302,14 +310,9 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                 const int kleft = kext - kb * TC_BK;
                 const int nks = (kleft >= TC_BK) ? 4 : (kleft + 7) / 8;
                 for (int ks = 0; ks < nks; ++ks) {
-                    uint64_t dAh, dAl, dBh, dBl;
-                    if (MODE == TC_DW) {             // MN-major: k-step = one 8-row group (1024 B); atoms 4096 B apart
-                        dAh = make_desc(sA_hi + ks * 1024, 4096, 1024); dAl = make_desc(sA_lo + ks * 1024, 4096, 1024);
-                        dBh = make_desc(sB_hi + ks * 1024, 4096, 1024); dBl = make_desc(sB_lo + ks * 1024, 4096, 1024);
-                    } else {                         // K-major: k-step = 32 bytes inside the swizzle row; 8-row groups 1024 B apart
-                        dAh = make_desc(sA_hi + ks * 32, 16, 1024); dAl = make_desc(sA_lo + ks * 32, 16, 1024);
-                        dBh = make_desc(sB_hi + ks * 32, 16, 1024); dBl = make_desc(sB_lo + ks * 32, 16, 1024);
-                    }
+                    // K-major: a k-step is 32 bytes inside the 128-byte swizzle row; 8-row groups are 1024 B apart
+                    const uint64_t dAh = make_desc(sA_hi + ks * 32, 16, 1024), dAl = make_desc(sA_lo + ks * 32, 16, 1024);
+                    const uint64_t dBh = make_desc(sB_hi + ks * 32, 16, 1024), dBl = make_desc(sB_lo + ks * 32, 16, 1024);
                     const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
                     umma_tf32(tmem_base, dAl, dBh, idesc, first);      // small terms first
                     umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
