@@ -202,59 +202,90 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
             uint8_t* sB_hi = sA_lo + TC_A_BYTES;
             uint8_t* sB_lo = sB_hi + TC_B_BYTES;
             const int k0 = kb * TC_BK;
+            constexpr int BROWS = TC_NCH / 16;                                       // B rows per thread (K-major loads)
             if (MODE == TC_FWD || MODE == TC_GE) {
+                // all global loads of this k-block are issued first (latency overlaps), then split + store
+                float4 xa[8], xbh[BROWS], xbl[BROWS];
+                const int kk = k0 + j * 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = rsub + 16 * i;
+                    xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MODE == TC_FWD) { if (anchor[i] >= 0 && kk < a.Kp) xa[i] = ldg4g(a.E + (size_t)anchor[i] * a.Kp + kk); }
+                    else { if (row < rows && kk < a.Np) xa[i] = ldg4g(a.M + (size_t)(u0 + row) * a.Np + kk); }
+                }
+#pragma unroll
+                for (int i = 0; i < BROWS; ++i) {
+                    const int row = rsub + 16 * i;
+                    if (row < nlen) {
+                        const size_t g = (size_t)(n0 + row) * ldb + kk;
+                        xbh[i] = ldg4g(Bhi + g); xbl[i] = ldg4g(Blo + g);
+                    }
+                }
                 // ---- A: K-major, 128 rows x 128 bytes, chunk j of row `row` at row*128 + ((j ^ (row&7))<<4)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int row = rsub + 16 * i;
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int kk = k0 + j * 4;
-                    if (MODE == TC_FWD) { if (anchor[i] >= 0 && kk < a.Kp) x = ldg4g(a.E + (size_t)anchor[i] * a.Kp + kk); }
-                    else { if (row < rows && kk < a.Np) x = ldg4g(a.M + (size_t)(u0 + row) * a.Np + kk); }
                     float4 hi, lo;
-                    split_tf32(x, hi, lo);
+                    split_tf32(xa[i], hi, lo);
                     const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
                     sts4(sA_hi, off, hi); sts4(sA_lo, off, lo);
                 }
                 // ---- B: K-major, nlen rows (n resp. p) x 128 bytes, from the pre-split weight arrays
-                for (int row = rsub; row < nlen; row += 16) {
-                    const size_t g = (size_t)(n0 + row) * ldb + k0 + j * 4;
-                    const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
-                    sts4(sB_hi, off, ldg4g(Bhi + g)); sts4(sB_lo, off, ldg4g(Blo + g));
+#pragma unroll
+                for (int i = 0; i < BROWS; ++i) {
+                    const int row = rsub + 16 * i;
+                    if (row < nlen) {
+                        const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+                        sts4(sB_hi, off, xbh[i]); sts4(sB_lo, off, xbl[i]);
+                    }
                 }
             } else {
                 // ---- dw: the contraction runs over the ROW index u of both operands, so the producers
                 //      transpose while storing: lane = u row of this k-block (K index), warps stride over the
                 //      16-byte column chunks.  For a fixed chunk and component the 32 lanes hit 32 different
                 //      banks (8 swizzled k-chunks x 4 words), so the 4-byte stores are conflict-free.
+                constexpr int BCH = TC_NCH / 16;                                      // B column chunks per thread
                 const int ul = lane, u = k0 + ul;
                 const int an = (u < rows) ? (tail ? __ldg(a.u_e1 + u0 + u) : __ldg(a.u_e2 + u0 + u)) : -1;
                 const uint32_t kc = ul >> 2, ke = (ul & 3) * 4;
-                for (int c = warp; c < 32; c += 4) {                                  // A rows: p = m0 + 4c + e
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int p = m0 + 4 * c;
-                    if (an >= 0 && p < a.Kp) x = ldg4g(a.E + (size_t)an * a.Kp + p);
+                float4 xa[8], xb[BCH];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {                                         // A rows: p = m0 + 4c + e
+                    const int p = m0 + 4 * (warp + 4 * i);
+                    xa[i] = (an >= 0 && p < a.Kp) ? ldg4g(a.E + (size_t)an * a.Kp + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < BCH; ++i) {                                       // B rows: n = n0 + 4c + e
+                    const int c = warp + 4 * i;
+                    xb[i] = (an >= 0 && 4 * c < nlen) ? ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + 4 * c)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
                     float4 hi, lo;
-                    split_tf32(x, hi, lo);
+                    split_tf32(xa[i], hi, lo);
                     const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const uint32_t row = 4 * c + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
+                        const uint32_t row = 4 * (warp + 4 * i) + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
                         *reinterpret_cast<float*>(sA_hi + off) = hv[e];
                         *reinterpret_cast<float*>(sA_lo + off) = lv[e];
                     }
                 }
-                for (int c = warp; 4 * c < nlen; c += 4) {                            // B rows: n = n0 + 4c + e
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (an >= 0) x = ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + 4 * c);
-                    float4 hi, lo;
-                    split_tf32(x, hi, lo);
-                    const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t row = 4 * c + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
-                        *reinterpret_cast<float*>(sB_hi + off) = hv[e];
-                        *reinterpret_cast<float*>(sB_lo + off) = lv[e];
+                for (int i = 0; i < BCH; ++i) {
+                    const int c = warp + 4 * i;
+                    if (4 * c < nlen) {
+                        float4 hi, lo;
+                        split_tf32(xb[i], hi, lo);
+                        const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t row = 4 * c + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
+                            *reinterpret_cast<float*>(sB_hi + off) = hv[e];
+                            *reinterpret_cast<float*>(sB_lo + off) = lv[e];
+                        }
                     }
                 }
             }

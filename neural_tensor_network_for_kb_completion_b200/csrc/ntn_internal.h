@@ -29,7 +29,7 @@ struct NtnDims {
 };
 
 #define NTN_TILE_ROWS   128      // unique triples per contraction tile (one relation per tile)
-#define NTN_CHUNK_ROWS  512      // unique triples per dW split-K chunk (one relation per chunk)
+#define NTN_CHUNK_ROWS  256      // unique triples per dW split-K chunk (one relation per chunk)
 #define NTN_SCORE_ROWS  32       // unique triples per score tile (8 warps x 4)
 #define NTN_HUB_SEG     32       // incident-list segment length for hub words / hub entities
 #define NTN_RING        8        // in-flight evaluations the host may enqueue without synchronising
