@@ -287,12 +287,30 @@ struct ScoreArgs {
     int64_t oU;
 };
 
+// Transpose-reduce: every lane holds 32 partial sums v[0..31]; afterwards v[0] on lane l is the
+// warp-wide total of partial sum number l.  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = up ? v[i] : v[i + o];
+            const float keep = up ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, o);
+        }
+    }
+}
+
 template <int KS, int CH, int ACT>
-__global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
-    constexpr int PAIR = (KS * CH <= 6) ? 2 : 1;       // corrupt columns in flight per warp (ILP)
+__global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
+    // corrupt columns per batch: their KS pre-activations each fill the 32 lanes (KS=3 -> 10 columns,
+    // the reference's corrupt_size); all row gathers of a batch are issued before any is used.
+    constexpr int COLB = (CH == 1) ? ((32 / KS) < 10 ? (32 / KS) : 10) : ((16 / KS) < 1 ? 1 : ((16 / KS) < 5 ? (16 / KS) : 5));
+    constexpr int V = COLB * KS;
     __shared__ double s_cost[8];
     __shared__ int s_nact[8];
-    __shared__ float s_dU[8][KS];
+    __shared__ float s_dU[8][32];
     const int tile = blockIdx.x;
     const int r = a.t_rel[tile], u0 = a.t_u0[tile], rows = a.t_n[tile];
     const bool tail = a.side[r] != 0;
@@ -301,7 +319,10 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
     float U[KS];
 #pragma unroll
     for (int s = 0; s < KS; ++s) U[s] = __ldg(a.theta + a.oU + (int64_t)r * KS + s);
-    // per-lane chunk validity and tail mask (elements >= d inside the last float4 are dropped)
+    const int my_s = lane % KS, my_j = lane / KS;       // lane l owns (column my_j, slice my_s) of a batch
+    const float my_U = U[0] * (my_s == 0) + [&] { float t = 0.f;
+#pragma unroll
+        for (int s = 1; s < KS; ++s) t += U[s] * (my_s == s); return t; }();
     bool cv[CH]; float4 cm[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -309,9 +330,8 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
         cv[c] = p < dq;
         cm[c] = make_float4(p < d ? 1.f : 0.f, p + 1 < d ? 1.f : 0.f, p + 2 < d ? 1.f : 0.f, p + 3 < d ? 1.f : 0.f);
     }
-    double cost_w = 0.0; int nact_w = 0; float dU_w[KS];
-#pragma unroll
-    for (int s = 0; s < KS; ++s) dU_w[s] = 0.f;
+    // lane-local accumulators, reduced once at the end of the tile
+    float cost_l = 0.f, dU_l = 0.f; int nact_w = 0;
 
     for (int i = warp; i < rows; i += 8) {
         const int u = u0 + i;
@@ -325,6 +345,9 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
             for (int c = 0; c < CH; ++c) t[s][c] = cv[c] ? ldg4(Trow + s * dq + (lane + 32 * c) * 4) : zero4();
             beta[s] = __ldg(Trow + KS * dq + s);
         }
+        float my_beta = 0.f;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) my_beta += beta[s] * (my_s == s);
         float4 eo[CH];
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
@@ -345,13 +368,21 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
             for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
                 for (int s = 0; s < KS; ++s) acc[s] += __shfl_xor_sync(FULL, acc[s], o);
+            // lane s evaluates the activation of slice s, then everyone reads all KS of them
+            float mine = 0.f;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) mine += (acc[s] + beta[s]) * (lane == s);
+            const float zmine = act_fn<ACT>(mine);
 #pragma unroll
             for (int s = 0; s < KS; ++s) {
-                zp[s] = act_fn<ACT>(acc[s] + beta[s]);
+                zp[s] = __shfl_sync(FULL, zmine, s);
                 sp = fmaf(U[s], zp[s], sp);                           // :204
                 tp[s] = act_diff<ACT>(zp[s]) * U[s];                  // :280
             }
         }
+        float my_zp = 0.f;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) my_zp += zp[s] * (my_s == s);
         float4 Macc[KS][CH]; float csum[KS];
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
@@ -360,65 +391,53 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
             for (int c = 0; c < CH; ++c) Macc[s][c] = zero4();
         }
         int cnt = 0;
-        for (int col = c0; col < c1; col += PAIR) {
-            float4 ev[PAIR][CH]; float acc[PAIR][KS];
+        for (int col = c0; col < c1; col += COLB) {
+            const int nb = min(COLB, c1 - col);
+            float4 ev[COLB][CH];
 #pragma unroll
-            for (int j = 0; j < PAIR; ++j) {
-                const bool ok = col + j < c1;
+            for (int j = 0; j < COLB; ++j) {
+                const bool ok = j < nb;
                 const int e3 = ok ? __ldg(a.c_e3 + col + j) : 0;
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
+                for (int c = 0; c < CH; ++c)
                     ev[j][c] = (ok && cv[c]) ? ldg4(a.E + (size_t)e3 * a.Kp + (lane + 32 * c) * 4) : zero4();
+            }
+            float v[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = 0.f;
+#pragma unroll
+            for (int j = 0; j < COLB; ++j)
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
                     ev[j][c].x *= cm[c].x; ev[j][c].y *= cm[c].y; ev[j][c].z *= cm[c].z; ev[j][c].w *= cm[c].w;
-                }
-            }
 #pragma unroll
-            for (int j = 0; j < PAIR; ++j)
+                    for (int s = 0; s < KS; ++s) v[j * KS + s] += dot4(t[s][c], ev[j][c]);
+                }
+            warp_transpose_reduce32(v, lane);                          // lane l: pre-activation (my_j, my_s)
+            const bool mine_valid = lane < V && my_j < nb;
+            const float zn = act_fn<ACT>(v[0] + my_beta);              // one activation per lane
+            // negative score of column j = sum over its KS lanes (NTN.java:205)
+            float sn = my_U * zn;
+#pragma unroll
+            for (int s = 1; s < KS; ++s) sn += __shfl_down_sync(FULL, my_U * zn, s);
+            const bool active_here = mine_valid && my_s == 0 && ((sp + 1.0f) > sn);   // :213 (strict, FP32)
+            const unsigned amask = __ballot_sync(FULL, active_here);   // bit j*KS = column j active
+            const bool my_active = mine_valid && ((amask >> (my_j * KS)) & 1u);
+            if (active_here) cost_l += (sp - sn) + 1.0f;               // :221
+            const int na = __popc(amask);
+            nact_w += na; cnt += na;                                   // :222
+            const float my_cc = my_active ? -act_diff<ACT>(zn) * my_U : 0.f;          // :281
+            if (my_active) dU_l += my_zp - zn;                         // :273
+            if (mine_valid) a.ccoef[(size_t)col * KS + lane] = my_cc;  // coalesced: (col+j)*KS + s = col*KS + lane
+#pragma unroll
+            for (int j = 0; j < COLB; ++j)
 #pragma unroll
                 for (int s = 0; s < KS; ++s) {
-                    acc[j][s] = 0.f;
+                    const float cc = __shfl_sync(FULL, my_cc, j * KS + s);
+                    csum[s] += cc;
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) acc[j][s] += dot4(t[s][c], ev[j][c]);
+                    for (int c = 0; c < CH; ++c) fma4(Macc[s][c], cc, ev[j][c]);
                 }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int j = 0; j < PAIR; ++j)
-#pragma unroll
-                    for (int s = 0; s < KS; ++s) acc[j][s] += __shfl_xor_sync(FULL, acc[j][s], o);
-#pragma unroll
-            for (int j = 0; j < PAIR; ++j) {
-                if (col + j >= c1) break;
-                float zn[KS], sn = 0.f;
-#pragma unroll
-                for (int s = 0; s < KS; ++s) {
-                    zn[s] = act_fn<ACT>(acc[j][s] + beta[s]);
-                    sn = fmaf(U[s], zn[s], sn);                       // :205
-                }
-                const bool active = (sp + 1.0f) > sn;                 // :213 (strict, FP32)
-                float cc[KS];
-                if (active) {
-                    cost_w += (double)((sp - sn) + 1.0f);             // :221
-                    ++nact_w; ++cnt;                                  // :222
-#pragma unroll
-                    for (int s = 0; s < KS; ++s) {
-                        dU_w[s] += zp[s] - zn[s];                     // :273
-                        cc[s] = -act_diff<ACT>(zn[s]) * U[s];         // :281
-                        csum[s] += cc[s];
-#pragma unroll
-                        for (int c = 0; c < CH; ++c) fma4(Macc[s][c], cc[s], ev[j][c]);
-                    }
-                } else {
-#pragma unroll
-                    for (int s = 0; s < KS; ++s) cc[s] = 0.f;
-                }
-                if (lane < KS) {
-                    float v = 0.f;
-#pragma unroll
-                    for (int s = 0; s < KS; ++s) if (s == lane) v = cc[s];
-                    a.ccoef[(size_t)(col + j) * KS + lane] = v;
-                }
-            }
         }
         float* Mrow = a.M + (size_t)u * a.Np;
 #pragma unroll
@@ -434,27 +453,29 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
         }
         // coefficient sums ride in the k slots after the slices; zero the rest of the row
         for (int n = KS * dq + lane; n < a.Np; n += 32) {
-            float v = 0.f;
+            float vv = 0.f;
 #pragma unroll
-            for (int s = 0; s < KS; ++s) if (n == KS * dq + s) v = csum[s];
-            Mrow[n] = v;
+            for (int s = 0; s < KS; ++s) if (n == KS * dq + s) vv = csum[s];
+            Mrow[n] = vv;
         }
     }
-    if (lane == 0) {
-        s_cost[warp] = cost_w; s_nact[warp] = nact_w;
+    // tile partials, fixed order: lanes, then warps
+    double cost_w = (double)cost_l;
 #pragma unroll
-        for (int s = 0; s < KS; ++s) s_dU[warp][s] = dU_w[s];
-    }
+    for (int o = 16; o > 0; o >>= 1) cost_w += __shfl_xor_sync(FULL, cost_w, o);
+    s_dU[warp][lane] = dU_l;
+    if (lane == 0) { s_cost[warp] = cost_w; s_nact[warp] = nact_w; }
     __syncthreads();
-    if (threadIdx.x == 0) {                                           // fixed order: deterministic
+    if (threadIdx.x == 0) {
         double c = 0.0; int n = 0;
         for (int w = 0; w < 8; ++w) { c += s_cost[w]; n += s_nact[w]; }
         a.tp_cost[tile] = c; a.tp_nact[tile] = n;
     }
     if (threadIdx.x < KS) {
-        float v = 0.f;
-        for (int w = 0; w < 8; ++w) v += s_dU[w][threadIdx.x];
-        a.tp_dU[(size_t)tile * KS + threadIdx.x] = v;
+        float vv = 0.f;
+        for (int w = 0; w < 8; ++w)
+            for (int l = threadIdx.x; l < V; l += KS) vv += s_dU[w][l];   // lanes that own this slice
+        a.tp_dU[(size_t)tile * KS + threadIdx.x] = vv;
     }
 }
 
