@@ -217,23 +217,26 @@ def main():
     kb = build_problem(world)
     hbm_peak, tf_peak, peak_kind = peaks()
 
-    # two batch jobs per rank (rotated between steps), each the rank's shard of the global batch
-    handles, sides = [], []
+    # two batch jobs (rotated between steps).  N > 1: ONE global batch job of world*BATCH triples (same
+    # e3 stream on every rank), sharded by unique triple round-robin within each relation
+    from neural_tensor_network_for_kb_completion_b200.distributed import shard_columns
+    handles, sides, results = [], [], []
     set_batch_ms = []
     for j in range(2):
-        tbj = DataFactory.from_kb(kb, BATCH, CORRUPT, seed=42 + 1000 * j + rank)
+        tbj = DataFactory.from_kb(kb, BATCH * world, CORRUPT, seed=42 + 1000 * j)
         h = _capi.Handle(D, K_SLICES, kb.R, kb.Ne, kb.Nw, BATCH * world, LAMBDA, wv_source=args.wv_source,
                          gemm_path=args.gemm_path, device=local_rank, reg_scale=1.0 / world)
         maps = tbj.entityWordMaps()
         h.set_entity_words(*maps)
         if args.wv_source == "frozen":
             h.set_frozen_wv(kb.wv)
-        bj = tbj.generateNewTrainingBatchJob(first=rank * BATCH if world > 1 else 0)
+        bj = shard_columns(*tbj.generateNewTrainingBatchJob(), rank, world)
         t0 = time.perf_counter()
         h.set_batch(*bj)
         set_batch_ms.append(1e3 * (time.perf_counter() - t0))
         h.set_stream(stream.cuda_stream)
         handles.append(h)
+        results.append(h.result_tensor())
         sr = JavaRandom(7 + j)
         present = np.zeros(kb.R, bool); present[np.unique(bj[1])] = True
         sides.append(np.array([1 if (present[r] and sr.nextDouble() > 0.5) else 0 for r in range(kb.R)], np.uint8))
@@ -257,6 +260,7 @@ def main():
         h.eval_dev(thetas[j].data_ptr(), sides[j], grads[j].data_ptr(), sync=False)
         if dist is not None:
             dist.all_reduce(grads[j])                       # every rank ends with the full-batch gradient
+            dist.all_reduce(results[j])                     # ... and the full-batch cost / n_active
         if sync:
             torch.cuda.synchronize()
 
@@ -289,6 +293,9 @@ def main():
             phase[kname] = phase.get(kname, 0.0) + v / len(handles)
         h.set_profiling(False)
     cost, nact = handles[(args.steps - 1) & 1].last_cost()
+    if dist is not None:
+        rr = results[(args.steps - 1) & 1].cpu().numpy()
+        cost, nact = float(rr[0]), int(round(float(rr[1])))
     if dist is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -343,6 +350,20 @@ def main():
             ach = groups[top]["bytes"] / tsec / 1e9
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                         "frac": ach / hbm_peak, "traffic": None, "peak_note": f"{peak_kind} copy bandwidth"}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f)
+            kmap = {"score": "k_score<3, 1, 0>", "gemm_fwd": "k_tc_gemm<0>", "gemm_dw": "k_tc_gemm<1>",
+                    "gemm_ge": "k_tc_gemm<2>", "entity_pull": "k_entity_pull<3>"}
+            if top == "word_pull":
+                roofline["traffic"] = tr["k_word_pull"]["dram_bytes_per_launch"] + tr["k_word_pull_hub"]["dram_bytes_per_launch"]
+            elif top in kmap:
+                roofline["traffic"] = tr[kmap[top]]["dram_bytes_per_launch"]
+            roofline["traffic_note"] = "dram__bytes_read+write per launch from profiles/r1_ncu_full_summary.txt (N=1 ncu capture)"
+        except Exception:
+            pass
+        roofline["algorithmic_bytes"] = groups[top]["bytes"]
+        roofline["algorithmic_flops"] = groups[top]["flops"]
         roofline["ms"] = phase[top]
         roofline["share_of_step"] = phase[top] / max(sum(phase.values()), 1e-9)
     per_group = {kname: {"ms": v, "GB/s": groups[kname]["bytes"] / (v * 1e-3) / 1e9 if v > 0 else None,

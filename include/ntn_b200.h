@@ -124,6 +124,9 @@ int ntn_eval_f32(ntn_handle* h, const float* theta, const uint8_t* corrupt_side,
 int ntn_eval_dev(ntn_handle* h, const float* d_theta, const uint8_t* corrupt_side,
                  float* d_grad, double* cost, int64_t* n_active);
 int ntn_last_cost(ntn_handle* h, double* cost, int64_t* n_active);   /* synchronises */
+/* DEVICE pointer to the last evaluation's 4 doubles {cost, n_active, data term, sum theta^2}: lets a
+ * data-parallel host all-reduce the scalars on the device together with the gradient. */
+double* ntn_result_dev(ntn_handle* h);
 
 int64_t ntn_internal_dimension(const ntn_handle* h);
 /* reference-order FP32 device vector (P) <-> internal-order device vector */

@@ -50,6 +50,7 @@ SYMBOLS = {
     "ntn_eval_f32": (C.c_int, [_P, _P, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int64)]),
     "ntn_eval_dev": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ntn_last_cost": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "ntn_result_dev": (_P, [_P]),
     "ntn_internal_dimension": (C.c_int64, [_P]),
     "ntn_to_internal_dev": (C.c_int, [_P, _P, _P]),
     "ntn_from_internal_dev": (C.c_int, [_P, _P, _P]),
@@ -183,6 +184,17 @@ class Handle:
         cost, nact = C.c_double(), C.c_int64()
         self._ck(self.lib.ntn_last_cost(self.h, C.byref(cost), C.byref(nact)))
         return cost.value, nact.value
+
+    def result_tensor(self):
+        """torch view (4 float64, on the device) of {cost, n_active, data term, sum theta^2}."""
+        import torch
+
+        class _Buf:
+            pass
+        b = _Buf()
+        b.__cuda_array_interface__ = {"shape": (4,), "typestr": "<f8", "data": (int(self.lib.ntn_result_dev(self.h)), False),
+                                      "version": 2, "strides": None}
+        return torch.as_tensor(b, device="cuda")
 
     def to_internal_dev(self, d_ref: int, d_int: int):
         self._ck(self.lib.ntn_to_internal_dev(self.h, d_ref, d_int))

@@ -468,6 +468,8 @@ extern "C" int ntn_last_cost(ntn_handle* h, double* cost, int64_t* n_active) {
     return NTN_OK;
 }
 
+extern "C" double* ntn_result_dev(ntn_handle* h) { return h ? h->d_out : nullptr; }
+
 extern "C" int ntn_last_phase_ms(ntn_handle* h, float* ms) {
     if (!h || !ms) return NTN_EINVAL;
     for (int s = 0; s < NTN_RING; ++s) drain_profile_slot(h, s);

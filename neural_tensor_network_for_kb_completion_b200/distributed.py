@@ -1,0 +1,78 @@
+"""Data-parallel evaluation of NTN.computeAt over the GPUs of one box.
+
+Every batch column contributes independently to cost and gradient given theta
+(/root/reference/src/NTN.java:114-409 is a sum over columns, :411-430 is linear in the entity
+gradient), so the batch job is sharded and the per-rank results are summed:
+
+  * unique training triples are dealt round-robin *within each relation* (every rank gets
+    n_r/G triples of every relation -> equal grouped-contraction shapes), each triple keeps all of
+    its corrupt copies (the de-duplication of DESIGN.md §3 survives);
+  * every rank evaluates its shard with reg_scale = 1/G and batch_divisor = the GLOBAL batch size,
+    so that ONE all-reduce(SUM) of [gradient | cost | n_active] is the full-batch result on every
+    rank (the regulariser is counted G times at weight 1/G);
+  * corrupt_side[r] is drawn once (rank 0's stream) and broadcast, like the reference's single
+    Math.random() per relation per evaluation (NTN.java:146).
+
+One process per GPU; torch.distributed is the plumbing (NCCL over NVLink on GPUs, gloo in the CPU
+tests).  The local evaluator is injected, so the same class drives the CUDA handle and the test's
+CPU evaluator.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_columns(e1, rel, e2, e3, rank: int, world: int):
+    """Columns of this rank: unique (rel, e1, e2) triples round-robin within their relation, in
+    order of first appearance, all corrupt copies of a triple on the same rank."""
+    e1, rel, e2, e3 = (np.asarray(x) for x in (e1, rel, e2, e3))
+    if world == 1:
+        return e1, rel, e2, e3
+    key = (rel.astype(np.int64) << 42) | (e1.astype(np.int64) << 21) | e2.astype(np.int64)
+    uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    # order unique triples by first appearance inside their relation
+    u_rel = rel[first]
+    order = np.lexsort((first, u_rel))
+    pos_in_rel = np.empty(len(uniq), np.int64)
+    sorted_rel = u_rel[order]
+    starts = np.r_[0, np.nonzero(np.diff(sorted_rel))[0] + 1]
+    start_of = np.repeat(starts, np.diff(np.r_[starts, len(order)]))
+    pos_in_rel[order] = np.arange(len(order)) - start_of
+    sel = (pos_in_rel[inv] % world) == rank
+    return e1[sel], rel[sel], e2[sel], e3[sel]
+
+
+class DataParallelNTN:
+    """computeAt over `world` ranks.  ``local_eval(theta, corrupt_side) -> (cost, grad, n_active)``
+    evaluates this rank's shard (grad: torch tensor on the rank's device, already including the
+    1/G-scaled regulariser)."""
+
+    def __init__(self, local_eval, num_relations: int, rank: int, world: int, draw_sides=None):
+        import torch.distributed as dist
+        self.dist, self.local_eval = dist, local_eval
+        self.R, self.rank, self.world = num_relations, rank, world
+        self.draw_sides = draw_sides
+
+    def broadcast_sides(self, side=None):
+        import torch
+        t = torch.zeros(self.R, dtype=torch.uint8)
+        if self.rank == 0:
+            s = self.draw_sides() if side is None else side
+            t = torch.from_numpy(np.ascontiguousarray(s, np.uint8)).clone()
+        if self.world > 1:
+            backend = self.dist.get_backend()
+            if backend == "nccl":
+                t = t.cuda()
+            self.dist.broadcast(t, src=0)
+        return t.cpu().numpy()
+
+    def computeAt(self, theta, corrupt_side=None):
+        import torch
+        side = self.broadcast_sides(corrupt_side)
+        cost, grad, nact = self.local_eval(theta, side)
+        if self.world > 1:
+            self.dist.all_reduce(grad)                                    # the one data-path collective
+            sc = torch.tensor([cost, float(nact)], dtype=torch.float64, device=grad.device)
+            self.dist.all_reduce(sc)
+            cost, nact = float(sc[0]), int(round(float(sc[1])))
+        return cost, grad, nact
