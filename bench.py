@@ -155,7 +155,7 @@ def run_reference(args):
     cores = os.cpu_count()
     val = trip / tt
     sample = f"per step: all columns of {m} of {kb.R} relations (rotating) of the 20,000x10 batch, float32 NumPy/OpenBLAS/SciPy"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "NTN cost+grad triples/sec (Freebase shape)", "value": val, "unit": "triples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -164,7 +164,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "oracle port of the reference formulation (NTN.java:92-443); the ND4j/JVM reference cannot run in this image",
-    }))
+    })
 
 
 def workload_config(kb, n_ranks, wv_source):
@@ -178,7 +178,21 @@ def workload_config(kb, n_ranks, wv_source):
                          "(~190 MB) exceeds the 126 MB L2"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The contract is ONE JSON line on stdout; libraries (NCCL's version banner) write there too,
+    so fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -413,7 +427,7 @@ def main():
             "roofline": roofline, "phase": per_group, "eval_roofline": eval_roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        emit(out)
     for h in handles:
         h.close()
     if dist is not None:

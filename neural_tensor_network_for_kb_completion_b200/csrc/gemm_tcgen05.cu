@@ -465,11 +465,11 @@ void ntn_tc_release(ntn_handle* h) {
     h->tc = nullptr;
 }
 
-int ntn_tc_w_prep(ntn_handle* h, const float* theta) {
+int ntn_tc_w_prep(ntn_handle* h, const float* theta, cudaStream_t stq) {
     TcState* st = (TcState*)h->tc;
     const NtnDims& dm = h->dm;
     int64_t n = (int64_t)dm.R * dm.Np * st->KpP + (int64_t)dm.R * st->KpN * st->NpP;
-    k_tc_w_prep<<<cdivi(n, 256), 256, 0, h->stream>>>(theta, h->side, st->WT_hi, st->WT_lo, st->W_hi, st->W_lo, dm,
+    k_tc_w_prep<<<cdivi(n, 256), 256, 0, stq>>>(theta, h->side, st->WT_hi, st->WT_lo, st->W_hi, st->W_lo, dm,
                                                       st->KpP, st->KpN, st->NpP);
     h->launches++;
     return NTN_OK;
@@ -483,10 +483,10 @@ int ntn_tc_gemm_fwd(ntn_handle* h) {
     return NTN_OK;
 }
 
-int ntn_tc_gemm_dw(ntn_handle* h) {
+int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t stq) {
     TcArgs a = tc_args(h, true);
     dim3 g(h->b.nchunks, cdivi(h->dm.Np, TC_NCH), cdivi(h->dm.Kp, 128));
-    k_tc_gemm<TC_DW><<<g, 160, TC_SMEM_BYTES, h->stream>>>(a);
+    k_tc_gemm<TC_DW><<<g, 160, TC_SMEM_BYTES, stq>>>(a);
     h->launches++;
     return NTN_OK;
 }

@@ -14,9 +14,9 @@ int ntn_word_blocks(const NtnDims& dm);
 int ntn_tc_supported(const ntn_handle* h);                     // gemm_tcgen05.cu
 int ntn_tc_prepare_batch(ntn_handle* h);
 void ntn_tc_release(ntn_handle* h);
-int ntn_tc_w_prep(ntn_handle* h, const float* theta);
+int ntn_tc_w_prep(ntn_handle* h, const float* theta, cudaStream_t st);
 int ntn_tc_gemm_fwd(ntn_handle* h);
-int ntn_tc_gemm_dw(ntn_handle* h);
+int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t st);
 int ntn_tc_gemm_ge(ntn_handle* h);
 int ntn_tc_check_error(ntn_handle* h);
 
@@ -114,6 +114,11 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
     }
     CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&h->ev_f0, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_j0, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_f1, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_j1, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->stream = h->own_stream;
@@ -129,7 +134,7 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
     CKC(cudaMalloc((void**)&h->d_out, 4 * sizeof(double)));
     CKC(cudaMallocHost((void**)&h->h_out, 4 * sizeof(double)));
     for (int s = 0; s < NTN_RING; ++s)
-        for (int i = 0; i <= NTN_NUM_PHASES; ++i) CKC(cudaEventCreate(&h->ev[s][i]));
+        for (int i = 0; i < NTN_NUM_PHASES; ++i) { CKC(cudaEventCreate(&h->ev[s][i][0])); CKC(cudaEventCreate(&h->ev[s][i][1])); }
 #undef CKC
     *out = h;
     return NTN_OK;
@@ -164,11 +169,13 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     if (h->h_stage) cudaFreeHost(h->h_stage);
     for (int s = 0; s < NTN_RING; ++s) {
         if (h->side_ev[s]) cudaEventDestroy(h->side_ev[s]);
-        for (int i = 0; i <= NTN_NUM_PHASES; ++i) if (h->ev[s][i]) cudaEventDestroy(h->ev[s][i]);
+        for (int i = 0; i < NTN_NUM_PHASES; ++i) for (int q = 0; q < 2; ++q) if (h->ev[s][i][q]) cudaEventDestroy(h->ev[s][i][q]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (cudaEvent_t e : {h->ev_f0, h->ev_j0, h->ev_f1, h->ev_j1}) if (e) cudaEventDestroy(e);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -194,10 +201,10 @@ extern "C" void* ntn_get_stream(ntn_handle* h) { return h ? (void*)h->stream : n
 // fold the event pairs of ring slot s into the per-phase accumulators (waits for that evaluation)
 static void drain_profile_slot(ntn_handle* h, int s) {
     if (!h->ev_pending[s]) return;
-    cudaEventSynchronize(h->ev[s][NTN_NUM_PHASES]);
     for (int i = 0; i < NTN_NUM_PHASES; ++i) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->ev[s][i], h->ev[s][i + 1]) == cudaSuccess) h->phase_acc[i] += ms;
+        cudaEventSynchronize(h->ev[s][i][1]);
+        if (cudaEventElapsedTime(&ms, h->ev[s][i][0], h->ev[s][i][1]) == cudaSuccess) h->phase_acc[i] += ms;
     }
     h->phase_n++;
     h->ev_pending[s] = false;
@@ -427,31 +434,48 @@ static int eval_internal(ntn_handle* h, const float* d_theta, const uint8_t* cor
     const bool prof = h->profiling;
     const int slot = h->ring_pos;
     h->ring_pos = (slot + 1) % NTN_RING;
-    int pe = 0;
     if (prof) drain_profile_slot(h, slot);
-    auto mark = [&]() { if (prof) cudaEventRecord(h->ev[slot][pe++], h->stream); };
+    // phase p runs on stream st: bracket it with its own event pair (phases on forked streams overlap)
+    auto begin = [&](int p, cudaStream_t st) { if (prof) cudaEventRecord(h->ev[slot][p][0], st); };
+    auto end = [&](int p, cudaStream_t st) { if (prof) cudaEventRecord(h->ev[slot][p][1], st); };
+    enum { P_EB, P_WP, P_FWD, P_SC, P_DW, P_GE, P_EP, P_WPULL, P_FIN };
     // pinned ring slot: wait only for the evaluation that used this slot NTN_RING calls ago
     CK(cudaEventSynchronize(h->side_ev[slot]));
     uint8_t* hs = h->h_side + (size_t)slot * dm.R;
     for (int r = 0; r < dm.R; ++r) hs[r] = corrupt_side[r] ? 1 : 0;
-    CK(cudaMemcpyAsync(h->side, hs, dm.R, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaEventRecord(h->side_ev[slot], h->stream));
+    cudaStream_t s0 = h->stream, s1 = h->stream3;
+    CK(cudaMemcpyAsync(h->side, hs, dm.R, cudaMemcpyHostToDevice, s0));
+    CK(cudaEventRecord(h->side_ev[slot], s0));
     const bool tc = h->gemm_path_active == NTN_GEMM_TCGEN05 && h->b.ntiles > 0;
     int rc;
-    mark(); ntn_launch_entity_build(h, wvt);                               // NTN.java:103
-    mark();
-    if (tc) { if ((rc = ntn_tc_w_prep(h, d_theta))) return rc; } else ntn_launch_w_prep(h, d_theta);
-    mark();
-    if (tc) { if ((rc = ntn_tc_gemm_fwd(h))) return rc; } else ntn_launch_gemm_fwd_simt(h);    // :163-197
-    mark(); ntn_launch_score(h, d_theta);                                  // :200-289
-    mark();
-    if (tc) { if ((rc = ntn_tc_gemm_dw(h))) return rc; } else ntn_launch_gemm_dw_simt(h);      // :301-349
-    mark();
-    if (tc) { if ((rc = ntn_tc_gemm_ge(h))) return rc; } else ntn_launch_gemm_ge_simt(h);      // :352-388
-    mark(); ntn_launch_entity_pull(h);                                     // Util.java:74-98
-    mark(); ntn_launch_word_pull(h, d_theta, d_grad);                      // :411-430
-    mark(); ntn_launch_finalize(h, d_theta, d_grad);                       // :398-401,433-438
-    mark();
+    // ---- fork: weight preparation runs beside the entity build
+    CK(cudaEventRecord(h->ev_f0, s0));
+    CK(cudaStreamWaitEvent(s1, h->ev_f0, 0));
+    begin(P_WP, s1);
+    if (tc) { if ((rc = ntn_tc_w_prep(h, d_theta, s1))) return rc; } else ntn_launch_w_prep(h, d_theta, s1);
+    end(P_WP, s1);
+    CK(cudaEventRecord(h->ev_j0, s1));
+    begin(P_EB, s0); ntn_launch_entity_build(h, wvt); end(P_EB, s0);                         // NTN.java:103
+    CK(cudaStreamWaitEvent(s0, h->ev_j0, 0));
+    begin(P_FWD, s0);
+    if (tc) { if ((rc = ntn_tc_gemm_fwd(h))) return rc; } else ntn_launch_gemm_fwd_simt(h);   // :163-197
+    end(P_FWD, s0);
+    begin(P_SC, s0); ntn_launch_score(h, d_theta); end(P_SC, s0);                            // :200-289
+    // ---- fork: dW contraction + small-block finalize beside the entity/word gradient chain
+    CK(cudaEventRecord(h->ev_f1, s0));
+    CK(cudaStreamWaitEvent(s1, h->ev_f1, 0));
+    begin(P_DW, s1);
+    if (tc) { if ((rc = ntn_tc_gemm_dw(h, s1))) return rc; } else ntn_launch_gemm_dw_simt(h, s1);   // :301-349
+    end(P_DW, s1);
+    begin(P_FIN, s1); ntn_launch_finalize_small(h, d_theta, d_grad, s1); end(P_FIN, s1);      // :398-401,433-438
+    CK(cudaEventRecord(h->ev_j1, s1));
+    begin(P_GE, s0);
+    if (tc) { if ((rc = ntn_tc_gemm_ge(h))) return rc; } else ntn_launch_gemm_ge_simt(h);     // :352-388
+    end(P_GE, s0);
+    begin(P_EP, s0); ntn_launch_entity_pull(h); end(P_EP, s0);                                // Util.java:74-98
+    begin(P_WPULL, s0); ntn_launch_word_pull(h, d_theta, d_grad); end(P_WPULL, s0);           // :411-430
+    CK(cudaStreamWaitEvent(s0, h->ev_j1, 0));
+    ntn_launch_final_reduce(h);                                                               // :430,437
     if (prof) h->ev_pending[slot] = true;
     CK(cudaMemcpyAsync(h->h_out, h->d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaGetLastError());

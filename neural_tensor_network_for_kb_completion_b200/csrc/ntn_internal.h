@@ -89,8 +89,10 @@ struct ntn_handle {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaStream_t stream2 = nullptr;          // forked branch (hub words), joined before the final reduce
+    cudaStream_t stream2 = nullptr;          // forked branch: hub words, joined inside the word pull
+    cudaStream_t stream3 = nullptr;          // forked branch: w_prep, then gemm_dw -> finalize_small
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_f0 = nullptr, ev_j0 = nullptr, ev_f1 = nullptr, ev_j1 = nullptr;
     std::string err;
     DeviceWords w;
     DeviceBatch b;
@@ -114,7 +116,7 @@ struct ntn_handle {
     int launches = 0;
     int gemm_path_active = NTN_GEMM_SIMT;
     bool profiling = false;
-    cudaEvent_t ev[NTN_RING][NTN_NUM_PHASES + 1] = {};
+    cudaEvent_t ev[NTN_RING][NTN_NUM_PHASES][2] = {};   // begin/end of each phase, on the stream it runs on
     bool ev_pending[NTN_RING] = {};
     double phase_acc[NTN_NUM_PHASES] = {};
     int phase_n = 0;
@@ -123,14 +125,15 @@ struct ntn_handle {
 
 // ---- kernel launchers (ntn_kernels.cu) ---------------------------------------------------
 void ntn_launch_entity_build(ntn_handle* h, const float* wvt);
-void ntn_launch_w_prep(ntn_handle* h, const float* theta);
+void ntn_launch_w_prep(ntn_handle* h, const float* theta, cudaStream_t st);
 void ntn_launch_gemm_fwd_simt(ntn_handle* h);
 void ntn_launch_score(ntn_handle* h, const float* theta);
-void ntn_launch_gemm_dw_simt(ntn_handle* h);
+void ntn_launch_gemm_dw_simt(ntn_handle* h, cudaStream_t st);
 void ntn_launch_gemm_ge_simt(ntn_handle* h);
 void ntn_launch_entity_pull(ntn_handle* h);
 void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad);
-void ntn_launch_finalize(ntn_handle* h, const float* theta, float* grad);
+void ntn_launch_finalize_small(ntn_handle* h, const float* theta, float* grad, cudaStream_t st);
+void ntn_launch_final_reduce(ntn_handle* h);
 void ntn_launch_to_internal(ntn_handle* h, const float* d_ref, float* d_int);
 void ntn_launch_from_internal(ntn_handle* h, const float* d_int, float* d_ref);
 void ntn_launch_transpose_wv_host_layout(ntn_handle* h, const float* d_wv_ref /* d x Nw */, float* d_wvt);

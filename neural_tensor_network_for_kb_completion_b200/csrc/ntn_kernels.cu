@@ -875,10 +875,10 @@ void ntn_launch_entity_build(ntn_handle* h, const float* wvt) {
     h->launches++;
 }
 
-void ntn_launch_w_prep(ntn_handle* h, const float* theta) {
+void ntn_launch_w_prep(ntn_handle* h, const float* theta, cudaStream_t st) {
     const NtnDims& dm = h->dm;
     int64_t n = (int64_t)dm.R * dm.Kp * dm.Np;
-    k_w_prep<<<cdiv(n, 256), 256, 0, h->stream>>>(theta, h->side, h->Waug, dm);
+    k_w_prep<<<cdiv(n, 256), 256, 0, st>>>(theta, h->side, h->Waug, dm);
     h->launches++;
 }
 
@@ -902,12 +902,12 @@ void ntn_launch_gemm_ge_simt(ntn_handle* h) {
     h->launches++;
 }
 
-void ntn_launch_gemm_dw_simt(ntn_handle* h) {
+void ntn_launch_gemm_dw_simt(ntn_handle* h, cudaStream_t st) {
     const NtnDims& dm = h->dm;
     if (h->b.nchunks == 0) return;
     GemmTables tb{h->b.ch_rel, h->b.ch_u0, h->b.ch_n, h->b.u_e1, h->b.u_e2, h->side};
     dim3 g(h->b.nchunks, cdiv(dm.Kp, GBM) * cdiv(dm.Np, GBN));
-    k_gemm_dw_simt<<<g, 256, 0, h->stream>>>(tb, h->E, h->b.M, h->b.dWpart, dm.Kp, dm.Np);
+    k_gemm_dw_simt<<<g, 256, 0, st>>>(tb, h->E, h->b.M, h->b.dWpart, dm.Kp, dm.Np);
     h->launches++;
 }
 
@@ -987,18 +987,26 @@ int ntn_small_blocks(const NtnDims& dm) {
 }
 int ntn_word_blocks(const NtnDims& dm) { return word_pull_blocks(dm); }
 
-void ntn_launch_finalize(ntn_handle* h, const float* theta, float* grad) {
+void ntn_launch_finalize_small(ntn_handle* h, const float* theta, float* grad, cudaStream_t st) {
     const NtnDims& dm = h->dm;
     const DeviceBatch& b = h->b;
     int nb = ntn_small_blocks(dm);
     int wb = word_pull_blocks(dm) + h->w.n_hub_words;
     FinArgs a{theta, b.dWpart, b.tp_dU, grad, b.relch_off, b.rels_off, h->side, h->reg_part + wb, dm,
               1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale};
-    k_finalize_small<<<nb, 256, 0, h->stream>>>(a);
+    k_finalize_small<<<nb, 256, 0, st>>>(a);
+    h->launches++;
+}
+
+void ntn_launch_final_reduce(ntn_handle* h) {
+    const NtnDims& dm = h->dm;
+    const DeviceBatch& b = h->b;
+    int nb = ntn_small_blocks(dm);
+    int wb = word_pull_blocks(dm) + h->w.n_hub_words;
     double lam = (double)h->cfg.lambda * (double)h->cfg.reg_scale;
     k_final_reduce<<<1, 256, 0, h->stream>>>(b.tp_cost, b.tp_nact, b.nstiles, h->reg_part, wb + nb,
                                              1.0 / (double)h->cfg.batch_divisor, 0.5 * lam, h->d_out);
-    h->launches += 2;
+    h->launches++;
 }
 
 void ntn_launch_to_internal(ntn_handle* h, const float* d_ref, float* d_int) {
