@@ -19,6 +19,7 @@
 // k_tc_w_prep (via TMA when NTN_TC_TMA is enabled).
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ntn_internal.h"
 
@@ -28,7 +29,7 @@
 #define TC_A_BYTES (128 * 128)    // one split of the A tile per stage
 #define TC_B_BYTES (TC_NCH * 128) // one split of the B tile per stage
 #define TC_STAGE_BYTES (2 * TC_A_BYTES + 2 * TC_B_BYTES)
-#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 256 /*barriers*/)
 #define TC_TMEM_COLS 256
 #define TC_SPIN_LIMIT (1u << 22)
 
@@ -37,6 +38,7 @@ struct TcState {
     float *W_hi = nullptr, *W_lo = nullptr;     // [R][KpN][NpP]  Waug,   K(=n)-major rows      (ge  B)
     int KpP = 0, KpN = 0, NpP = 0;
     int* err = nullptr;                         // device flag: a bounded wait expired
+    long long* dbg = nullptr;                   // 3 x 256 cycle stamps of CTA (0,0,0) per mode (debug timeline)
     bool attr_set = false;
 };
 
@@ -112,15 +114,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
            ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// x = hi + lo with hi, lo exactly representable in TF32 (10 explicit mantissa bits).  Rounding is done with
+// full-rate integer ops (add half an ulp of the 13 dropped bits, mask): cvt.rna.tf32.f32 goes through the
+// slow conversion pipe and was measured to dominate the producers (profiles/r1_tc_timeline.txt).
+__device__ __forceinline__ float tf32_round(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
-    auto sp = [](float v, float& h, float& l) {
-        uint32_t hb, lb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-        h = __uint_as_float(hb);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - h));
-        l = __uint_as_float(lb);
-    };
-    sp(x.x, hi.x, lo.x); sp(x.y, hi.y, lo.y); sp(x.z, hi.z, lo.z); sp(x.w, hi.w, lo.w);
+    hi.x = tf32_round(x.x); hi.y = tf32_round(x.y); hi.z = tf32_round(x.z); hi.w = tf32_round(x.w);
+    lo.x = tf32_round(x.x - hi.x); lo.y = tf32_round(x.y - hi.y); lo.z = tf32_round(x.z - hi.z); lo.w = tf32_round(x.w - hi.w);
 }
 __device__ __forceinline__ float4 ldg4g(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void sts4(uint8_t* base, uint32_t off, const float4& v) { *reinterpret_cast<float4*>(base + off) = v; }
@@ -135,14 +135,17 @@ struct TcArgs {
     float *T, *GA, *dWpart;
     int Kp, Np, KpP, KpN, NpP;
     int* err;
+    long long* dbg;                    // cycle-stamp timeline of CTA (0,0,0), or null
 };
 
 enum { TC_FWD = 0, TC_DW = 1, TC_GE = 2 };
 
 template <int MODE>
 __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // SWIZZLE_128B tiles need 1024-byte alignment.  The array is used directly (no pointer arithmetic through
+    // integers) so that the stores below stay in the shared state space (STS): with generic stores the compiler
+    // cannot hoist the global loads above them and every load round trip is exposed.
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
     // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready; then the TMEM base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
@@ -153,6 +156,12 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x;
+    // debug timeline: thread 0 (producer) stamps slots [0,128), thread 128 (MMA issuer) slots [128,256)
+    long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 0 || threadIdx.x == 128))
+                         ? a.dbg + MODE * 256 + (threadIdx.x == 128 ? 128 : 0) : nullptr;
+    int dbg_n = 0;
+    auto stamp = [&]() { if (dbg && dbg_n < 128) dbg[dbg_n++] = clock64(); };
+    stamp();
     const int r = a.t_rel[item], u0 = a.t_u0[item], rows = a.t_n[item];
     const bool tail = a.side[r] != 0;
 
@@ -173,6 +182,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    stamp();
 
     if (warp < 4) {
         // ================================ producers ================================
@@ -197,6 +207,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
             const int s = kb % TC_STAGES;
             const uint32_t ph = (kb / TC_STAGES) & 1;
             alive = mbar_wait(empty_bar(s), ph ^ 1, a.err);
+            stamp();
             uint8_t* sA_hi = smem + s * TC_STAGE_BYTES;
             uint8_t* sA_lo = sA_hi + TC_A_BYTES;
             uint8_t* sB_hi = sA_lo + TC_A_BYTES;
@@ -222,6 +233,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                         xbh[i] = ldg4g(Bhi + g); xbl[i] = ldg4g(Blo + g);
                     }
                 }
+                if (dbg && __float_as_uint(xa[0].x) != 0x7fc12345u) stamp();      // first loaded value has arrived
                 // ---- A: K-major, 128 rows x 128 bytes, chunk j of row `row` at row*128 + ((j ^ (row&7))<<4)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -231,6 +243,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                     const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
                     sts4(sA_hi, off, hi); sts4(sA_lo, off, lo);
                 }
+                stamp();                                                          // A split + stored
                 // ---- B: K-major, nlen rows (n resp. p) x 128 bytes, from the pre-split weight arrays
 #pragma unroll
                 for (int i = 0; i < BROWS; ++i) {
@@ -240,6 +253,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                         sts4(sB_hi, off, xbh[i]); sts4(sB_lo, off, xbl[i]);
                     }
                 }
+                stamp();                                                          // B stored
             } else {
                 // ---- dw: the contraction runs over the ROW index u of both operands, so the producers
                 //      transpose while storing: lane = u row of this k-block (K index), warps stride over the
@@ -291,10 +305,12 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
             }
             fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
             mbar_arrive(full_bar(s));
+            stamp();
         }
         // ================================ epilogue ================================
         if (alive) alive = mbar_wait(acc_bar, 0, a.err);
         tc_fence_after();
+        stamp();
         if (alive) {
             const int row = warp * 32 + lane;            // TMEM lane = accumulator row
             const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -325,6 +341,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                 }
             }
         }
+        stamp();
         tc_fence_before();
     } else {
         // ================================ MMA issuer ================================
@@ -335,6 +352,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
             const uint32_t ph = (kb / TC_STAGES) & 1;
             alive = mbar_wait(full_bar(s), ph, a.err);
             tc_fence_after();
+            stamp();
             if (lane == 0 && alive) {
                 const uint32_t sA_hi = smem_u32(smem + s * TC_STAGE_BYTES);
                 const uint32_t sA_lo = sA_hi + TC_A_BYTES, sB_hi = sA_lo + TC_A_BYTES, sB_lo = sB_hi + TC_B_BYTES;
@@ -352,6 +370,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                 umma_commit(empty_bar(s));                              // stage free once these MMAs have read it
                 if (kb == nkb - 1) umma_commit(acc_bar);                // accumulator complete
             }
+            stamp();
             __syncwarp();
         }
         tc_fence_before();
@@ -380,11 +399,8 @@ __device__ __forceinline__ float waug_at(const float* theta, const NtnDims& dm, 
     return theta[dm.ob + (int64_t)r * k + s];
 }
 __device__ __forceinline__ void split1(float v, float& h, float& l) {
-    uint32_t hb, lb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-    h = __uint_as_float(hb);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - h));
-    l = __uint_as_float(lb);
+    h = tf32_round(v);
+    l = tf32_round(v - h);
 }
 __global__ void __launch_bounds__(256) k_tc_w_prep(const float* __restrict__ theta, const uint8_t* __restrict__ side,
                                                    float* WT_hi, float* WT_lo, float* W_hi, float* W_lo, NtnDims dm,
@@ -430,6 +446,7 @@ static TcArgs tc_args(ntn_handle* h, bool chunks) {
     a.T = b.T; a.GA = b.GA; a.dWpart = b.dWpart;
     a.Kp = h->dm.Kp; a.Np = h->dm.Np; a.KpP = st->KpP; a.KpN = st->KpN; a.NpP = st->NpP;
     a.err = st->err;
+    a.dbg = st->dbg;
     return a;
 }
 
@@ -443,7 +460,8 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
         cudaError_t e;
         if ((e = cudaMalloc((void**)&st->WT_hi, nA * 4)) || (e = cudaMalloc((void**)&st->WT_lo, nA * 4)) ||
             (e = cudaMalloc((void**)&st->W_hi, nB * 4)) || (e = cudaMalloc((void**)&st->W_lo, nB * 4)) ||
-            (e = cudaMalloc((void**)&st->err, 4)) || (e = cudaMemset(st->err, 0, 4))) {
+            (e = cudaMalloc((void**)&st->err, 4)) || (e = cudaMemset(st->err, 0, 4)) ||
+            (getenv("NTN_TC_TIMELINE") && ((e = cudaMalloc((void**)&st->dbg, 3 * 256 * 8)) || (e = cudaMemset(st->dbg, 0, 3 * 256 * 8))))) {
             h->err = std::string("tcgen05 state: ") + cudaGetErrorString(e);
             return NTN_ECUDA;
         }
@@ -460,7 +478,7 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
 void ntn_tc_release(ntn_handle* h) {
     TcState* st = (TcState*)h->tc;
     if (!st) return;
-    cudaFree(st->WT_hi); cudaFree(st->WT_lo); cudaFree(st->W_hi); cudaFree(st->W_lo); cudaFree(st->err);
+    cudaFree(st->WT_hi); cudaFree(st->WT_lo); cudaFree(st->W_hi); cudaFree(st->W_lo); cudaFree(st->err); cudaFree(st->dbg);
     delete st;
     h->tc = nullptr;
 }
@@ -498,6 +516,21 @@ int ntn_tc_gemm_ge(ntn_handle* h) {
     k_tc_gemm<TC_GE><<<g, 160, TC_SMEM_BYTES, h->stream>>>(a);
     h->launches++;
     return NTN_OK;
+}
+
+// debug: copy the 3 x 256 cycle stamps (as doubles relative to each mode's first stamp); returns count or 0
+int64_t ntn_tc_fetch_timeline(ntn_handle* h, float* out, int64_t cap) {
+    TcState* st = (TcState*)h->tc;
+    if (!st || !st->dbg) return 0;
+    if (out && cap >= 768) {
+        long long tmp[768];
+        cudaMemcpy(tmp, st->dbg, sizeof(tmp), cudaMemcpyDeviceToHost);
+        for (int m = 0; m < 3; ++m) {
+            long long t0 = tmp[m * 256];
+            for (int i = 0; i < 256; ++i) out[m * 256 + i] = tmp[m * 256 + i] ? (float)(tmp[m * 256 + i] - t0) : -1.f;
+        }
+    }
+    return 768;
 }
 
 int ntn_tc_check_error(ntn_handle* h) {

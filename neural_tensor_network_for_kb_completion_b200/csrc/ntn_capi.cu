@@ -19,6 +19,7 @@ int ntn_tc_gemm_fwd(ntn_handle* h);
 int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t st);
 int ntn_tc_gemm_ge(ntn_handle* h);
 int ntn_tc_check_error(ntn_handle* h);
+int64_t ntn_tc_fetch_timeline(ntn_handle* h, float* out, int64_t cap);
 
 static thread_local std::string g_create_err;
 
@@ -160,7 +161,7 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     DeviceWords& w = h->w;
     dev_free(w.fwd_off); dev_free(w.fwd_idx); dev_free(w.w_off); dev_free(w.w_ent); dev_free(w.len_bwd);
     dev_free(w.wh_word); dev_free(w.wh_begin); dev_free(w.wh_end); dev_free(w.wh_first); dev_free(w.wh_count);
-    dev_free(w.wh_part); dev_free(w.hub_words);
+    dev_free(w.wh_part); dev_free(w.hub_words); dev_free(w.w_rec);
     dev_free(h->wv_frozen); dev_free(h->E); dev_free(h->gE); dev_free(h->Waug); dev_free(h->side);
     dev_free(h->reg_part); dev_free(h->d_out); dev_free(h->d_ref_theta); dev_free(h->d_ref_grad);
     dev_free(h->d_int_theta); dev_free(h->d_int_grad);
@@ -275,13 +276,16 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
     std::vector<int> hub_words;
     for (int i = 0; i < dm.Nw; ++i) if (count[i] > 0) hub_words.push_back(i);
     w.n_hub_words = (int)hub_words.size();
+    std::vector<int4> wrec(dm.Nw);
+    for (int i = 0; i < dm.Nw; ++i)
+        wrec[i] = make_int4(woff[i], woff[i + 1], woff[i + 1] > woff[i] ? went[woff[i]] : -1, count[i]);
     int rc;
     if ((rc = dev_upload(h, &w.fwd_off, vfo)) || (rc = dev_upload(h, &w.fwd_idx, vfi)) ||
         (rc = dev_upload(h, &w.w_off, woff)) || (rc = dev_upload(h, &w.w_ent, went)) ||
         (rc = dev_upload(h, &w.len_bwd, lb)) || (rc = dev_upload(h, &w.wh_word, sr)) ||
         (rc = dev_upload(h, &w.wh_begin, sb)) || (rc = dev_upload(h, &w.wh_end, se)) ||
         (rc = dev_upload(h, &w.wh_first, first)) || (rc = dev_upload(h, &w.wh_count, count)) ||
-        (rc = dev_upload(h, &w.hub_words, hub_words)) ||
+        (rc = dev_upload(h, &w.hub_words, hub_words)) || (rc = dev_upload(h, &w.w_rec, wrec)) ||
         (rc = dev_alloc(h, &w.wh_part, (size_t)w.n_hub_segs * dm.dq)))
         return rc;
     CK(cudaStreamSynchronize(h->stream));     // host vectors go out of scope
@@ -631,6 +635,7 @@ extern "C" int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, 
     else if (s == "dWpart") { src = b.dWpart; n = (int64_t)b.nchunks * dm.Kp * dm.Np; }
     else if (s == "E") { src = h->E; n = (int64_t)dm.Ne * dm.Kp; }
     else if (s == "gE") { src = h->gE; n = (int64_t)dm.Ne * dm.dq; }
+    else if (s == "tc_timeline") return ntn_tc_fetch_timeline(h, out, cap);
     else return -1;
     if (out && cap >= n && n > 0) cudaMemcpy(out, src, n * sizeof(float), cudaMemcpyDeviceToHost);
     return n;

@@ -75,6 +75,7 @@ struct DeviceWords {
     int nnz_f = 0, nnz_b = 0;
     int *fwd_off = nullptr, *fwd_idx = nullptr;    // entity -> forward words
     int *w_off = nullptr, *w_ent = nullptr;        // word -> entities of the backward lists (inverse CSR)
+    int4 *w_rec = nullptr;                         // per word {j0, j1, first entity, hub segment count}
     float *len_bwd = nullptr;                      // Ne, as float
     int n_hub_segs = 0, n_hub_words = 0;
     int *hub_words = nullptr;                      // ids of the hub words

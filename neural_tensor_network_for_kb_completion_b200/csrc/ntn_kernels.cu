@@ -509,16 +509,14 @@ __device__ __forceinline__ float4 pull_range(const PullArgs& a, int j0, int j1, 
             const int4 rec = ok ? __ldg(a.inc + jb + i) : make_int4(0, 0, 2, 0);
             const bool tail = a.side[rec.w] != 0;
             const bool anchor = ok && ((rec.z == 0 && tail) || (rec.z == 1 && !tail));
-            bool any = false;
+            // coefficient and row loads are issued together: gating the rows on "any coefficient non-zero"
+            // (inactive column, NTN.java:229-239) would add one more dependent round trip to every incident
 #pragma unroll
-            for (int s = 0; s < KS; ++s) {
-                co[i][s] = (ok && !anchor) ? __ldg(a.coef + (size_t)rec.y * KS + s) : 0.f;
-                any |= co[i][s] != 0.f;                              // all zero: inactive column (NTN.java:229-239)
-            }
+            for (int s = 0; s < KS; ++s) co[i][s] = (ok && !anchor) ? __ldg(a.coef + (size_t)rec.y * KS + s) : 0.f;
             const float* Trow = a.T + (size_t)rec.x * a.Np + c * 4;
-            rows[i][0] = (any || anchor) ? ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : Trow) : zero4();
+            rows[i][0] = ok ? ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : Trow) : zero4();
 #pragma unroll
-            for (int s = 1; s < KS; ++s) rows[i][s] = any ? ldg4(Trow + s * a.dq) : zero4();
+            for (int s = 1; s < KS; ++s) rows[i][s] = (ok && !anchor) ? ldg4(Trow + s * a.dq) : zero4();
             if (anchor) co[i][0] = 1.f;
         }
 #pragma unroll
@@ -576,6 +574,7 @@ struct WordArgs {
     const float *gE, *len_bwd, *theta;
     float* grad;
     const int *w_off, *w_ent;
+    const int4* w_rec;                   // {j0, j1, first entity (or -1), hub segment count}: one load instead of a chain
     const int *wh_first, *wh_count, *wh_begin, *wh_end, *hub_words;
     float* wh_part;
     double* reg_part;      // [word blocks | hub words | small-block finalize]
@@ -676,11 +675,21 @@ __global__ void __launch_bounds__(256) k_word_pull(WordArgs a) {
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int w = (int)(gid / cpr), c = (int)(gid - (int64_t)w * cpr);
     float reg = 0.f;
-    if (w < a.Nw && a.wh_count[w] == 0) {
-        size_t o = (size_t)a.oWV + (size_t)w * a.dq + c * 4;
-        float4 th = ldg4(a.theta + o);
-        float4 acc = word_range(a, __ldg(a.w_off + w), __ldg(a.w_off + w + 1), c);
-        reg = word_store(a, o, th, acc);
+    if (w < a.Nw) {
+        const int4 rec = __ldg(a.w_rec + w);
+        if (rec.w == 0) {                                            // hub words are finished elsewhere
+            size_t o = (size_t)a.oWV + (size_t)w * a.dq + c * 4;
+            float4 th = ldg4(a.theta + o);
+            float4 acc = zero4();
+            if (rec.y - rec.x == 1) {                                // the common case: exactly one entity
+                const float len = __ldg(a.len_bwd + rec.z);
+                float4 v = ldg4(a.gE + (size_t)rec.z * a.dq + c * 4);
+                acc = make_float4(v.x / len, v.y / len, v.z / len, v.w / len);
+            } else if (rec.y > rec.x) {
+                acc = word_range(a, rec.x, rec.y, c);
+            }
+            reg = word_store(a, o, th, acc);
+        }
     }
     reg = warp_sum(reg);
     if ((threadIdx.x & 31) == 0) s_reg[threadIdx.x >> 5] = (double)reg;
@@ -962,7 +971,7 @@ static int word_pull_blocks(const NtnDims& dm) { return cdiv((int64_t)dm.Nw * (d
 void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad) {
     const NtnDims& dm = h->dm;
     const DeviceWords& w = h->w;
-    WordArgs a{h->gE, w.len_bwd, theta, grad, w.w_off, w.w_ent, w.wh_first, w.wh_count, w.wh_begin, w.wh_end,
+    WordArgs a{h->gE, w.len_bwd, theta, grad, w.w_off, w.w_ent, w.w_rec, w.wh_first, w.wh_count, w.wh_begin, w.wh_end,
                w.hub_words, w.wh_part, h->reg_part, dm.Nw, dm.dq, w.n_hub_segs, w.n_hub_words, word_pull_blocks(dm),
                dm.oWVint, 1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale};
     const int cpr = dm.dq / 4;
