@@ -5,8 +5,8 @@
 //   dw   dWaug_r[p, n] = sum_u  [E_anchor(u) | 1][p] * M[u, n]  (split-K)  NTN.java:301-349
 //   ge   GA[u, p]      = sum_n  M[u, n] * Waug_r[p, n]                     NTN.java:352-388
 //
-// One CTA = one 128-row accumulator tile in TMEM (tcgen05.alloc), N <= 160 columns.
-//   warps 0-3  producers: gather / load FP32 operand rows, split x = hi + lo (hi = rna-tf32(x),
+// One CTA = one 128-row accumulator tile in TMEM (tcgen05.alloc), N <= 160 columns, 288 threads.
+//   warps 0-3 and 5-8  two producer groups taking alternate k-blocks: gather / load FP32 operand rows, split x = hi + lo (hi = rna-tf32(x),
 //              lo = rna-tf32(x - hi)), store both into 128B-swizzled UMMA shared-memory tiles,
 //              fence.proxy.async, arrive on the stage's "full" mbarrier; afterwards the same warps
 //              run the epilogue (tcgen05.ld -> registers -> global).
@@ -15,8 +15,7 @@
 //              tcgen05.commit releases the stage ("empty" mbarrier) / signals the epilogue.
 // All operands are K-major SWIZZLE_128B tiles (row = M/N index, 128 bytes of K per row).  dw contracts
 // over the ROW index of both of its operands, so its producers transpose while they store.
-// The weight operand is read from pre-split hi/lo arrays written once per evaluation by
-// k_tc_w_prep (via TMA when NTN_TC_TMA is enabled).
+// The weight operand Waug is written once per evaluation by k_tc_w_prep in both K-major orientations.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -34,8 +33,8 @@
 #define TC_SPIN_LIMIT (1u << 22)
 
 struct TcState {
-    float *WT_hi = nullptr, *WT_lo = nullptr;   // [R][Np][KpP]   Waug^T, K(=p)-major rows      (fwd B)
-    float *W_hi = nullptr, *W_lo = nullptr;     // [R][KpN][NpP]  Waug,   K(=n)-major rows      (ge  B)
+    float *WT = nullptr;                        // [R][Np][KpP]   Waug^T, K(=p)-major rows      (fwd B)
+    float *W = nullptr;                         // [R][KpN][NpP]  Waug,   K(=n)-major rows      (ge  B)
     int KpP = 0, KpN = 0, NpP = 0;
     int* err = nullptr;                         // device flag: a bounded wait expired
     long long* dbg = nullptr;                   // 3 x 256 cycle stamps of CTA (0,0,0) per mode (debug timeline)
@@ -131,7 +130,7 @@ struct TcArgs {
     const int *u_e1, *u_e2;
     const uint8_t* side;
     const float *E, *M;
-    const float *WT_hi, *WT_lo, *W_hi, *W_lo;
+    const float *WT, *W;
     float *T, *GA, *dWpart;
     int Kp, Np, KpP, KpN, NpP;
     int* err;
@@ -140,8 +139,21 @@ struct TcArgs {
 
 enum { TC_FWD = 0, TC_DW = 1, TC_GE = 2 };
 
+#define TC_THREADS 288            // warps 0-3: producer group 0 + epilogue, warp 4: MMA issuer, warps 5-8: producer group 1
+
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float v[16]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int MODE>
-__global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a) {
     // SWIZZLE_128B tiles need 1024-byte alignment.  The array is used directly (no pointer arithmetic through
     // integers) so that the stores below stay in the shared state space (STS): with generic stores the compiler
     // cannot hoist the global loads above them and every load round trip is exposed.
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x;
-    // debug timeline: thread 0 (producer) stamps slots [0,128), thread 128 (MMA issuer) slots [128,256)
+    // debug timeline: thread 0 (producer group 0) stamps slots [0,128), thread 128 (MMA issuer) slots [128,256)
     long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 0 || threadIdx.x == 128))
                          ? a.dbg + MODE * 256 + (threadIdx.x == 128 ? 128 : 0) : nullptr;
     int dbg_n = 0;
@@ -184,12 +196,15 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
     const uint32_t tmem_base = *tmem_slot;
     stamp();
 
-    if (warp < 4) {
+    if (warp != 4) {
         // ================================ producers ================================
-        const int t = threadIdx.x;                       // 0..127
+        // two groups of 128 threads take alternate k-blocks, so two k-blocks' global loads are in flight
+        const int group = warp > 4 ? 1 : 0;
+        const int t = threadIdx.x - (group ? 160 : 0);   // 0..127 inside the group
+        const int gw = t >> 5;                           // warp inside the group
         const int j = t & 7;                             // 16-byte chunk inside a 128-byte swizzle row
         const int rsub = t >> 3;                         // 0..15
-        int anchor[8];                                   // fwd: gathered entity of this thread's 8 rows; dw: per k-block
+        int anchor[8];                                   // fwd: gathered entity of this thread's 8 rows
         if (MODE == TC_FWD) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -197,13 +212,11 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                 anchor[i] = (row < rows) ? (tail ? __ldg(a.u_e1 + u0 + row) : __ldg(a.u_e2 + u0 + row)) : -1;
             }
         }
-        const float* Bhi = (MODE == TC_FWD) ? a.WT_hi + (size_t)r * a.Np * a.KpP
-                          : (MODE == TC_GE) ? a.W_hi + (size_t)r * a.KpN * a.NpP : nullptr;
-        const float* Blo = (MODE == TC_FWD) ? a.WT_lo + (size_t)r * a.Np * a.KpP
-                          : (MODE == TC_GE) ? a.W_lo + (size_t)r * a.KpN * a.NpP : nullptr;
+        const float* Bw = (MODE == TC_FWD) ? a.WT + (size_t)r * a.Np * a.KpP
+                         : (MODE == TC_GE) ? a.W + (size_t)r * a.KpN * a.NpP : nullptr;
         const int ldb = (MODE == TC_FWD) ? a.KpP : a.NpP;
         bool alive = true;
-        for (int kb = 0; kb < nkb && alive; ++kb) {
+        for (int kb = group; kb < nkb && alive; kb += 2) {
             const int s = kb % TC_STAGES;
             const uint32_t ph = (kb / TC_STAGES) & 1;
             alive = mbar_wait(empty_bar(s), ph ^ 1, a.err);
@@ -216,7 +229,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
             constexpr int BROWS = TC_NCH / 16;                                       // B rows per thread (K-major loads)
             if (MODE == TC_FWD || MODE == TC_GE) {
                 // all global loads of this k-block are issued first (latency overlaps), then split + store
-                float4 xa[8], xbh[BROWS], xbl[BROWS];
+                float4 xa[8], xb[BROWS];
                 const int kk = k0 + j * 4;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -228,12 +241,8 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
 #pragma unroll
                 for (int i = 0; i < BROWS; ++i) {
                     const int row = rsub + 16 * i;
-                    if (row < nlen) {
-                        const size_t g = (size_t)(n0 + row) * ldb + kk;
-                        xbh[i] = ldg4g(Bhi + g); xbl[i] = ldg4g(Blo + g);
-                    }
+                    xb[i] = (row < nlen) ? ldg4g(Bw + (size_t)(n0 + row) * ldb + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                if (dbg && __float_as_uint(xa[0].x) != 0x7fc12345u) stamp();      // first loaded value has arrived
                 // ---- A: K-major, 128 rows x 128 bytes, chunk j of row `row` at row*128 + ((j ^ (row&7))<<4)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -243,17 +252,18 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                     const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
                     sts4(sA_hi, off, hi); sts4(sA_lo, off, lo);
                 }
-                stamp();                                                          // A split + stored
-                // ---- B: K-major, nlen rows (n resp. p) x 128 bytes, from the pre-split weight arrays
+                // ---- B: K-major, nlen rows (n resp. p) x 128 bytes of Waug, split here as well: reading one FP32
+                //      copy instead of pre-split hi/lo arrays halves the L2 traffic of the operand every CTA re-reads
 #pragma unroll
                 for (int i = 0; i < BROWS; ++i) {
                     const int row = rsub + 16 * i;
                     if (row < nlen) {
+                        float4 hi, lo;
+                        split_tf32(xb[i], hi, lo);
                         const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
-                        sts4(sB_hi, off, xbh[i]); sts4(sB_lo, off, xbl[i]);
+                        sts4(sB_hi, off, hi); sts4(sB_lo, off, lo);
                     }
                 }
-                stamp();                                                          // B stored
             } else {
                 // ---- dw: the contraction runs over the ROW index u of both operands, so the producers
                 //      transpose while storing: lane = u row of this k-block (K index), warps stride over the
@@ -266,12 +276,12 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                 float4 xa[8], xb[BCH];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {                                         // A rows: p = m0 + 4c + e
-                    const int p = m0 + 4 * (warp + 4 * i);
+                    const int p = m0 + 4 * (gw + 4 * i);
                     xa[i] = (an >= 0 && p < a.Kp) ? ldg4g(a.E + (size_t)an * a.Kp + p) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int i = 0; i < BCH; ++i) {                                       // B rows: n = n0 + 4c + e
-                    const int c = warp + 4 * i;
+                    const int c = gw + 4 * i;
                     xb[i] = (an >= 0 && 4 * c < nlen) ? ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + 4 * c)
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -282,14 +292,14 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
                     const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const uint32_t row = 4 * (warp + 4 * i) + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
+                        const uint32_t row = 4 * (gw + 4 * i) + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
                         *reinterpret_cast<float*>(sA_hi + off) = hv[e];
                         *reinterpret_cast<float*>(sA_lo + off) = lv[e];
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < BCH; ++i) {
-                    const int c = warp + 4 * i;
+                    const int c = gw + 4 * i;
                     if (4 * c < nlen) {
                         float4 hi, lo;
                         split_tf32(xb[i], hi, lo);
@@ -307,41 +317,59 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
             mbar_arrive(full_bar(s));
             stamp();
         }
-        // ================================ epilogue ================================
-        if (alive) alive = mbar_wait(acc_bar, 0, a.err);
-        tc_fence_after();
-        stamp();
-        if (alive) {
-            const int row = warp * 32 + lane;            // TMEM lane = accumulator row
-            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-            for (int c0 = 0; c0 < nlen; c0 += 16) {
-                float v[16];
-                tmem_ld16(trow + c0, v);
-                if (MODE == TC_FWD) {
-                    if (row < rows) {
-                        float* dst = a.T + (size_t)(u0 + row) * a.Np + n0 + c0;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
-                } else if (MODE == TC_GE) {
-                    if (row < rows) {
-                        float* dst = a.GA + (size_t)(u0 + row) * a.Kp + n0 + c0;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (n0 + c0 + 4 * q < a.Kp) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
-                } else {
-                    // partial stored transposed, [n][p]: lanes = consecutive p -> coalesced
-                    const int p = m0 + row;
+        // ================================ epilogue (group 0: warps 0-3 own TMEM lanes 32w..32w+31) ================
+        if (group == 0) {
+            if (alive) alive = mbar_wait(acc_bar, 0, a.err);
+            tc_fence_after();
+            stamp();
+            const int row = gw * 32 + lane;              // TMEM lane = accumulator row
+            const uint32_t trow = tmem_base + ((uint32_t)(gw * 32) << 16);
+            if (MODE == TC_DW) {
+                // partial stored transposed, [n][p]: lanes = consecutive p -> coalesced 128-byte stores
+                const int p = m0 + row;
+                for (int c0 = 0; c0 < nlen && alive; c0 += 32) {
+                    float v[32];
+                    tmem_ld16_issue(trow + c0, v);
+                    if (c0 + 16 < nlen) tmem_ld16_issue(trow + c0 + 16, v + 16);
+                    tmem_ld_wait();
                     if (p < a.Kp) {
                         float* dst = a.dWpart + (size_t)item * a.Kp * a.Np + (size_t)(n0 + c0) * a.Kp + p;
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) dst[(size_t)q * a.Kp] = v[q];
+                        for (int q = 0; q < 32; ++q)
+                            if (c0 + q < nlen) dst[(size_t)q * a.Kp] = v[q];
                     }
                 }
+            } else {
+                // all MMAs have completed, so the pipeline stages are free: stage the tile in shared memory
+                // (row pitch nlen+4 floats) and write it out with fully coalesced 16-byte stores
+                const int pitch = nlen + 4;
+                float* stg = reinterpret_cast<float*>(smem);
+                for (int c0 = 0; c0 < nlen && alive; c0 += 32) {
+                    float v[32];
+                    tmem_ld16_issue(trow + c0, v);
+                    if (c0 + 16 < nlen) tmem_ld16_issue(trow + c0 + 16, v + 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (c0 + 4 * q < nlen)
+                            *reinterpret_cast<float4*>(stg + (size_t)row * pitch + c0 + 4 * q) =
+                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+                epi_bar_sync();
+                const int c4n = nlen >> 2;                       // <= 40 float4 per row: lanes, then lanes 0..7 again
+                float* out = (MODE == TC_FWD) ? a.T : a.GA;
+                const int ldo = (MODE == TC_FWD) ? a.Np : a.Kp;
+                for (int rr = gw; rr < rows; rr += 4) {          // one warp per row: contiguous 16-byte stores
+                    float* orow = out + (size_t)(u0 + rr) * ldo + n0;
+                    const float* srow = stg + (size_t)rr * pitch;
+                    if (lane < c4n && n0 + 4 * lane < ldo)
+                        *reinterpret_cast<float4*>(orow + 4 * lane) = *reinterpret_cast<const float4*>(srow + 4 * lane);
+                    if (lane + 32 < c4n && n0 + 4 * (lane + 32) < ldo)
+                        *reinterpret_cast<float4*>(orow + 4 * (lane + 32)) = *reinterpret_cast<const float4*>(srow + 4 * (lane + 32));
+                }
             }
+            stamp();
         }
-        stamp();
         tc_fence_before();
     } else {
         // ================================ MMA issuer ================================
@@ -380,8 +408,8 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm(TcArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// per-evaluation weight preparation: Waug_r (see k_w_prep in ntn_kernels.cu) pre-split into tf32
-// hi/lo, in the two K-major layouts the kernels above read.  Padding rows/columns are zero.
+// per-evaluation weight preparation: Waug_r (see k_w_prep in ntn_kernels.cu) in the two K-major
+// layouts the kernels above read.  Padding rows/columns are zero.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float waug_at(const float* theta, const NtnDims& dm, int r, bool tail, int p, int n) {
     const int d = dm.d, k = dm.k, dq = dm.dq;
@@ -403,25 +431,20 @@ __device__ __forceinline__ void split1(float v, float& h, float& l) {
     l = tf32_round(v - h);
 }
 __global__ void __launch_bounds__(256) k_tc_w_prep(const float* __restrict__ theta, const uint8_t* __restrict__ side,
-                                                   float* WT_hi, float* WT_lo, float* W_hi, float* W_lo, NtnDims dm,
-                                                   int KpP, int KpN, int NpP) {
+                                                   float* WT, float* W, NtnDims dm, int KpP, int KpN, int NpP) {
     const int64_t nA = (int64_t)dm.R * dm.Np * KpP, nB = (int64_t)dm.R * KpN * NpP;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nA) {
         int r = (int)(i / ((int64_t)dm.Np * KpP));
         int rem = (int)(i - (int64_t)r * dm.Np * KpP);
         int n = rem / KpP, p = rem - n * KpP;
-        float h, l;
-        split1(waug_at(theta, dm, r, side[r] != 0, p, n), h, l);
-        WT_hi[i] = h; WT_lo[i] = l;
+        WT[i] = waug_at(theta, dm, r, side[r] != 0, p, n);
     } else if (i < nA + nB) {
         i -= nA;
         int r = (int)(i / ((int64_t)KpN * NpP));
         int rem = (int)(i - (int64_t)r * KpN * NpP);
         int p = rem / NpP, n = rem - p * NpP;
-        float h, l;
-        split1(waug_at(theta, dm, r, side[r] != 0, p, n), h, l);
-        W_hi[i] = h; W_lo[i] = l;
+        W[i] = waug_at(theta, dm, r, side[r] != 0, p, n);
     }
 }
 
@@ -442,7 +465,7 @@ static TcArgs tc_args(ntn_handle* h, bool chunks) {
     TcArgs a{};
     a.t_rel = chunks ? b.ch_rel : b.t_rel; a.t_u0 = chunks ? b.ch_u0 : b.t_u0; a.t_n = chunks ? b.ch_n : b.t_n;
     a.u_e1 = b.u_e1; a.u_e2 = b.u_e2; a.side = h->side; a.E = h->E; a.M = b.M;
-    a.WT_hi = st->WT_hi; a.WT_lo = st->WT_lo; a.W_hi = st->W_hi; a.W_lo = st->W_lo;
+    a.WT = st->WT; a.W = st->W;
     a.T = b.T; a.GA = b.GA; a.dWpart = b.dWpart;
     a.Kp = h->dm.Kp; a.Np = h->dm.Np; a.KpP = st->KpP; a.KpN = st->KpN; a.NpP = st->NpP;
     a.err = st->err;
@@ -458,8 +481,7 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
         st->KpP = rup(dm.Kp, TC_BK); st->KpN = rup(dm.Kp, 16); st->NpP = rup(dm.Np, TC_BK);
         size_t nA = (size_t)dm.R * dm.Np * st->KpP, nB = (size_t)dm.R * st->KpN * st->NpP;
         cudaError_t e;
-        if ((e = cudaMalloc((void**)&st->WT_hi, nA * 4)) || (e = cudaMalloc((void**)&st->WT_lo, nA * 4)) ||
-            (e = cudaMalloc((void**)&st->W_hi, nB * 4)) || (e = cudaMalloc((void**)&st->W_lo, nB * 4)) ||
+        if ((e = cudaMalloc((void**)&st->WT, nA * 4)) || (e = cudaMalloc((void**)&st->W, nB * 4)) ||
             (e = cudaMalloc((void**)&st->err, 4)) || (e = cudaMemset(st->err, 0, 4)) ||
             (getenv("NTN_TC_TIMELINE") && ((e = cudaMalloc((void**)&st->dbg, 3 * 256 * 8)) || (e = cudaMemset(st->dbg, 0, 3 * 256 * 8))))) {
             h->err = std::string("tcgen05 state: ") + cudaGetErrorString(e);
@@ -478,7 +500,7 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
 void ntn_tc_release(ntn_handle* h) {
     TcState* st = (TcState*)h->tc;
     if (!st) return;
-    cudaFree(st->WT_hi); cudaFree(st->WT_lo); cudaFree(st->W_hi); cudaFree(st->W_lo); cudaFree(st->err); cudaFree(st->dbg);
+    cudaFree(st->WT); cudaFree(st->W); cudaFree(st->err); cudaFree(st->dbg);
     delete st;
     h->tc = nullptr;
 }
@@ -487,8 +509,7 @@ int ntn_tc_w_prep(ntn_handle* h, const float* theta, cudaStream_t stq) {
     TcState* st = (TcState*)h->tc;
     const NtnDims& dm = h->dm;
     int64_t n = (int64_t)dm.R * dm.Np * st->KpP + (int64_t)dm.R * st->KpN * st->NpP;
-    k_tc_w_prep<<<cdivi(n, 256), 256, 0, stq>>>(theta, h->side, st->WT_hi, st->WT_lo, st->W_hi, st->W_lo, dm,
-                                                      st->KpP, st->KpN, st->NpP);
+    k_tc_w_prep<<<cdivi(n, 256), 256, 0, stq>>>(theta, h->side, st->WT, st->W, dm, st->KpP, st->KpN, st->NpP);
     h->launches++;
     return NTN_OK;
 }
@@ -496,7 +517,7 @@ int ntn_tc_w_prep(ntn_handle* h, const float* theta, cudaStream_t stq) {
 int ntn_tc_gemm_fwd(ntn_handle* h) {
     TcArgs a = tc_args(h, false);
     dim3 g(h->b.ntiles, cdivi(h->dm.Np, TC_NCH));
-    k_tc_gemm<TC_FWD><<<g, 160, TC_SMEM_BYTES, h->stream>>>(a);
+    k_tc_gemm<TC_FWD><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a);
     h->launches++;
     return NTN_OK;
 }
@@ -504,7 +525,7 @@ int ntn_tc_gemm_fwd(ntn_handle* h) {
 int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t stq) {
     TcArgs a = tc_args(h, true);
     dim3 g(h->b.nchunks, cdivi(h->dm.Np, TC_NCH), cdivi(h->dm.Kp, 128));
-    k_tc_gemm<TC_DW><<<g, 160, TC_SMEM_BYTES, stq>>>(a);
+    k_tc_gemm<TC_DW><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a);
     h->launches++;
     return NTN_OK;
 }
@@ -513,7 +534,7 @@ int ntn_tc_gemm_ge(ntn_handle* h) {
     TcArgs a = tc_args(h, false);
     TcState* st = (TcState*)h->tc;
     dim3 g(h->b.ntiles, cdivi(st->KpN, TC_NCH));
-    k_tc_gemm<TC_GE><<<g, 160, TC_SMEM_BYTES, h->stream>>>(a);
+    k_tc_gemm<TC_GE><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a);
     h->launches++;
     return NTN_OK;
 }
