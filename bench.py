@@ -287,8 +287,6 @@ def main():
     for i in range(args.warmup):
         step(i, sync=True)
     launches_per_eval = h0.launches
-    for h in handles:
-        h.set_profiling(True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -301,6 +299,13 @@ def main():
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    # per-kernel-group times: the same steps again with CUDA events bracketing every group on the stream it
+    # runs on (this mode launches the kernels directly instead of replaying the captured graph)
+    for h in handles:
+        h.set_profiling(True)
+    for i in range(min(args.steps, 40)):
+        step(i)
+    barrier()
     phase = {}
     for h in handles:
         for kname, v in h.phase_ms().items():

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include <thread>
 
@@ -14,6 +15,7 @@ int ntn_word_blocks(const NtnDims& dm);
 int ntn_tc_supported(const ntn_handle* h);                     // gemm_tcgen05.cu
 int ntn_tc_prepare_batch(ntn_handle* h);
 void ntn_tc_release(ntn_handle* h);
+void ntn_drop_graphs(ntn_handle* h);
 int ntn_tc_w_prep(ntn_handle* h, const float* theta, cudaStream_t st);
 int ntn_tc_gemm_fwd(ntn_handle* h);
 int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t st);
@@ -103,6 +105,7 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
     if (h->cfg.reg_scale == 0.f) h->cfg.reg_scale = 1.f;
     h->dm = make_dims(*cfg);
     h->device = cfg->device;
+    h->use_graph = getenv("NTN_NO_GRAPH") == nullptr;
     auto bail = [&](int rc) { g_create_err = h->err; ntn_destroy(h); return rc; };
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(NTN_ECUDA); } } while (0)
     CKC(cudaSetDevice(h->device));
@@ -156,6 +159,7 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    ntn_drop_graphs(h);
     ntn_tc_release(h);
     free_batch(h->b);
     DeviceWords& w = h->w;
@@ -255,6 +259,7 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
     int nf = fwd_off[dm.Ne], nb = bwd_off[dm.Ne];
     for (int j = 0; j < nf; ++j) if (fwd_idx[j] < 0 || fwd_idx[j] >= dm.Nw) FAIL(NTN_EINVAL, "forward word index out of range");
     for (int j = 0; j < nb; ++j) if (bwd_idx[j] < 0 || bwd_idx[j] >= dm.Nw) FAIL(NTN_EINVAL, "backward word index out of range");
+    ntn_drop_graphs(h);
     DeviceWords& w = h->w;
     w.nnz_f = nf; w.nnz_b = nb;
     std::vector<int> vfo(fwd_off, fwd_off + dm.Ne + 1), vfi(fwd_idx, fwd_idx + nf);
@@ -298,6 +303,7 @@ extern "C" int ntn_set_frozen_wv(ntn_handle* h, const float* wv) {
     if (!wv) FAIL(NTN_EINVAL, "null argument");
     CK(cudaSetDevice(h->device));
     const NtnDims& dm = h->dm;
+    ntn_drop_graphs(h);
     float* tmp = nullptr;
     size_t n = (size_t)dm.d * dm.Nw;
     CK(cudaMalloc((void**)&tmp, n * sizeof(float)));
@@ -380,6 +386,7 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
     build_hub_segments(inc_off, dm.Ne, sr, sb, se, first, count);
 
     CK(cudaStreamSynchronize(h->stream));
+    ntn_drop_graphs(h);
     free_batch(h->b);
     DeviceBatch& b = h->b;
     b.N = n; b.Nu = Nu; b.ntiles = (int)t_rel.size(); b.nchunks = (int)ch_rel.size(); b.n_inc = n_inc;
@@ -420,36 +427,13 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
     return NTN_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// the evaluation driver                                          NTN.computeAt, NTN.java:92-443
-// ------------------------------------------------------------------------------------------
-static int eval_internal(ntn_handle* h, const float* d_theta, const uint8_t* corrupt_side, float* d_grad) {
-    const NtnDims& dm = h->dm;
-    if (!h->w.set) FAIL(NTN_ESTATE, "ntn_set_entity_words has not been called");
-    if (!corrupt_side) FAIL(NTN_EINVAL, "corrupt_side is null");
-    const float* wvt;
-    if (h->cfg.wv_source == NTN_WV_FROZEN) {
-        if (!h->wv_frozen) FAIL(NTN_ESTATE, "wv_source is NTN_WV_FROZEN but ntn_set_frozen_wv has not been called");
-        wvt = h->wv_frozen;
-    } else {
-        wvt = d_theta + dm.oWVint;
-    }
-    h->launches = 0;
-    const bool prof = h->profiling;
-    const int slot = h->ring_pos;
-    h->ring_pos = (slot + 1) % NTN_RING;
-    if (prof) drain_profile_slot(h, slot);
-    // phase p runs on stream st: bracket it with its own event pair (phases on forked streams overlap)
+// Enqueue the kernels of one evaluation on h->stream with its forked branches (also what gets captured
+// into the CUDA graph).  prof: bracket every phase with its own event pair.
+static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_grad, const float* wvt, bool prof, int slot) {
     auto begin = [&](int p, cudaStream_t st) { if (prof) cudaEventRecord(h->ev[slot][p][0], st); };
     auto end = [&](int p, cudaStream_t st) { if (prof) cudaEventRecord(h->ev[slot][p][1], st); };
     enum { P_EB, P_WP, P_FWD, P_SC, P_DW, P_GE, P_EP, P_WPULL, P_FIN };
-    // pinned ring slot: wait only for the evaluation that used this slot NTN_RING calls ago
-    CK(cudaEventSynchronize(h->side_ev[slot]));
-    uint8_t* hs = h->h_side + (size_t)slot * dm.R;
-    for (int r = 0; r < dm.R; ++r) hs[r] = corrupt_side[r] ? 1 : 0;
     cudaStream_t s0 = h->stream, s1 = h->stream3;
-    CK(cudaMemcpyAsync(h->side, hs, dm.R, cudaMemcpyHostToDevice, s0));
-    CK(cudaEventRecord(h->side_ev[slot], s0));
     const bool tc = h->gemm_path_active == NTN_GEMM_TCGEN05 && h->b.ntiles > 0;
     int rc;
     // ---- fork: weight preparation runs beside the entity build
@@ -480,8 +464,68 @@ static int eval_internal(ntn_handle* h, const float* d_theta, const uint8_t* cor
     begin(P_WPULL, s0); ntn_launch_word_pull(h, d_theta, d_grad); end(P_WPULL, s0);           // :411-430
     CK(cudaStreamWaitEvent(s0, h->ev_j1, 0));
     ntn_launch_final_reduce(h);                                                               // :430,437
-    if (prof) h->ev_pending[slot] = true;
-    CK(cudaMemcpyAsync(h->h_out, h->d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_out, h->d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, s0));
+    return NTN_OK;
+}
+
+void ntn_drop_graphs(ntn_handle* h) {
+    for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
+// ------------------------------------------------------------------------------------------
+// the evaluation driver                                          NTN.computeAt, NTN.java:92-443
+// ------------------------------------------------------------------------------------------
+static int eval_internal(ntn_handle* h, const float* d_theta, const uint8_t* corrupt_side, float* d_grad) {
+    const NtnDims& dm = h->dm;
+    if (!h->w.set) FAIL(NTN_ESTATE, "ntn_set_entity_words has not been called");
+    if (!corrupt_side) FAIL(NTN_EINVAL, "corrupt_side is null");
+    const float* wvt;
+    if (h->cfg.wv_source == NTN_WV_FROZEN) {
+        if (!h->wv_frozen) FAIL(NTN_ESTATE, "wv_source is NTN_WV_FROZEN but ntn_set_frozen_wv has not been called");
+        wvt = h->wv_frozen;
+    } else {
+        wvt = d_theta + dm.oWVint;
+    }
+    const bool prof = h->profiling;
+    const int slot = h->ring_pos;
+    h->ring_pos = (slot + 1) % NTN_RING;
+    if (prof) drain_profile_slot(h, slot);
+    // pinned ring slot: wait only for the evaluation that used this slot NTN_RING calls ago
+    CK(cudaEventSynchronize(h->side_ev[slot]));
+    uint8_t* hs = h->h_side + (size_t)slot * dm.R;
+    for (int r = 0; r < dm.R; ++r) hs[r] = corrupt_side[r] ? 1 : 0;
+    CK(cudaMemcpyAsync(h->side, hs, dm.R, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->side_ev[slot], h->stream));
+    int rc;
+    if (prof || !h->use_graph || h->stream == nullptr /* legacy default stream cannot be captured */) {
+        h->launches = 0;
+        if ((rc = enqueue_eval_kernels(h, d_theta, d_grad, wvt, prof, slot))) return rc;
+        if (prof) h->ev_pending[slot] = true;
+    } else {
+        // the kernel sequence (with its forked branches) is captured once per (theta, grad) buffer pair and
+        // replayed: the evaluation is a dozen short kernels, so launch latency and inter-kernel gaps matter
+        ntn_handle::GraphEntry* ge = nullptr;
+        for (auto& g : h->graphs) if (g.theta == d_theta && g.grad == d_grad && g.stream == h->stream) ge = &g;
+        if (!ge) {
+            if (h->graphs.size() >= 8) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+            cudaGraph_t graph = nullptr;
+            h->launches = 0;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_eval_kernels(h, d_theta, d_grad, wvt, false, slot);
+            cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) FAIL(NTN_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+            ntn_handle::GraphEntry ne{d_theta, d_grad, h->stream, nullptr, h->launches};
+            e = cudaGraphInstantiate(&ne.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) FAIL(NTN_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+            h->graphs.push_back(ne);
+            ge = &h->graphs.back();
+        }
+        h->launches = ge->launches;
+        CK(cudaGraphLaunch(ge->exec, h->stream));
+    }
     CK(cudaGetLastError());
     return NTN_OK;
 }
