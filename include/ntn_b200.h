@@ -142,6 +142,26 @@ int ntn_set_stream(ntn_handle* h, void* cuda_stream);
 int ntn_reset_stream(ntn_handle* h);
 void* ntn_get_stream(ntn_handle* h);
 
+/* ---- optimiser: device-resident L-BFGS (Run_NTN.java:119-124) ----------------------------- */
+/* The reference's minimiser (umass-nlp LBFGSMinimizer) is an un-vendored jar; the algorithm used here is
+ * defined in csrc/lbfgs.cu / DESIGN.md (parity unpinned).  theta stays in HBM (internal layout); every trial
+ * point is one ntn_eval_dev on the current batch job; sides_fn is called once per evaluation to draw that
+ * evaluation's corrupt sides (the reference draws Math.random() inside computeAt, NTN.java:146). */
+typedef void (*ntn_sides_fn)(void* ctx, uint8_t* corrupt_side /* R, to fill */);
+typedef struct ntn_lbfgs_opts {
+    int32_t max_iters;      /* LBFGSMinimizer.Opts.maxIters; Run_NTN sets 5 (batch_iterations)   */
+    int32_t history;        /* curvature pairs kept (0 = default 6)                              */
+    double  tol;            /* relative function-change tolerance (0 = default 1e-4)             */
+} ntn_lbfgs_opts;
+typedef struct ntn_lbfgs_result {
+    double  min_obj_val;    /* IOptimizer.Result.minObjVal */
+    double  first_cost;     /* cost at the starting point   */
+    int32_t iters, evals, did_converge;
+    int64_t n_active_last;
+} ntn_lbfgs_result;
+int ntn_lbfgs_minimize(ntn_handle* h, float* d_theta /* device, internal layout, in/out */,
+                       const ntn_lbfgs_opts* opts, ntn_sides_fn sides_fn, void* ctx, ntn_lbfgs_result* result);
+
 /* ---- eval-side scoring ("next" row N1) -------------------------------------------------- */
 /* Scores of n triples (NTN.computeBestThresholds / getPrediction, NTN.java:587-712). */
 int ntn_score(ntn_handle* h, const double* theta, int64_t n,

@@ -35,6 +35,17 @@ class Config(C.Structure):
                 ("reg_scale", C.c_float)]
 
 
+class LbfgsOpts(C.Structure):
+    _fields_ = [("max_iters", C.c_int32), ("history", C.c_int32), ("tol", C.c_double)]
+
+
+class LbfgsResult(C.Structure):
+    _fields_ = [("min_obj_val", C.c_double), ("first_cost", C.c_double), ("iters", C.c_int32), ("evals", C.c_int32),
+                ("did_converge", C.c_int32), ("n_active_last", C.c_int64)]
+
+
+SIDES_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_uint8))
+
 # name -> (restype, argtypes): every symbol include/ntn_b200.h declares
 _P = C.c_void_p
 _I32P = C.POINTER(C.c_int32)
@@ -59,6 +70,7 @@ SYMBOLS = {
     "ntn_set_stream": (C.c_int, [_P, _P]),
     "ntn_reset_stream": (C.c_int, [_P]),
     "ntn_get_stream": (_P, [_P]),
+    "ntn_lbfgs_minimize": (C.c_int, [_P, _P, C.POINTER(LbfgsOpts), SIDES_FN, _P, C.POINTER(LbfgsResult)]),
     "ntn_score": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, _P]),
     "ntn_last_launch_count": (C.c_int, [_P]),
     "ntn_active_gemm_path": (C.c_int, [_P]),
@@ -226,6 +238,20 @@ class Handle:
         m = {"reference_eval": SCORE_REFERENCE_EVAL, "train": SCORE_TRAIN}[mode]
         self._ck(self.lib.ntn_score(self.h, _ptr(theta), len(e1), _ptr(e1), _ptr(rel), _ptr(e2), m, _ptr(out)))
         return out
+
+    def lbfgs_minimize(self, d_theta: int, draw_sides, max_iters=5, history=0, tol=0.0):
+        """Device-resident L-BFGS on the current batch job; ``draw_sides()`` returns this evaluation's
+        corrupt sides (uint8[R]).  Returns the LbfgsResult; theta is updated in place on the device."""
+        R = self.R
+
+        def _cb(_ctx, out):
+            s = np.ascontiguousarray(draw_sides(), np.uint8)
+            for r in range(R):
+                out[r] = int(s[r])
+        cb = SIDES_FN(_cb)
+        opts, res = LbfgsOpts(max_iters, history, tol), LbfgsResult()
+        self._ck(self.lib.ntn_lbfgs_minimize(self.h, d_theta, C.byref(opts), cb, None, C.byref(res)))
+        return res
 
     def debug_fetch(self, name):
         n = self.lib.ntn_debug_fetch(self.h, name.encode(), None, 0)

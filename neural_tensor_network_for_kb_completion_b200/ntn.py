@@ -28,6 +28,7 @@ class NTN:
         self.activationFunc = activation_function
         self.update = 0                                            # NTN.java:39,66
         self.tbj = tbj
+        self.device = device
         self.side_rand = JavaRandom(side_seed)
         self.handle = _capi.Handle(embeddingSize, numberOfEntities, numberOfRelations, numberOfWords,
                                    batchSize, self.lamda, activation=activation_function,

@@ -104,3 +104,38 @@ def make_shaped(shape: str, d: int = 100, Nw: int = 67447, T: int | None = None,
     Ne, R, T_full, n_dev, n_test = SHAPES[shape]
     return make_kb(Ne, R, T_full if T is None else T, Nw, d,
                    n_dev if with_eval else 0, n_test if with_eval else 0, seed=seed)
+
+
+def make_structured_kb(Ne=600, R=4, T=3000, d=16, clusters=12, n_dev=400, n_test=400, seed=0) -> SyntheticKB:
+    """A small KB with learnable structure, for the train -> threshold -> accuracy flow: every entity
+    belongs to a latent cluster and is named after its cluster's word plus a private word; relation r
+    links cluster c to cluster (a_r*c + b_r) mod clusters.  Positives follow the rule, negatives do not."""
+    rng = np.random.default_rng(seed)
+    cl = rng.integers(0, clusters, size=Ne)
+    vocab_words = [f"c{i}" for i in range(clusters)] + [f"p{i}" for i in range(Ne)] + ["unknown"]
+    names = [f"__c{cl[n]}_p{n}_{1 + n % 9}" for n in range(Ne)]
+    Nw = len(vocab_words)
+    wv = (np.random.default_rng(seed + 1).standard_normal((d, Nw)) * 0.1).astype(np.float32)
+    a = rng.integers(1, clusters, size=R) | 1
+    b = rng.integers(0, clusters, size=R)
+    members = [np.nonzero(cl == c)[0] for c in range(clusters)]
+
+    def sample(n, positive):
+        rel = rng.integers(0, R, size=n)
+        e1 = rng.integers(0, Ne, size=n)
+        tgt = (a[rel] * cl[e1] + b[rel]) % clusters
+        if not positive:
+            tgt = (tgt + rng.integers(1, clusters, size=n)) % clusters
+        e2 = np.array([rng.choice(members[t]) if len(members[t]) else rng.integers(0, Ne) for t in tgt])
+        return np.stack([e1, rel, e2], 1).astype(np.int32)
+
+    def labelled(n):
+        pos, neg = sample(n // 2, True), sample(n - n // 2, False)
+        t = np.concatenate([pos, neg])
+        lab = np.r_[np.ones(len(pos), np.int32), -np.ones(len(neg), np.int32)]
+        perm = rng.permutation(n)
+        return np.concatenate([t, lab[:, None]], 1)[perm].astype(np.int32)
+
+    return SyntheticKB(d=d, entity_names=names, vocab_words=vocab_words, wv=wv,
+                       relations=[f"_rel{i}" for i in range(R)], train=sample(T, True),
+                       dev=labelled(n_dev), test=labelled(n_test))

@@ -324,3 +324,30 @@ def test_full_size_wordnet_shape_against_oracle():
     print(f"full-size: cost {cost:.8f} vs {c_ref:.8f}; n_active {nact} vs {aux['n_active']}; "
           f"max|dgrad| {np.abs(grad - g_ref).max():.3e}; min|margin| {aux['min_abs_margin']:.2e}")
     h.close()
+
+
+def test_device_lbfgs_matches_numpy_definition():
+    """csrc/lbfgs.cu against oracle/lbfgs_ref.py (same algorithm, float64, oracle cost/grad) with the corrupt
+    sides held fixed so the objective is deterministic: same iteration/evaluation counts, same decrease."""
+    from neural_tensor_network_for_kb_completion_b200.lbfgs import LBFGSMinimizer, Opts
+    from oracle import lbfgs_ref
+    kb, p, batch, side, theta0 = small_problem(Ne=300, R=4, T=500, Nw=200, d=20, batch=400, corrupt=5, seed=12, lam=1e-3)
+    theta = f32(theta0)
+    h = make_handle(p, "theta")
+    h.set_batch(*batch)
+
+    class Fn:                                   # minimal stand-in for the NTN mirror: fixed sides
+        handle, device, update = h, 0, 0
+        def _sync_batch(self): pass
+        def drawCorruptSides(self): return side
+    res = LBFGSMinimizer().minimize(Fn(), theta, Opts(maxIters=5))
+    ref_theta, ref_f, ref_it, ref_ev, _ = lbfgs_ref.minimize(lambda t: ntn_ref.compute_at(t, p, *batch, side), theta, 5)
+    c0 = ntn_ref.compute_at(theta, p, *batch, side)[0]
+    assert res.firstObjVal == pytest.approx(c0, rel=1e-5)
+    assert res.minObjVal < c0 and ref_f < c0
+    assert (res.iters, res.evals) == (ref_it, ref_ev)
+    assert res.minObjVal == pytest.approx(ref_f, rel=2e-3)
+    assert np.linalg.norm(res.minArg - ref_theta) <= 2e-2 * np.linalg.norm(ref_theta - theta)
+    # the returned argument really has the returned objective value
+    assert ntn_ref.compute_at(res.minArg, p, *batch, side)[0] == pytest.approx(res.minObjVal, rel=1e-4)
+    h.close()

@@ -1,0 +1,98 @@
+"""End-to-end Run_NTN flow on the GPU (train -> thresholds -> accuracy) against the same flow driven by the
+CPU oracle (same seeds, same L-BFGS definition, same threshold sweep): final dev/test accuracy within the
+north-star band.  Also the loaders / checkpoint formats (next rows N2, N3) on files written in the Socher
+layout."""
+import os
+
+import numpy as np
+import pytest
+
+from neural_tensor_network_for_kb_completion_b200 import run_ntn, synth
+from neural_tensor_network_for_kb_completion_b200.data_factory import DataFactory, JavaRandom
+from oracle import data_ref, lbfgs_ref, ntn_ref
+from oracle.java_random import JavaRandom as OracleRandom
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_flow(kb, cfg):
+    """Run_NTN.java:103-149 with every number computed by the oracle (float64)."""
+    vocab = {w: i for i, w in enumerate(kb.vocab_words)}
+    fo, fi, bo, bi, lb = data_ref.build_entity_word_maps(kb.entity_names, vocab)
+    p = ntn_ref.NTNProblem(d=kb.d, k=cfg.sliceSize, R=kb.R, Ne=kb.Ne, Nw=kb.Nw, lam=cfg.lamda, batch_size=cfg.batchSize,
+                           fwd_off=fo, fwd_idx=fi, bwd_off=bo, bwd_idx=bi, len_bwd=lb)
+    e3_rand, side_rand = OracleRandom(cfg.seed), OracleRandom(7)
+    # same theta0 as the NTN mirror (init_seed=3)
+    rng = np.random.default_rng(3)
+    r = 1.0 / np.sqrt(2.0 * kb.d)
+    theta = np.concatenate([rng.random(kb.R * cfg.sliceSize * kb.d * kb.d) * r, np.full(kb.R * 2 * kb.d * cfg.sliceSize, 0.4),
+                            np.full(kb.R * cfg.sliceSize, 0.01), np.full(kb.R * cfg.sliceSize, 0.8),
+                            kb.wv.astype(np.float64).ravel()]).astype(np.float32).astype(np.float64)
+    wvf = kb.wv if cfg.wv_source == "frozen" else None
+    for _ in range(cfg.numIterations):
+        batch = data_ref.generate_batch_job(kb.train[:, 0], kb.train[:, 1], kb.train[:, 2], cfg.batchSize, cfg.corrupt_size,
+                                            kb.Ne, e3_rand)
+
+        def fn(th):
+            side = data_ref.draw_corrupt_sides(batch[1], kb.R, side_rand)
+            return ntn_ref.compute_at(th, p, *batch, side, wv_frozen=wvf)
+        theta = lbfgs_ref.minimize(fn, theta, cfg.batch_iterations)[0]
+    s_dev = ntn_ref.score_triples_reference_eval(theta, p, kb.dev[:, 0], kb.dev[:, 1], kb.dev[:, 2], wv_frozen=wvf)
+    thr, _ = ntn_ref.compute_best_thresholds(s_dev, kb.dev[:, 1], kb.dev[:, 3], kb.R)
+    s_test = ntn_ref.score_triples_reference_eval(theta, p, kb.test[:, 0], kb.test[:, 1], kb.test[:, 2], wv_frozen=wvf)
+    return (ntn_ref.get_prediction(s_dev, kb.dev[:, 1], kb.dev[:, 3], thr)[1],
+            ntn_ref.get_prediction(s_test, kb.test[:, 1], kb.test[:, 3], thr)[1], theta)
+
+
+@pytest.mark.parametrize("wv_source", ["theta", "frozen"])
+def test_train_threshold_accuracy_flow_matches_oracle_flow(wv_source):
+    kb = synth.make_structured_kb(Ne=400, R=3, T=1500, d=12, clusters=8, n_dev=1000, n_test=1000, seed=1)
+    cfg = run_ntn.Config(batchSize=1000, numWVdimensions=12, numIterations=6, batch_iterations=5, sliceSize=2,
+                         corrupt_size=4, lamda=1e-4, wv_source=wv_source, seed=42)
+    tbj = DataFactory.from_kb(kb, cfg.batchSize, cfg.corrupt_size, seed=cfg.seed)
+    out = run_ntn.train_and_evaluate(tbj, cfg, log=lambda *_: None)
+    dev_ref, test_ref, theta_ref = oracle_flow(kb, cfg)
+    first, last = out["history"][0][0], out["history"][-1][1]
+    assert last < first                                            # training reduces the objective
+    if wv_source == "theta":
+        assert out["accuracy"] > 0.6                               # and the structure is learnt
+    # north star: final dev/test accuracy within 0.2 points of the reference flow.  With 1000 labelled triples one
+    # flipped prediction is 0.1 point; FP32-vs-FP64 trajectories may flip a couple.
+    assert abs(out["dev_accuracy"] - dev_ref) <= 0.004, (out["dev_accuracy"], dev_ref)
+    assert abs(out["accuracy"] - test_ref) <= 0.004, (out["accuracy"], test_ref)
+
+
+def test_socher_files_mat_vectors_and_theta_checkpoints(tmp_path):
+    from scipy.io import savemat
+    kb = synth.make_structured_kb(Ne=120, R=3, T=300, d=8, clusters=6, n_dev=40, n_test=40, seed=2)
+    d = str(tmp_path)
+    open(os.path.join(d, "entities.txt"), "w").write("\n".join(kb.entity_names) + "\n")
+    open(os.path.join(d, "relations.txt"), "w").write("\n".join(kb.relations) + "\n")
+    name = lambda t: f"{kb.entity_names[t[0]]}\t{kb.relations[t[1]]}\t{kb.entity_names[t[2]]}"
+    open(os.path.join(d, "train.txt"), "w").write("\n".join(name(t) for t in kb.train) + "\n")
+    for fn, arr in (("dev.txt", kb.dev), ("test.txt", kb.test)):
+        open(os.path.join(d, fn), "w").write("\n".join(name(t) + f"\t{t[3]}" for t in arr) + "\n")
+    words = np.empty((1, kb.Nw), dtype=object)
+    for i, w in enumerate(kb.vocab_words):
+        words[0, i] = np.array([w])
+    savemat(os.path.join(d, "initEmbed.mat"), {"words": words, "We": kb.wv.T.astype(np.float64)})   # Nw x d (App. B15)
+    cfg = run_ntn.Config(batchSize=100, numWVdimensions=8, numIterations=2, batch_iterations=2, sliceSize=2, corrupt_size=2)
+    tbj = run_ntn.load_data(d, cfg)
+    ref = DataFactory.from_kb(kb, 100, 2)
+    assert tbj.getNumOfentities() == kb.Ne and tbj.getNumOfRelations() == kb.R and tbj.getNumOfWords() == kb.Nw
+    assert np.array_equal(tbj.trainingTripples, kb.train) and np.array_equal(tbj.devTripples, kb.dev)
+    assert np.allclose(tbj.getWordVectorMaxtrixLoaded(), kb.wv)
+    for a, b in zip(tbj.entityWordMaps(), ref.entityWordMaps()):
+        assert np.array_equal(a, b)
+    out = run_ntn.train_and_evaluate(tbj, cfg, theta_save_path=d, log=lambda *_: None)
+    ck = os.path.join(d, "theta_opt_iteration_0.txt")
+    assert os.path.exists(ck)
+    back = run_ntn.read_theta_txt(ck)
+    assert back.shape == out["theta"].shape and np.all(np.isfinite(back))
+
+
+def test_host_java_random_is_bit_exact_with_oracle():
+    a, b = JavaRandom(42), OracleRandom(42)
+    assert a.nextInts(2000, 75043).tolist() == [b.next_int(75043) for _ in range(2000)]
+    assert [a.nextDouble() for _ in range(50)] == [b.next_double() for _ in range(50)]
+    assert a.nextInts(100, 1024).tolist() == [b.next_int(1024) for _ in range(100)]
