@@ -30,7 +30,7 @@ class NTN:
         self.tbj = tbj
         self.device = device
         self.side_rand = JavaRandom(side_seed)
-        self.handle = _capi.Handle(embeddingSize, numberOfEntities, numberOfRelations, numberOfWords,
+        self.handle = _capi.Handle(embeddingSize, sliceSize, numberOfRelations, numberOfEntities, numberOfWords,
                                    batchSize, self.lamda, activation=activation_function,
                                    wv_source=wv_source, gemm_path=gemm_path, device=device, reg_scale=reg_scale)
         self.handle.set_entity_words(*tbj.entityWordMaps())
