@@ -184,6 +184,16 @@ const char* ntn_phase_name(int i);
  * to the host; returns its element count (call with out == NULL to size the buffer), -1 if unknown. */
 int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, int64_t cap);
 
+/* ---- C++ host layer test hooks (csrc/host/ntn_host.hpp; no GPU needed) ----------------------- */
+/* java.util.Random: n draws of nextInt(bound) (bound == 0: nextInt()), then m draws of nextDouble(). */
+int ntn_host_java_random(int64_t seed, int32_t bound, int64_t n, int32_t* ints, int64_t m, double* doubles);
+/* DataFactory name parsing: '\n'-separated entity names and vocabulary -> forward / backward CSRs. */
+int ntn_host_entity_word_maps(const char* names, const char* words, int32_t* fwd_off, int32_t* fwd_idx, int32_t* bwd_off,
+                              int32_t* bwd_idx, int32_t* len_bwd, int64_t cap, int64_t* nf, int64_t* nb);
+/* DataFactory.generateNewTrainingBatchJob (DataFactory.java:116-136), columns of the `calls`-th batch job. */
+int ntn_host_generate_batch(const int32_t* train, int64_t ntrain, int32_t batch, int32_t corrupt, int32_t num_entities,
+                            int64_t seed, int32_t calls, int32_t* e1, int32_t* rel, int32_t* e2, int32_t* e3);
+
 const char* ntn_version(void);
 
 #ifdef __cplusplus

@@ -78,6 +78,10 @@ SYMBOLS = {
     "ntn_last_phase_ms": (C.c_int, [_P, _P]),
     "ntn_phase_name": (C.c_char_p, [C.c_int]),
     "ntn_debug_fetch": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64]),
+    "ntn_host_java_random": (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _P, C.c_int64, _P]),
+    "ntn_host_entity_word_maps": (C.c_int, [C.c_char_p, C.c_char_p, _P, _P, _P, _P, _P, C.c_int64,
+                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ntn_host_generate_batch": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "ntn_version": (C.c_char_p, []),
 }
 

@@ -1,0 +1,58 @@
+// C-ABI test hooks over the C++ host layer (csrc/host/ntn_host.hpp): the CPU test-suite checks these
+// bit-exactly against the oracle (java.util.Random stream, entity/word maps, batch job order).
+#include <cstring>
+
+#include "host/ntn_host.hpp"
+
+using namespace ntnhost;
+
+extern "C" {
+
+// n draws of nextInt(bound) (bound > 0) or nextInt() (bound == 0), then m draws of nextDouble()
+int ntn_host_java_random(int64_t seed, int32_t bound, int64_t n, int32_t* ints, int64_t m, double* doubles) {
+    try {
+        JavaRandom r(seed);
+        for (int64_t i = 0; i < n; ++i) ints[i] = bound > 0 ? r.nextInt(bound) : r.nextInt();
+        for (int64_t i = 0; i < m; ++i) doubles[i] = r.nextDouble();
+        return NTN_OK;
+    } catch (...) { return NTN_EINVAL; }
+}
+
+// names / words: '\n'-separated.  Outputs sized by the caller: fwd_off, bwd_off (Ne+1), len_bwd (Ne),
+// fwd_idx / bwd_idx (cap entries each); *nf, *nb receive the used counts.
+int ntn_host_entity_word_maps(const char* names, const char* words, int32_t* fwd_off, int32_t* fwd_idx, int32_t* bwd_off,
+                              int32_t* bwd_idx, int32_t* len_bwd, int64_t cap, int64_t* nf, int64_t* nb) {
+    try {
+        auto split = [](const char* s) { std::vector<std::string> v; std::string cur;
+            for (const char* p = s; *p; ++p) { if (*p == '\n') { v.push_back(cur); cur.clear(); } else cur.push_back(*p); }
+            if (!cur.empty()) v.push_back(cur);
+            return v; };
+        DataFactory f(1, 1, 1);
+        f.setEntities(split(names)); f.setVocabulary(split(words));
+        std::vector<int32_t> fo, fi, bo, bi, lb;
+        f.entityWordMaps(fo, fi, bo, bi, lb);
+        if ((int64_t)fi.size() > cap || (int64_t)bi.size() > cap) return NTN_EINVAL;
+        memcpy(fwd_off, fo.data(), fo.size() * 4); memcpy(bwd_off, bo.data(), bo.size() * 4); memcpy(len_bwd, lb.data(), lb.size() * 4);
+        memcpy(fwd_idx, fi.data(), fi.size() * 4); memcpy(bwd_idx, bi.data(), bi.size() * 4);
+        *nf = (int64_t)fi.size(); *nb = (int64_t)bi.size();
+        return NTN_OK;
+    } catch (...) { return NTN_EINVAL; }
+}
+
+// DataFactory.generateNewTrainingBatchJob over `ntrain` training triples (e1, rel, e2 interleaved), called `calls` times;
+// the columns of the LAST call are written (batch*corrupt entries each).
+int ntn_host_generate_batch(const int32_t* train, int64_t ntrain, int32_t batch, int32_t corrupt, int32_t num_entities,
+                            int64_t seed, int32_t calls, int32_t* e1, int32_t* rel, int32_t* e2, int32_t* e3) {
+    try {
+        DataFactory f(batch, corrupt, 1, false, seed);
+        std::vector<std::string> names((size_t)num_entities, "__x_1");
+        f.entitiesNumWord = names;
+        for (int64_t i = 0; i < ntrain; ++i) f.trainingTripples.push_back(Tripple{train[3 * i], train[3 * i + 1], train[3 * i + 2], 0});
+        for (int c = 0; c < calls; ++c) f.generateNewTrainingBatchJob();
+        size_t n = f.bj_e1.size();
+        memcpy(e1, f.bj_e1.data(), n * 4); memcpy(rel, f.bj_rel.data(), n * 4); memcpy(e2, f.bj_e2.data(), n * 4); memcpy(e3, f.bj_e3.data(), n * 4);
+        return NTN_OK;
+    } catch (...) { return NTN_EINVAL; }
+}
+
+}  // extern "C"

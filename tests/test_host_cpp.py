@@ -1,0 +1,71 @@
+"""The compiled (C++) host layer -- csrc/host/ntn_host.hpp through its C-ABI test hooks -- against the oracle,
+bit for bit: java.util.Random stream, entity-name parsing -> forward/backward word maps (with the reference's
+malformed-name quirks), batch-job order and corrupt indices.  No GPU needed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from neural_tensor_network_for_kb_completion_b200 import _capi, synth
+from oracle import data_ref
+from oracle.java_random import JavaRandom
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_capi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _capi.load()
+
+
+def jr(lib, seed, bound, n, m=0):
+    ints, dbl = np.zeros(max(n, 1), np.int32), np.zeros(max(m, 1), np.float64)
+    assert lib.ntn_host_java_random(seed, bound, n, ints.ctypes.data, m, dbl.ctypes.data) == 0
+    return ints[:n], dbl[:m]
+
+
+def test_cpp_java_random_known_answers_and_stream(lib):
+    assert jr(lib, 42, 0, 1)[0][0] == -1170105035 and jr(lib, 0, 0, 1)[0][0] == -1155484576
+    assert jr(lib, 42, 100, 5)[0].tolist() == [30, 63, 48, 84, 70]
+    assert jr(lib, 42, 75043, 8)[0].tolist() == [35870, 25511, 45555, 64931, 40108, 3288, 5558, 26082]
+    assert jr(lib, 42, 0, 0, 3)[1].tolist() == [0.7275636800328681, 0.6832234717598454, 0.30871945533265976]
+    for seed, bound in ((7, 38696), (123456789, 1024), (-5, 3), (99, (1 << 30) + 1)):
+        ints, dbl = jr(lib, seed, bound, 3000, 100)
+        r = JavaRandom(seed)
+        assert ints.tolist() == [r.next_int(bound) for _ in range(3000)]
+        assert dbl.tolist() == [r.next_double() for _ in range(100)]
+
+
+def test_cpp_entity_word_maps_match_oracle_including_quirks(lib):
+    kb = synth.make_kb(800, 5, 10, 120, 4, oov_frac=0.15, seed=5)
+    names = list(kb.entity_names)
+    names[3], names[9], names[17], names[40] = "__w1__1", "__2", "__w5_w6_w7_w8_3", "__a_"
+    vocab = {w: i for i, w in enumerate(kb.vocab_words)}
+    want = data_ref.build_entity_word_maps(names, vocab)
+    Ne, cap = len(names), 8 * len(names)
+    fo, bo, lb = np.zeros(Ne + 1, np.int32), np.zeros(Ne + 1, np.int32), np.zeros(Ne, np.int32)
+    fi, bi = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    nf, nb = C.c_int64(), C.c_int64()
+    rc = lib.ntn_host_entity_word_maps("\n".join(names).encode(), "\n".join(kb.vocab_words).encode(), fo.ctypes.data,
+                                       fi.ctypes.data, bo.ctypes.data, bi.ctypes.data, lb.ctypes.data, cap, C.byref(nf), C.byref(nb))
+    assert rc == 0
+    got = (fo, fi[:nf.value], bo, bi[:nb.value], lb)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    assert not np.array_equal(fo, bo)                       # the malformed names make the two lists differ
+
+
+def test_cpp_batch_job_matches_oracle_across_consecutive_jobs(lib):
+    kb = synth.make_kb(500, 4, 300, 50, 4, seed=6)
+    train = np.ascontiguousarray(kb.train, np.int32)
+    B, Cc, n = 120, 7, 120 * 7
+    out = [np.zeros(n, np.int32) for _ in range(4)]
+    rc = lib.ntn_host_generate_batch(train.ctypes.data, len(train), B, Cc, kb.Ne, 42, 3, *(o.ctypes.data for o in out))
+    assert rc == 0
+    r = JavaRandom(42)
+    for _ in range(3):                                      # the Random stream continues from job to job
+        want = data_ref.generate_batch_job(train[:, 0], train[:, 1], train[:, 2], B, Cc, kb.Ne, r)
+    for a, b in zip(out, want):
+        assert np.array_equal(a, b)
