@@ -6,7 +6,6 @@
 #include <cstring>
 #include <cstdlib>
 #include <numeric>
-#include <thread>
 
 #include "ntn_internal.h"
 
@@ -172,6 +171,7 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     if (h->h_side) cudaFreeHost(h->h_side);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_stage) cudaFreeHost(h->h_stage);
+    for (cudaEvent_t e : h->xfer_ev) cudaEventDestroy(e);
     for (int s = 0; s < NTN_RING; ++s) {
         if (h->side_ev[s]) cudaEventDestroy(h->side_ev[s]);
         for (int i = 0; i < NTN_NUM_PHASES; ++i) for (int q = 0; q < 2; ++q) if (h->ev[s][i][q]) cudaEventDestroy(h->ev[s][i][q]);
@@ -577,19 +577,46 @@ extern "C" int ntn_from_internal_dev(ntn_handle* h, const float* d_int, float* d
     return NTN_OK;
 }
 
-// host <-> pinned staging with type conversion, split over a few threads (the arrays are ~57 MB)
-template <typename S, typename D> static void convert_parallel(const S* src, D* dst, int64_t n) {
-    unsigned hw = std::thread::hardware_concurrency();
-    int nt = (int)std::min<int64_t>(std::max(1u, std::min(hw, 8u)), std::max<int64_t>(1, n / (1 << 18)));
-    auto work = [=](int t) {
-        int64_t a = n * t / nt, b = n * (t + 1) / nt;
-        for (int64_t i = a; i < b; ++i) dst[i] = (D)src[i];      // double -> float rounds like Util.java:49-55
-    };
-    if (nt <= 1) { work(0); return; }
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto& x : th) x.join();
+// host <-> pinned staging with type conversion.  The arrays are ~57 MB; conversion runs on an OpenMP pool and is
+// pipelined against the PCIe copies in NTN_XFER_CHUNK-element chunks (convert chunk i+1 while chunk i is in flight).
+#define NTN_XFER_CHUNK (1 << 21)
+template <typename S, typename D> static void convert_range(const S* src, D* dst, int64_t n) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) dst[i] = (D)src[i];          // double -> float rounds like Util.java:49-55
+}
+template <typename S, typename D> static void convert_parallel(const S* src, D* dst, int64_t n) { convert_range(src, dst, n); }
+
+// theta (host, S) -> pinned float staging -> device, chunk-pipelined
+template <typename S> static cudaError_t upload_pipelined(ntn_handle* h, const S* src, float* d_dst, int64_t n) {
+    for (int64_t o = 0; o < n; o += NTN_XFER_CHUNK) {
+        int64_t c = std::min<int64_t>(NTN_XFER_CHUNK, n - o);
+        convert_range(src + o, h->h_stage + o, c);
+        cudaError_t e = cudaMemcpyAsync(d_dst + o, h->h_stage + o, (size_t)c * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+// device -> pinned float staging -> host (D), chunk-pipelined on the handle's stream
+template <typename D> static cudaError_t download_pipelined(ntn_handle* h, const float* d_src, D* dst, int64_t n) {
+    const int nchunks = (int)((n + NTN_XFER_CHUNK - 1) / NTN_XFER_CHUNK);
+    if ((int)h->xfer_ev.size() < nchunks) {
+        size_t old = h->xfer_ev.size();
+        h->xfer_ev.resize(nchunks);
+        for (size_t i = old; i < h->xfer_ev.size(); ++i) cudaEventCreateWithFlags(&h->xfer_ev[i], cudaEventDisableTiming);
+    }
+    for (int i = 0; i < nchunks; ++i) {
+        int64_t o = (int64_t)i * NTN_XFER_CHUNK, c = std::min<int64_t>(NTN_XFER_CHUNK, n - o);
+        cudaError_t e = cudaMemcpyAsync(h->h_stage + o, d_src + o, (size_t)c * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) return e;
+        cudaEventRecord(h->xfer_ev[i], h->stream);
+    }
+    for (int i = 0; i < nchunks; ++i) {
+        int64_t o = (int64_t)i * NTN_XFER_CHUNK, c = std::min<int64_t>(NTN_XFER_CHUNK, n - o);
+        cudaError_t e = cudaEventSynchronize(h->xfer_ev[i]);
+        if (e != cudaSuccess) return e;
+        convert_range(h->h_stage + o, dst + o, c);
+    }
+    return cudaSuccess;
 }
 
 static int ensure_host_path(ntn_handle* h) {
@@ -612,19 +639,15 @@ static int eval_host(ntn_handle* h, const TH* theta, const uint8_t* corrupt_side
     if (rc) return rc;
     const NtnDims& dm = h->dm;
     CK(cudaStreamSynchronize(h->stream));
-    convert_parallel(theta, h->h_stage, dm.P);
-    CK(cudaMemcpyAsync(h->d_ref_theta, h->h_stage, (size_t)dm.P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(upload_pipelined(h, theta, h->d_ref_theta, dm.P));
     ntn_launch_to_internal(h, h->d_ref_theta, h->d_int_theta);
     rc = eval_internal(h, h->d_int_theta, corrupt_side, h->d_int_grad);
     if (rc) return rc;
     int launches = h->launches + 2;
     ntn_launch_from_internal(h, h->d_int_grad, h->d_ref_grad);
     h->launches = launches + 2;
-    CK(cudaMemcpyAsync(h->h_stage, h->d_ref_grad, (size_t)dm.P * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    rc = ntn_last_cost(h, cost, n_active);
-    if (rc) return rc;
-    convert_parallel(h->h_stage, grad, dm.P);
-    return NTN_OK;
+    CK(download_pipelined(h, h->d_ref_grad, grad, dm.P));
+    return ntn_last_cost(h, cost, n_active);
 }
 
 extern "C" int ntn_eval(ntn_handle* h, const double* theta, const uint8_t* corrupt_side, double* cost, double* grad,

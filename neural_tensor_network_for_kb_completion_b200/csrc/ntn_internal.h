@@ -114,6 +114,7 @@ struct ntn_handle {
     float *d_ref_theta = nullptr, *d_ref_grad = nullptr;   // P (reference order)
     float *d_int_theta = nullptr, *d_int_grad = nullptr;   // Pint
     float *h_stage = nullptr;     // pinned, P floats
+    std::vector<cudaEvent_t> xfer_ev;   // per-chunk D2H completion events
     int launches = 0;
     int gemm_path_active = NTN_GEMM_SIMT;
     bool profiling = false;
