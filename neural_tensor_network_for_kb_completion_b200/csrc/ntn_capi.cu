@@ -164,7 +164,7 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     DeviceWords& w = h->w;
     dev_free(w.fwd_off); dev_free(w.fwd_idx); dev_free(w.w_off); dev_free(w.w_ent); dev_free(w.len_bwd);
     dev_free(w.wh_word); dev_free(w.wh_begin); dev_free(w.wh_end); dev_free(w.wh_first); dev_free(w.wh_count);
-    dev_free(w.wh_part); dev_free(w.hub_words); dev_free(w.w_rec);
+    dev_free(w.wh_part); dev_free(w.hub_words); dev_free(w.w_rec); dev_free(w.fwd_rec);
     dev_free(h->wv_frozen); dev_free(h->E); dev_free(h->gE); dev_free(h->Waug); dev_free(h->side);
     dev_free(h->reg_part); dev_free(h->d_out); dev_free(h->d_ref_theta); dev_free(h->d_ref_grad);
     dev_free(h->d_int_theta); dev_free(h->d_int_grad);
@@ -281,6 +281,11 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
     std::vector<int> hub_words;
     for (int i = 0; i < dm.Nw; ++i) if (count[i] > 0) hub_words.push_back(i);
     w.n_hub_words = (int)hub_words.size();
+    std::vector<int4> frec(dm.Ne);
+    for (int n = 0; n < dm.Ne; ++n) {
+        int j0 = fwd_off[n], cnt = fwd_off[n + 1] - fwd_off[n];
+        frec[n] = make_int4(j0, cnt, fwd_idx[j0], cnt > 1 ? fwd_idx[j0 + 1] : 0);
+    }
     std::vector<int4> wrec(dm.Nw);
     for (int i = 0; i < dm.Nw; ++i)
         wrec[i] = make_int4(woff[i], woff[i + 1], woff[i + 1] > woff[i] ? went[woff[i]] : -1, count[i]);
@@ -290,7 +295,7 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
         (rc = dev_upload(h, &w.len_bwd, lb)) || (rc = dev_upload(h, &w.wh_word, sr)) ||
         (rc = dev_upload(h, &w.wh_begin, sb)) || (rc = dev_upload(h, &w.wh_end, se)) ||
         (rc = dev_upload(h, &w.wh_first, first)) || (rc = dev_upload(h, &w.wh_count, count)) ||
-        (rc = dev_upload(h, &w.hub_words, hub_words)) || (rc = dev_upload(h, &w.w_rec, wrec)) ||
+        (rc = dev_upload(h, &w.hub_words, hub_words)) || (rc = dev_upload(h, &w.w_rec, wrec)) || (rc = dev_upload(h, &w.fwd_rec, frec)) ||
         (rc = dev_alloc(h, &w.wh_part, (size_t)w.n_hub_segs * dm.dq)))
         return rc;
     CK(cudaStreamSynchronize(h->stream));     // host vectors go out of scope

@@ -74,6 +74,7 @@ struct DeviceWords {
     bool set = false;
     int nnz_f = 0, nnz_b = 0;
     int *fwd_off = nullptr, *fwd_idx = nullptr;    // entity -> forward words
+    int4 *fwd_rec = nullptr;                       // per entity {first index, word count, word 0, word 1}
     int *w_off = nullptr, *w_ent = nullptr;        // word -> entities of the backward lists (inverse CSR)
     int4 *w_rec = nullptr;                         // per word {j0, j1, first entity, hub segment count}
     float *len_bwd = nullptr;                      // Ne, as float

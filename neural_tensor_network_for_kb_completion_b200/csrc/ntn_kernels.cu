@@ -49,25 +49,31 @@ template <int ACT> __device__ __forceinline__ float act_diff(float z) {   // NTN
 //     E[n, 0:d] = (1/cnt) sum_j WVt[word_j(n), :],  E[n, d] = 1,  E[n, d+1:Kp] = 0
 //     One thread per (entity, float4 chunk).  HBM-bound: reads nnz*dq, writes Ne*Kp.
 // ==========================================================================================
-__global__ void __launch_bounds__(256) k_entity_build(const float* __restrict__ wvt, const int* __restrict__ off,
+__global__ void __launch_bounds__(256) k_entity_build(const float* __restrict__ wvt, const int4* __restrict__ rec,
                                                       const int* __restrict__ idx, float* __restrict__ E,
                                                       int Ne, int d, int dq, int Kp) {
-    // flat mapping: one thread per (entity, float4 chunk of the Kp-wide row)
+    // flat mapping: one thread per (entity, float4 chunk of the Kp-wide row).  rec = {first index into idx, word
+    // count, word 0, word 1}: entities of one or two words (92 %) need no second dependent index load.
     const int cpr = Kp >> 2;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int n = (int)(gid / cpr), c = (int)(gid - (int64_t)n * cpr);
     if (n >= Ne) return;
-    int j0 = __ldg(off + n), j1 = __ldg(off + n + 1);
-    int cnt = j1 - j0;
+    const int4 r = __ldg(rec + n);
+    const int cnt = r.y;
     float4 acc = zero4();
     if (c * 4 < dq) {
-        for (int jb = j0; jb < j1; jb += 4) {                        // word order, like :410-418
-            float4 v[4];
+        if (cnt <= 2) {
+            acc = ldg4(wvt + (size_t)r.z * dq + c * 4);
+            if (cnt == 2) { float4 v = ldg4(wvt + (size_t)r.w * dq + c * 4); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        } else {
+            for (int jb = r.x; jb < r.x + cnt; jb += 4) {            // word order, like :410-418
+                float4 v[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                v[i] = (jb + i < j1) ? ldg4(wvt + (size_t)__ldg(idx + jb + i) * dq + c * 4) : zero4();
+                for (int i = 0; i < 4; ++i)
+                    v[i] = (jb + i < r.x + cnt) ? ldg4(wvt + (size_t)__ldg(idx + jb + i) * dq + c * 4) : zero4();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
+                for (int i = 0; i < 4; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
+            }
         }
         if (cnt > 1) {                                               // :420 (single word: copy, :429)
             float fc = (float)cnt;
@@ -538,7 +544,7 @@ __global__ void __launch_bounds__(256) k_entity_pull_hub(PullArgs a) {
 }
 
 template <int KS>
-__global__ void __launch_bounds__(256) k_entity_pull(PullArgs a) {
+__global__ void __launch_bounds__(256, (KS <= 4) ? 6 : 2) k_entity_pull(PullArgs a) {
     const int cpr = a.dq >> 2;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int n = (int)(gid / cpr), c = (int)(gid - (int64_t)n * cpr);
@@ -669,7 +675,7 @@ __global__ void __launch_bounds__(1024) k_word_finish_hub(WordArgs a) {
 }
 
 // one thread per (word, float4 chunk); hub words are finished by k_word_finish_hub
-__global__ void __launch_bounds__(256) k_word_pull(WordArgs a) {
+__global__ void __launch_bounds__(256, 6) k_word_pull(WordArgs a) {
     __shared__ double s_reg[8];
     const int cpr = a.dq >> 2;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -879,7 +885,7 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 void ntn_launch_entity_build(ntn_handle* h, const float* wvt) {
     const NtnDims& dm = h->dm;
-    k_entity_build<<<cdiv((int64_t)dm.Ne * (dm.Kp / 4), 256), 256, 0, h->stream>>>(wvt, h->w.fwd_off, h->w.fwd_idx, h->E,
+    k_entity_build<<<cdiv((int64_t)dm.Ne * (dm.Kp / 4), 256), 256, 0, h->stream>>>(wvt, h->w.fwd_rec, h->w.fwd_idx, h->E,
                                                                                    dm.Ne, dm.d, dm.dq, dm.Kp);
     h->launches++;
 }
