@@ -263,7 +263,17 @@ def main():
                              kb.wv.astype(np.float64).ravel()]).astype(np.float32)
     theta_host = theta_trained_like(theta0).astype(np.float64)
     thetas = [torch.empty(Pint, dtype=torch.float32, device=dev) for _ in range(2)]
-    grads = [torch.empty(Pint, dtype=torch.float32, device=dev) for _ in range(2)]
+    exchange, exchange_us = None, {}
+    if dist is not None:
+        # one collective per evaluation: [gradient | cost, n_active] in one buffer, fastest available all-reduce
+        from neural_tensor_network_for_kb_completion_b200.distributed import GradientExchange
+        exchange = GradientExchange(Pint + 4, dev, n_buffers=2)
+        exchange_us = exchange.autotune()
+        grads = exchange.buffers
+        for h in handles:
+            h.set_grad_tail(True)
+    else:
+        grads = [torch.empty(Pint + 4, dtype=torch.float32, device=dev) for _ in range(2)]
     for t in thetas:
         h0.upload_theta(theta_host, t.data_ptr())
     torch.cuda.synchronize()
@@ -273,8 +283,7 @@ def main():
         h = handles[j]
         h.eval_dev(thetas[j].data_ptr(), sides[j], grads[j].data_ptr(), sync=False)
         if dist is not None:
-            dist.all_reduce(grads[j])                       # every rank ends with the full-batch gradient
-            dist.all_reduce(results[j])                     # ... and the full-batch cost / n_active
+            exchange.all_reduce(grads[j])                   # every rank ends with the full-batch gradient, cost, n_active
         if sync:
             torch.cuda.synchronize()
 
@@ -313,8 +322,7 @@ def main():
         h.set_profiling(False)
     cost, nact = handles[(args.steps - 1) & 1].last_cost()
     if dist is not None:
-        rr = results[(args.steps - 1) & 1].cpu().numpy()
-        cost, nact = float(rr[0]), int(round(float(rr[1])))
+        cost, nact = _capi.Handle.unpack_tail(grads[(args.steps - 1) & 1][Pint:Pint + 4].cpu().numpy())
     if dist is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -334,8 +342,8 @@ def main():
             hj = handles[j]
             hj.upload_theta(theta_host, thetas[j].data_ptr())
             hj.eval_dev(thetas[j].data_ptr(), sides[j], grads[j].data_ptr(), sync=False)
-            dist.all_reduce(grads[j])
-            grad_host[:] = hj.download_theta(grads[j].data_ptr())
+            exchange.all_reduce(grads[j])
+            hj.download_theta(grads[j].data_ptr(), out=grad_host)
     for i in range(3):
         e2e_step(i)
     barrier()
@@ -419,14 +427,15 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(kb, world, args.wv_source), gemm_path=h0.gemm_path,
-                           set_batch_ms=float(np.mean(set_batch_ms))),
+                           set_batch_ms=float(np.mean(set_batch_ms)),
+                           exchange=(exchange.variant if exchange else None), exchange_us=exchange_us),
             "evals_per_s": 1e3 / ms_step, "columns_per_s": BATCH * CORRUPT * world / (ms_step * 1e-3),
             "cost": cost, "n_active": nact,
             "clocks": clocks,
             "e2e": {"value": BATCH * world / e2e_s, "unit": "triples/s", "ms_per_step": 1e3 * e2e_s,
                     "h2d_bytes_per_step": 4 * P + kb.R, "d2h_bytes_per_step": 4 * P + 32,
                     "api": "ntn_eval(double* theta, uint8* corrupt_side, double* cost, double* grad) with host buffers"
-                           if world == 1 else "ntn_upload_theta + ntn_eval_dev + NCCL all-reduce + ntn_download_theta"},
+                           if world == 1 else "ntn_upload_theta + ntn_eval_dev + gradient all-reduce + ntn_download_theta"},
             "gpu_launches": launches_per_eval * args.steps,
             "launches_per_eval": launches_per_eval,
             "roofline": roofline, "phase": per_group, "eval_roofline": eval_roofline,

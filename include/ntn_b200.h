@@ -127,6 +127,10 @@ int ntn_last_cost(ntn_handle* h, double* cost, int64_t* n_active);   /* synchron
 /* DEVICE pointer to the last evaluation's 4 doubles {cost, n_active, data term, sum theta^2}: lets a
  * data-parallel host all-reduce the scalars on the device together with the gradient. */
 double* ntn_result_dev(ntn_handle* h);
+/* Data-parallel hosts: with on != 0 every ntn_eval_dev also writes 4 floats after the gradient, at
+ * d_grad[ntn_internal_dimension() .. +4) = {cost_hi, cost_lo, n_active >> 12, n_active & 4095} (exact float pairs),
+ * so ONE sum all-reduce of Pint+4 floats carries the gradient and the scalars.  d_grad must then have Pint+4 floats. */
+int ntn_set_grad_tail(ntn_handle* h, int on);
 
 int64_t ntn_internal_dimension(const ntn_handle* h);
 /* reference-order FP32 device vector (P) <-> internal-order device vector */

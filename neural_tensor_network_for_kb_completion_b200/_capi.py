@@ -62,6 +62,7 @@ SYMBOLS = {
     "ntn_eval_dev": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ntn_last_cost": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ntn_result_dev": (_P, [_P]),
+    "ntn_set_grad_tail": (C.c_int, [_P, C.c_int]),
     "ntn_internal_dimension": (C.c_int64, [_P]),
     "ntn_to_internal_dev": (C.c_int, [_P, _P, _P]),
     "ntn_from_internal_dev": (C.c_int, [_P, _P, _P]),
@@ -201,6 +202,15 @@ class Handle:
         self._ck(self.lib.ntn_last_cost(self.h, C.byref(cost), C.byref(nact)))
         return cost.value, nact.value
 
+    def set_grad_tail(self, on=True):
+        self._ck(self.lib.ntn_set_grad_tail(self.h, int(on)))
+
+    @staticmethod
+    def unpack_tail(tail):
+        """(cost, n_active) from the 4 summed tail floats."""
+        t = [float(x) for x in tail]
+        return t[0] + t[1], int(round(t[2])) * 4096 + int(round(t[3]))
+
     def result_tensor(self):
         """torch view (4 float64, on the device) of {cost, n_active, data term, sum theta^2}."""
         import torch
@@ -223,8 +233,8 @@ class Handle:
         assert theta.size == self.P
         self._ck(self.lib.ntn_upload_theta(self.h, _ptr(theta), d_int))
 
-    def download_theta(self, d_int: int):
-        out = np.empty(self.P, np.float64)
+    def download_theta(self, d_int: int, out=None):
+        out = np.empty(self.P, np.float64) if out is None else out
         self._ck(self.lib.ntn_download_theta(self.h, d_int, _ptr(out)))
         return out
 

@@ -468,7 +468,7 @@ static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_gr
     begin(P_EP, s0); ntn_launch_entity_pull(h); end(P_EP, s0);                                // Util.java:74-98
     begin(P_WPULL, s0); ntn_launch_word_pull(h, d_theta, d_grad); end(P_WPULL, s0);           // :411-430
     CK(cudaStreamWaitEvent(s0, h->ev_j1, 0));
-    ntn_launch_final_reduce(h);                                                               // :430,437
+    ntn_launch_final_reduce(h, h->grad_tail ? d_grad + h->dm.Pint : nullptr);                 // :430,437
     CK(cudaMemcpyAsync(h->h_out, h->d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, s0));
     return NTN_OK;
 }
@@ -546,6 +546,12 @@ extern "C" int ntn_last_cost(ntn_handle* h, double* cost, int64_t* n_active) {
 }
 
 extern "C" double* ntn_result_dev(ntn_handle* h) { return h ? h->d_out : nullptr; }
+extern "C" int ntn_set_grad_tail(ntn_handle* h, int on) {
+    if (!h) return NTN_EINVAL;
+    ntn_drop_graphs(h);
+    h->grad_tail = on != 0;
+    return NTN_OK;
+}
 
 extern "C" int ntn_last_phase_ms(ntn_handle* h, float* ms) {
     if (!h || !ms) return NTN_EINVAL;
@@ -672,8 +678,7 @@ extern "C" int ntn_upload_theta(ntn_handle* h, const double* theta, float* d_int
     if (rc) return rc;
     const NtnDims& dm = h->dm;
     CK(cudaStreamSynchronize(h->stream));
-    convert_parallel(theta, h->h_stage, dm.P);
-    CK(cudaMemcpyAsync(h->d_ref_theta, h->h_stage, (size_t)dm.P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(upload_pipelined(h, theta, h->d_ref_theta, dm.P));
     ntn_launch_to_internal(h, h->d_ref_theta, d_int);
     CK(cudaStreamSynchronize(h->stream));
     return NTN_OK;
@@ -686,9 +691,7 @@ extern "C" int ntn_download_theta(ntn_handle* h, const float* d_int, double* the
     if (rc) return rc;
     const NtnDims& dm = h->dm;
     ntn_launch_from_internal(h, d_int, h->d_ref_grad);
-    CK(cudaMemcpyAsync(h->h_stage, h->d_ref_grad, (size_t)dm.P * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    convert_parallel(h->h_stage, theta, dm.P);
+    CK(download_pipelined(h, h->d_ref_grad, theta, dm.P));
     return NTN_OK;
 }
 

@@ -128,6 +128,7 @@ struct ntn_handle {
     struct GraphEntry { const float* theta; float* grad; cudaStream_t stream; cudaGraphExec_t exec; int launches; };
     std::vector<GraphEntry> graphs;
     bool use_graph = true;
+    bool grad_tail = false;       // the caller's gradient buffer has 4 extra floats for {cost, n_active}
 };
 
 // ---- kernel launchers (ntn_kernels.cu) ---------------------------------------------------
@@ -140,7 +141,7 @@ void ntn_launch_gemm_ge_simt(ntn_handle* h);
 void ntn_launch_entity_pull(ntn_handle* h);
 void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad);
 void ntn_launch_finalize_small(ntn_handle* h, const float* theta, float* grad, cudaStream_t st);
-void ntn_launch_final_reduce(ntn_handle* h);
+void ntn_launch_final_reduce(ntn_handle* h, float* tail);
 void ntn_launch_to_internal(ntn_handle* h, const float* d_ref, float* d_int);
 void ntn_launch_from_internal(ntn_handle* h, const float* d_int, float* d_ref);
 void ntn_launch_transpose_wv_host_layout(ntn_handle* h, const float* d_wv_ref /* d x Nw */, float* d_wvt);

@@ -778,7 +778,8 @@ __global__ void __launch_bounds__(256) k_finalize_small(FinArgs a) {
 // single block: cost = sum(tile costs)/B + 0.5*lambda*sum(theta^2)      NTN.java:430,437
 __global__ void __launch_bounds__(256) k_final_reduce(const double* __restrict__ tp_cost, const int* __restrict__ tp_nact,
                                                       int ntiles, const double* __restrict__ reg_part, int nreg,
-                                                      double inv_B, double half_lam, double* __restrict__ out) {
+                                                      double inv_B, double half_lam, double* __restrict__ out,
+                                                      float* __restrict__ tail) {
     __shared__ double s_a[256], s_b[256], s_c[256];
     double c = 0.0, n = 0.0, r = 0.0;
     for (int i = threadIdx.x; i < ntiles; i += 256) { c += tp_cost[i]; n += (double)tp_nact[i]; }
@@ -798,6 +799,12 @@ __global__ void __launch_bounds__(256) k_final_reduce(const double* __restrict__
         out[1] = s_b[0];
         out[2] = s_a[0] * inv_B;       // data term alone
         out[3] = s_c[0];               // sum theta^2
+        if (tail) {                    // {cost, n_active} as exact float pairs after the gradient: one collective covers all
+            const float chi = (float)out[0];
+            tail[0] = chi; tail[1] = (float)(out[0] - (double)chi);
+            const long long na = (long long)s_b[0];
+            tail[2] = (float)(na >> 12); tail[3] = (float)(na & 4095);
+        }
     }
 }
 
@@ -1013,14 +1020,14 @@ void ntn_launch_finalize_small(ntn_handle* h, const float* theta, float* grad, c
     h->launches++;
 }
 
-void ntn_launch_final_reduce(ntn_handle* h) {
+void ntn_launch_final_reduce(ntn_handle* h, float* tail) {
     const NtnDims& dm = h->dm;
     const DeviceBatch& b = h->b;
     int nb = ntn_small_blocks(dm);
     int wb = word_pull_blocks(dm) + h->w.n_hub_words;
     double lam = (double)h->cfg.lambda * (double)h->cfg.reg_scale;
     k_final_reduce<<<1, 256, 0, h->stream>>>(b.tp_cost, b.tp_nact, b.nstiles, h->reg_part, wb + nb,
-                                             1.0 / (double)h->cfg.batch_divisor, 0.5 * lam, h->d_out);
+                                             1.0 / (double)h->cfg.batch_divisor, 0.5 * lam, h->d_out, tail);
     h->launches++;
 }
 
