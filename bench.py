@@ -96,21 +96,24 @@ def theta_trained_like(theta0, seed=11):
 
 
 def work_model(dm, n_u, n_cols, nnz_f, nnz_b):
-    """Algorithmic bytes / FLOPs per kernel group for one evaluation."""
+    """Algorithmic (compulsory) HBM bytes and FLOPs per kernel group for one evaluation: every
+    buffer a group must read or write is counted ONCE -- row gathers that re-read a table (entity rows, T' rows)
+    are served by the 126 MB L2 and are not counted, exactly like SURVEY.md §8d's B_alg."""
     d, k, R, Ne, Nw = dm["d"], dm["k"], dm["R"], dm["Ne"], dm["Nw"]
     P = R * k * d * d + R * 2 * d * k + 2 * R * k + d * Nw
     row, aug = d * 4, (d + 1) * (k * d + k)
+    trow = 4 * (k * d + k)                                   # one T' / M row
+    ents = min(Ne, 2 * n_u + n_cols)                         # distinct entity rows a batch can touch
     g = {
-        "entity_build": dict(bytes=nnz_f * row + Ne * row + 4 * (Ne + 1 + nnz_f), flops=nnz_f * d),
+        "entity_build": dict(bytes=min(nnz_f, Nw) * row + Ne * row + 4 * (Ne + 1 + nnz_f), flops=nnz_f * d),
         "w_prep": dict(bytes=2 * 4 * R * aug, flops=0),
-        "gemm_fwd": dict(bytes=n_u * row + 4 * n_u * (k * d + k) + 4 * R * aug, flops=2 * n_u * aug),
-        "score": dict(bytes=2 * 4 * n_u * (k * d + k) + (n_u + n_cols) * row + 4 * n_cols * (k + 1) + 12 * n_u,
-                      flops=4 * k * d * (n_u + n_cols)),
-        "gemm_dw": dict(bytes=n_u * row + 4 * n_u * (k * d + k) + 4 * R * aug, flops=2 * n_u * aug),
-        "gemm_ge": dict(bytes=4 * n_u * (k * d + k) + n_u * row + 4 * R * aug, flops=2 * n_u * aug),
-        "entity_pull": dict(bytes=(n_u + n_cols) * (k * row + 4 * k + 8) + n_u * row + Ne * row,
+        "gemm_fwd": dict(bytes=min(n_u, Ne) * row + n_u * trow + 4 * R * aug, flops=2 * n_u * aug),
+        "score": dict(bytes=2 * n_u * trow + ents * row + 4 * n_cols * (k + 1) + 12 * n_u, flops=4 * k * d * (n_u + n_cols)),
+        "gemm_dw": dict(bytes=min(n_u, Ne) * row + n_u * trow + 4 * R * aug, flops=2 * n_u * aug),
+        "gemm_ge": dict(bytes=n_u * trow + n_u * row + 4 * R * aug, flops=2 * n_u * aug),
+        "entity_pull": dict(bytes=n_u * trow + (n_u + n_cols) * (4 * k + 16) + n_u * row + Ne * row,
                             flops=2 * k * d * (n_u + n_cols)),
-        "word_pull": dict(bytes=nnz_b * row + 2 * Nw * row + 4 * (Nw + 1 + nnz_b), flops=3 * Nw * d),
+        "word_pull": dict(bytes=Ne * row + 2 * Nw * row + 4 * (Nw + 1 + nnz_b), flops=3 * Nw * d),
         "finalize": dict(bytes=3 * 4 * R * aug, flops=R * aug),
     }
     b_alg = 8 * P + 16 * Ne * d + 12 * n_u + 4 * n_cols + 4 * (Ne + 1 + nnz_f)     # SURVEY.md §8d

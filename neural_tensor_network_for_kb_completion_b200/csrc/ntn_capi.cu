@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <numeric>
+#include <thread>
 
 #include "ntn_internal.h"
 
@@ -591,8 +592,19 @@ extern "C" int ntn_from_internal_dev(ntn_handle* h, const float* d_int, float* d
 // host <-> pinned staging with type conversion.  The arrays are ~57 MB; conversion runs on an OpenMP pool and is
 // pipelined against the PCIe copies in NTN_XFER_CHUNK-element chunks (convert chunk i+1 while chunk i is in flight).
 #define NTN_XFER_CHUNK (1 << 21)
+// torchrun exports OMP_NUM_THREADS=1 to every rank; the staging loops size their own team: the host cores divided
+// among the ranks of this box (LOCAL_WORLD_SIZE), at most 16.
+static int convert_threads() {
+    static int nt = [] {
+        unsigned hw = std::thread::hardware_concurrency();
+        const char* lws = getenv("LOCAL_WORLD_SIZE");
+        int ranks = lws ? std::max(1, atoi(lws)) : 1;
+        return (int)std::max(1u, std::min(16u, (hw ? hw : 1u) / (unsigned)ranks));
+    }();
+    return nt;
+}
 template <typename S, typename D> static void convert_range(const S* src, D* dst, int64_t n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(convert_threads())
     for (int64_t i = 0; i < n; ++i) dst[i] = (D)src[i];          // double -> float rounds like Util.java:49-55
 }
 template <typename S, typename D> static void convert_parallel(const S* src, D* dst, int64_t n) { convert_range(src, dst, n); }
