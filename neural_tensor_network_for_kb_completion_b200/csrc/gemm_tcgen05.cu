@@ -15,7 +15,9 @@
 //              tcgen05.commit releases the stage ("empty" mbarrier) / signals the epilogue.
 // All operands are K-major SWIZZLE_128B tiles (row = M/N index, 128 bytes of K per row).  dw contracts
 // over the ROW index of both of its operands, so its producers transpose while they store.
-// The weight operand Waug is written once per evaluation by k_tc_w_prep in both K-major orientations.
+// The weight operand Waug is written once per evaluation by k_tc_w_prep in both K-major orientations; in fwd and ge
+// it is fed by TMA (cp.async.bulk.tensor 2-D boxes from pre-split hi/lo arrays, SWIZZLE_128B tensor maps, completion
+// bytes on the stage's full mbarrier); NTN_TC_TMA=0 selects the software-loaded fallback.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -35,6 +37,11 @@
 struct TcState {
     float *WT = nullptr;                        // [R][Np][KpP]   Waug^T, K(=p)-major rows      (fwd B)
     float *W = nullptr;                         // [R][KpN][NpP]  Waug,   K(=n)-major rows      (ge  B)
+    // TMA path: the same two arrays pre-split into TF32 hi/lo, and their tiled tensor maps (SWIZZLE_128B boxes)
+    bool use_tma = false;
+    float *WT_hi = nullptr, *WT_lo = nullptr, *W_hi = nullptr, *W_lo = nullptr;
+    CUtensorMap mWT_hi, mWT_lo, mW_hi, mW_lo;
+    int box_fwd = 0, box_ge = 0;                // rows per TMA box
     int KpP = 0, KpN = 0, NpP = 0;
     int* err = nullptr;                         // device flag: a bounded wait expired
     long long* dbg = nullptr;                   // 3 x 256 cycle stamps of CTA (0,0,0) per mode (debug timeline)
@@ -67,6 +74,17 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
         if (mbar_try_wait(bar, parity)) return true;
     atomicExch(err, 1);
     return false;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA: one 2-D tile (inner coordinate x in elements, row y) global -> shared, completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -135,6 +153,8 @@ struct TcArgs {
     int Kp, Np, KpP, KpN, NpP;
     int* err;
     long long* dbg;                    // cycle-stamp timeline of CTA (0,0,0), or null
+    int b_rows_per_rel;                // TMA path: rows of the weight tensor per relation (Np resp. KpN)
+    int b_box_rows;                    // TMA path: rows per box (expect_tx bytes = 2 * rows * 128)
 };
 
 enum { TC_FWD = 0, TC_DW = 1, TC_GE = 2 };
@@ -152,8 +172,9 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float v[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a) {
+template <int MODE, bool TMA_B>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __grid_constant__ CUtensorMap mapB_hi,
+                                                           const __grid_constant__ CUtensorMap mapB_lo) {
     // SWIZZLE_128B tiles need 1024-byte alignment.  The array is used directly (no pointer arithmetic through
     // integers) so that the stores below stay in the shared state space (STS): with generic stores the compiler
     // cannot hoist the global loads above them and every load round trip is exposed.
@@ -185,9 +206,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a) {
     const int nkb = (kext + TC_BK - 1) / TC_BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+        // full: 128 producer arrivals (+ the TMA issuer's arrive.expect_tx when the weight tile comes by TMA)
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), TMA_B ? 129 : 128); mbar_init(empty_bar(s), 1); }
         mbar_init(acc_bar, 1);
         fence_barrier_init();
+        if (TMA_B) { tma_prefetch_desc(&mapB_hi); tma_prefetch_desc(&mapB_lo); }
     }
     if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TC_TMEM_COLS);
     tc_fence_before();
@@ -227,6 +250,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a) {
             uint8_t* sB_lo = sB_hi + TC_B_BYTES;
             const int k0 = kb * TC_BK;
             constexpr int BROWS = TC_NCH / 16;                                       // B rows per thread (K-major loads)
+            if (TMA_B && t == 0) {
+                // weight tile by TMA: two boxes (hi, lo) of 32 floats x b_box_rows rows land directly in the swizzled
+                // UMMA layout; their bytes complete on the stage's full barrier
+                mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)a.b_box_rows * 128u);
+                const int y = r * a.b_rows_per_rel + n0;
+                tma_load_2d(smem_u32(sB_hi), &mapB_hi, k0, y, full_bar(s));
+                tma_load_2d(smem_u32(sB_lo), &mapB_lo, k0, y, full_bar(s));
+            }
             if (MODE == TC_FWD || MODE == TC_GE) {
                 // all global loads of this k-block are issued first (latency overlaps), then split + store
                 float4 xa[8], xb[BROWS];
@@ -238,10 +269,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a) {
                     if (MODE == TC_FWD) { if (anchor[i] >= 0 && kk < a.Kp) xa[i] = ldg4g(a.E + (size_t)anchor[i] * a.Kp + kk); }
                     else { if (row < rows && kk < a.Np) xa[i] = ldg4g(a.M + (size_t)(u0 + row) * a.Np + kk); }
                 }
+                if (!TMA_B) {
 #pragma unroll
-                for (int i = 0; i < BROWS; ++i) {
-                    const int row = rsub + 16 * i;
-                    xb[i] = (row < nlen) ? ldg4g(Bw + (size_t)(n0 + row) * ldb + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < BROWS; ++i) {
+                        const int row = rsub + 16 * i;
+                        xb[i] = (row < nlen) ? ldg4g(Bw + (size_t)(n0 + row) * ldb + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
                 // ---- A: K-major, 128 rows x 128 bytes, chunk j of row `row` at row*128 + ((j ^ (row&7))<<4)
 #pragma unroll
@@ -254,14 +287,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a) {
                 }
                 // ---- B: K-major, nlen rows (n resp. p) x 128 bytes of Waug, split here as well: reading one FP32
                 //      copy instead of pre-split hi/lo arrays halves the L2 traffic of the operand every CTA re-reads
+                if (!TMA_B) {
 #pragma unroll
-                for (int i = 0; i < BROWS; ++i) {
-                    const int row = rsub + 16 * i;
-                    if (row < nlen) {
-                        float4 hi, lo;
-                        split_tf32(xb[i], hi, lo);
-                        const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
-                        sts4(sB_hi, off, hi); sts4(sB_lo, off, lo);
+                    for (int i = 0; i < BROWS; ++i) {
+                        const int row = rsub + 16 * i;
+                        if (row < nlen) {
+                            float4 hi, lo;
+                            split_tf32(xb[i], hi, lo);
+                            const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+                            sts4(sB_hi, off, hi); sts4(sB_lo, off, lo);
+                        }
                     }
                 }
             } else {
@@ -431,20 +466,25 @@ __device__ __forceinline__ void split1(float v, float& h, float& l) {
     l = tf32_round(v - h);
 }
 __global__ void __launch_bounds__(256) k_tc_w_prep(const float* __restrict__ theta, const uint8_t* __restrict__ side,
-                                                   float* WT, float* W, NtnDims dm, int KpP, int KpN, int NpP) {
+                                                   float* WT, float* W, float* WT_hi, float* WT_lo, float* W_hi, float* W_lo,
+                                                   NtnDims dm, int KpP, int KpN, int NpP) {
     const int64_t nA = (int64_t)dm.R * dm.Np * KpP, nB = (int64_t)dm.R * KpN * NpP;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nA) {
         int r = (int)(i / ((int64_t)dm.Np * KpP));
         int rem = (int)(i - (int64_t)r * dm.Np * KpP);
         int n = rem / KpP, p = rem - n * KpP;
-        WT[i] = waug_at(theta, dm, r, side[r] != 0, p, n);
+        const float v = waug_at(theta, dm, r, side[r] != 0, p, n);
+        WT[i] = v;
+        if (WT_hi) { float h, l; split1(v, h, l); WT_hi[i] = h; WT_lo[i] = l; }
     } else if (i < nA + nB) {
         i -= nA;
         int r = (int)(i / ((int64_t)KpN * NpP));
         int rem = (int)(i - (int64_t)r * KpN * NpP);
         int p = rem / NpP, n = rem - p * NpP;
-        W[i] = waug_at(theta, dm, r, side[r] != 0, p, n);
+        const float v = waug_at(theta, dm, r, side[r] != 0, p, n);
+        W[i] = v;
+        if (W_hi) { float h, l; split1(v, h, l); W_hi[i] = h; W_lo[i] = l; }
     }
 }
 
@@ -459,6 +499,30 @@ int ntn_tc_supported(const ntn_handle* h) {
     return 1;
 }
 
+// tiled tensor map over a row-major [rows][inner] FP32 array: boxes of 32 floats (one 128-byte swizzle row) x box_rows
+// (the driver entry point is resolved at run time so that the library does not link libcuda and still loads on a
+//  machine without a driver, where every entry point reports NTN_ECUDA)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+    static EncodeTiledFn cuTensorMapEncodeTiled = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (EncodeTiledFn)fn;
+    }();
+    if (!cuTensorMapEncodeTiled) return false;
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {inner * sizeof(float)};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static TcArgs tc_args(ntn_handle* h, bool chunks) {
     TcState* st = (TcState*)h->tc;
     const DeviceBatch& b = h->b;
@@ -470,6 +534,7 @@ static TcArgs tc_args(ntn_handle* h, bool chunks) {
     a.Kp = h->dm.Kp; a.Np = h->dm.Np; a.KpP = st->KpP; a.KpN = st->KpN; a.NpP = st->NpP;
     a.err = st->err;
     a.dbg = st->dbg;
+    a.b_rows_per_rel = 0; a.b_box_rows = 0;
     return a;
 }
 
@@ -487,9 +552,29 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
             h->err = std::string("tcgen05 state: ") + cudaGetErrorString(e);
             return NTN_ECUDA;
         }
-        if ((e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
-            (e = cudaFuncSetAttribute(k_tc_gemm<TC_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
-            (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES))) {
+        const char* tma_env = getenv("NTN_TC_TMA");
+        st->use_tma = !(tma_env && tma_env[0] == '0');
+        if (st->use_tma) {
+            if ((e = cudaMalloc((void**)&st->WT_hi, nA * 4)) || (e = cudaMalloc((void**)&st->WT_lo, nA * 4)) ||
+                (e = cudaMalloc((void**)&st->W_hi, nB * 4)) || (e = cudaMalloc((void**)&st->W_lo, nB * 4))) {
+                h->err = std::string("tcgen05 TMA state: ") + cudaGetErrorString(e);
+                return NTN_ECUDA;
+            }
+            st->box_fwd = std::min(TC_NCH, dm.Np);
+            st->box_ge = std::min(TC_NCH, st->KpN);
+            if (!make_map(&st->mWT_hi, st->WT_hi, st->KpP, (uint64_t)dm.R * dm.Np, st->box_fwd) ||
+                !make_map(&st->mWT_lo, st->WT_lo, st->KpP, (uint64_t)dm.R * dm.Np, st->box_fwd) ||
+                !make_map(&st->mW_hi, st->W_hi, st->NpP, (uint64_t)dm.R * st->KpN, st->box_ge) ||
+                !make_map(&st->mW_lo, st->W_lo, st->NpP, (uint64_t)dm.R * st->KpN, st->box_ge)) {
+                h->err = "cuTensorMapEncodeTiled failed";
+                return NTN_ECUDA;
+            }
+        }
+        if ((e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_DW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES))) {
             h->err = std::string("tcgen05 smem attribute: ") + cudaGetErrorString(e);
             return NTN_ECUDA;
         }
@@ -501,6 +586,7 @@ void ntn_tc_release(ntn_handle* h) {
     TcState* st = (TcState*)h->tc;
     if (!st) return;
     cudaFree(st->WT); cudaFree(st->W); cudaFree(st->err); cudaFree(st->dbg);
+    cudaFree(st->WT_hi); cudaFree(st->WT_lo); cudaFree(st->W_hi); cudaFree(st->W_lo);
     delete st;
     h->tc = nullptr;
 }
@@ -509,15 +595,22 @@ int ntn_tc_w_prep(ntn_handle* h, const float* theta, cudaStream_t stq) {
     TcState* st = (TcState*)h->tc;
     const NtnDims& dm = h->dm;
     int64_t n = (int64_t)dm.R * dm.Np * st->KpP + (int64_t)dm.R * st->KpN * st->NpP;
-    k_tc_w_prep<<<cdivi(n, 256), 256, 0, stq>>>(theta, h->side, st->WT, st->W, dm, st->KpP, st->KpN, st->NpP);
+    k_tc_w_prep<<<cdivi(n, 256), 256, 0, stq>>>(theta, h->side, st->WT, st->W, st->WT_hi, st->WT_lo, st->W_hi, st->W_lo, dm,
+                                                      st->KpP, st->KpN, st->NpP);
     h->launches++;
     return NTN_OK;
 }
 
 int ntn_tc_gemm_fwd(ntn_handle* h) {
     TcArgs a = tc_args(h, false);
+    TcState* st = (TcState*)h->tc;
     dim3 g(h->b.ntiles, cdivi(h->dm.Np, TC_NCH));
-    k_tc_gemm<TC_FWD><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a);
+    if (st->use_tma) {
+        a.b_rows_per_rel = h->dm.Np; a.b_box_rows = st->box_fwd;
+        k_tc_gemm<TC_FWD, true><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mWT_hi, st->mWT_lo);
+    } else {
+        k_tc_gemm<TC_FWD, false><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mWT_hi, st->mWT_lo);
+    }
     h->launches++;
     return NTN_OK;
 }
@@ -525,7 +618,8 @@ int ntn_tc_gemm_fwd(ntn_handle* h) {
 int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t stq) {
     TcArgs a = tc_args(h, true);
     dim3 g(h->b.nchunks, cdivi(h->dm.Np, TC_NCH), cdivi(h->dm.Kp, 128));
-    k_tc_gemm<TC_DW><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a);
+    TcState* st = (TcState*)h->tc;
+    k_tc_gemm<TC_DW, false><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo);
     h->launches++;
     return NTN_OK;
 }
@@ -534,7 +628,12 @@ int ntn_tc_gemm_ge(ntn_handle* h) {
     TcArgs a = tc_args(h, false);
     TcState* st = (TcState*)h->tc;
     dim3 g(h->b.ntiles, cdivi(st->KpN, TC_NCH));
-    k_tc_gemm<TC_GE><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a);
+    if (st->use_tma) {
+        a.b_rows_per_rel = st->KpN; a.b_box_rows = st->box_ge;
+        k_tc_gemm<TC_GE, true><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mW_hi, st->mW_lo);
+    } else {
+        k_tc_gemm<TC_GE, false><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mW_hi, st->mW_lo);
+    }
     h->launches++;
     return NTN_OK;
 }
