@@ -32,6 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SHAPE, D, K_SLICES, NW, BATCH, CORRUPT, LAMBDA = "freebase", 100, 3, 67447, 20000, 10, 1e-4
+CONFIG_NAME = "BASELINE.json configs[2]"
+# headline = c3.  c1: Wordnet-shaped batch (configs[1]); c4: Freebase-shaped FULL batch, all 316,232 triples x 10 (configs[3])
+CONFIGS = {"c1": ("wordnet", 20000, "BASELINE.json configs[1]"), "c3": ("freebase", 20000, "BASELINE.json configs[2]"),
+           "c4": ("freebase", 316232, "BASELINE.json configs[3], per-GPU share of the full batch")}
 
 
 def peaks():
@@ -171,8 +175,8 @@ def run_reference(args):
 
 
 def workload_config(kb, n_ranks, wv_source):
-    return {"workload": f"Freebase-shaped synthetic: {kb.Ne} entities, {kb.R} relations, d={D}, k={K_SLICES}, "
-                        f"{BATCH} triples x {CORRUPT} corrupt per GPU (BASELINE.json configs[2])",
+    return {"workload": f"{SHAPE.capitalize()}-shaped synthetic: {kb.Ne} entities, {kb.R} relations, d={D}, k={K_SLICES}, "
+                        f"{BATCH} triples x {CORRUPT} corrupt per GPU ({CONFIG_NAME})",
             "entities": kb.Ne, "relations": kb.R, "d": D, "k": K_SLICES, "words": kb.Nw,
             "batch_per_gpu": BATCH, "corrupt": CORRUPT, "columns_per_gpu": BATCH * CORRUPT,
             "global_batch": BATCH * n_ranks, "wv_source": wv_source, "theta": "theta0 + N(0,0.05^2)",
@@ -205,7 +209,10 @@ def main():
     ap.add_argument("--gemm-path", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     args = ap.parse_args()
+    global SHAPE, BATCH, CONFIG_NAME
+    SHAPE, BATCH, CONFIG_NAME = CONFIGS[args.config]
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
@@ -418,7 +425,7 @@ def main():
         dt = time.perf_counter() - t0
         c_gpu, g_gpu, _ = handles[0].eval(theta_host, sides[0])
         cpu = {"value": BATCH / dt, "unit": "triples/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "1 full evaluation of the 20,000 x 10 batch, float32 NumPy/OpenBLAS/SciPy restatement of "
+               "sample": f"1 full evaluation of the {BATCH:,} x {CORRUPT} batch, float32 NumPy/OpenBLAS/SciPy restatement of "
                          "the reference formulation (oracle/ntn_ref.py); the ND4j/JVM reference cannot run here",
                "seconds_per_eval": dt,
                "gpu_vs_cpu_f32_cost_rel_diff": abs(c_gpu - c_cpu) / max(abs(c_cpu), 1e-30),
@@ -426,7 +433,7 @@ def main():
 
     if rank == 0:
         out = {
-            "metric": "NTN cost+grad triples/sec (Freebase shape)", "value": triples_per_s, "unit": "triples/s",
+            "metric": f"NTN cost+grad triples/sec ({SHAPE.capitalize()} shape)", "value": triples_per_s, "unit": "triples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(kb, world, args.wv_source), gemm_path=h0.gemm_path,
