@@ -150,7 +150,7 @@ static void free_batch(DeviceBatch& b) {
     dev_free(b.t_rel); dev_free(b.t_u0); dev_free(b.t_n); dev_free(b.ch_rel); dev_free(b.ch_u0); dev_free(b.ch_n);
     dev_free(b.relch_off); dev_free(b.reltile_off); dev_free(b.inc_off); dev_free(b.inc);
     dev_free(b.eh_ent); dev_free(b.eh_begin); dev_free(b.eh_end); dev_free(b.eh_first); dev_free(b.eh_count);
-    dev_free(b.T); dev_free(b.M); dev_free(b.GA); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.dWpart);
+    dev_free(b.T); dev_free(b.M); dev_free(b.GA); dev_free(b.GV); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.dWpart);
     dev_free(b.tp_cost); dev_free(b.tp_nact); dev_free(b.tp_dU); dev_free(b.eh_part);
     b = DeviceBatch();
 }
@@ -361,12 +361,15 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
     for (int r = 0; r < dm.R; ++r) rel_off[r + 1] += rel_off[r];
     std::vector<int> t_rel, t_u0, t_n, ch_rel, ch_u0, ch_n, relch_off(dm.R + 1, 0), reltile_off(dm.R + 1, 0);
     std::vector<int> st_rel, st_u0, st_n, rels_off(dm.R + 1, 0);
+    // split-K chunk of the dW contraction: about two chunks per SM (every chunk costs a Kp x Np partial that the
+    // finalize kernel sums serially), never below NTN_CHUNK_ROWS, a multiple of the 32-row k-block
+    const int chunk_rows = std::max(NTN_CHUNK_ROWS, (int)round_up((Nu + 2 * h->sm_count - 1) / (2 * h->sm_count), 32));
     for (int r = 0; r < dm.R; ++r) {
         for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += NTN_TILE_ROWS) {
             t_rel.push_back(r); t_u0.push_back(u0); t_n.push_back(std::min(NTN_TILE_ROWS, rel_off[r + 1] - u0));
         }
-        for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += NTN_CHUNK_ROWS) {
-            ch_rel.push_back(r); ch_u0.push_back(u0); ch_n.push_back(std::min(NTN_CHUNK_ROWS, rel_off[r + 1] - u0));
+        for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += chunk_rows) {
+            ch_rel.push_back(r); ch_u0.push_back(u0); ch_n.push_back(std::min(chunk_rows, rel_off[r + 1] - u0));
         }
         for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += NTN_SCORE_ROWS) {
             st_rel.push_back(r); st_u0.push_back(u0); st_n.push_back(std::min(NTN_SCORE_ROWS, rel_off[r + 1] - u0));
@@ -394,9 +397,15 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
     CK(cudaStreamSynchronize(h->stream));
     ntn_drop_graphs(h);
     free_batch(h->b);
+    // entity-gradient pull variant: while T' (Nu x Np floats) stays L2-resident every incident re-reads its k T' rows;
+    // beyond that k_score materialises one contribution row per incident (measured: C3 0.256 vs 0.278 ms with rows,
+    // C4 2.89 vs 2.42 ms).  NTN_GV=0/1 overrides.
+    bool use_gv = (size_t)Nu * dm.Np * sizeof(float) > ((size_t)48 << 20);
+    if (const char* e = getenv("NTN_GV")) use_gv = e[0] == '1';
     DeviceBatch& b = h->b;
     b.N = n; b.Nu = Nu; b.ntiles = (int)t_rel.size(); b.nchunks = (int)ch_rel.size(); b.n_inc = n_inc;
     b.nstiles = (int)st_rel.size();
+    b.use_gv = use_gv;
     b.n_ent_hub_segs = (int)sr.size();
     int rc;
     if ((rc = dev_upload(h, &b.u_e1, u_e1)) || (rc = dev_upload(h, &b.u_e2, u_e2)) || (rc = dev_upload(h, &b.u_rel, u_rel)) ||
@@ -411,7 +420,7 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
         (rc = dev_upload(h, &b.eh_begin, sb)) || (rc = dev_upload(h, &b.eh_end, se)) ||
         (rc = dev_upload(h, &b.eh_first, first)) || (rc = dev_upload(h, &b.eh_count, count)) ||
         (rc = dev_alloc(h, &b.T, (size_t)Nu * dm.Np)) || (rc = dev_alloc(h, &b.M, (size_t)Nu * dm.Np)) ||
-        (rc = dev_alloc(h, &b.GA, (size_t)Nu * dm.Kp)) || (rc = dev_alloc(h, &b.acoef, ((size_t)Nu + (size_t)n) * dm.k)) ||
+        (rc = dev_alloc(h, &b.GA, (size_t)Nu * dm.Kp)) || (rc = dev_alloc(h, &b.GV, use_gv ? ((size_t)Nu + (size_t)n) * dm.dq : 1)) || (rc = dev_alloc(h, &b.acoef, ((size_t)Nu + (size_t)n) * dm.k)) ||
         (rc = dev_alloc(h, &b.dWpart, (size_t)b.nchunks * dm.Kp * dm.Np)) ||
         (rc = dev_alloc(h, &b.tp_cost, (size_t)b.nstiles)) || (rc = dev_alloc(h, &b.tp_nact, (size_t)b.nstiles)) ||
         (rc = dev_alloc(h, &b.tp_dU, (size_t)b.nstiles * dm.k)) ||

@@ -40,6 +40,7 @@ struct DeviceBatch {
     int ntiles = 0, nchunks = 0, nstiles = 0;
     int n_inc = 0;               // incidents = 2*Nu + N
     int n_ent_hub_segs = 0;
+    bool use_gv = false;         // large batch: k_score materialises one contribution row per incident (GV)
     // unique triples, sorted by (rel, e1, e2)
     int *u_e1 = nullptr, *u_e2 = nullptr, *u_rel = nullptr;
     int *c_off = nullptr;        // Nu+1: corrupt columns of each unique triple
@@ -61,6 +62,7 @@ struct DeviceBatch {
     float *T = nullptr;          // Nu x Np   T' = [E_anchor | 1] * Waug
     float *M = nullptr;          // Nu x Np   backward coefficients folded with the gathered rows
     float *GA = nullptr;         // Nu x Kp   anchor-entity gradient rows
+    float *GV = nullptr;         // (Nu + N) x dq   per-incident contribution rows (non-anchor roles), written by k_score
     float *acoef = nullptr;      // (Nu + N) x k : a_{u,s} rows, then c_{col,s} rows (one allocation)
     float *ccoef = nullptr;      // = acoef + Nu*k
     float *dWpart = nullptr;     // nchunks x Kp x Np

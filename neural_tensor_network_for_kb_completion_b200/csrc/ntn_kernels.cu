@@ -286,6 +286,8 @@ __global__ void __launch_bounds__(256) k_gemm_dw_simt(GemmTables tb, const float
 struct ScoreArgs {
     const float *theta, *E, *T;
     float *M, *acoef, *ccoef;
+    float* GV;                 // (Nu + N) x dq: per-incident contribution rows for the entity pull
+    int Nu;
     const int *t_rel, *t_u0, *t_n, *u_e1, *u_e2, *c_off, *c_e3;
     const uint8_t* side;
     double* tp_cost; int* tp_nact; float* tp_dU;
@@ -308,7 +310,7 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane
     }
 }
 
-template <int KS, int CH, int ACT>
+template <int KS, int CH, int ACT, bool GVW>
 __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
     // corrupt columns per batch: their KS pre-activations each fill the 32 lanes (KS=3 -> 10 columns,
     // the reference's corrupt_size); all row gathers of a batch are issued before any is used.
@@ -436,16 +438,30 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
             if (my_active) dU_l += my_zp - zn;                         // :273
             if (mine_valid) a.ccoef[(size_t)col * KS + lane] = my_cc;  // coalesced: (col+j)*KS + s = col*KS + lane
 #pragma unroll
-            for (int j = 0; j < COLB; ++j)
+            for (int j = 0; j < COLB; ++j) {
+                float4 gv[CH];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) gv[c] = zero4();
 #pragma unroll
                 for (int s = 0; s < KS; ++s) {
                     const float cc = __shfl_sync(FULL, my_cc, j * KS + s);
                     csum[s] += cc;
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) fma4(Macc[s][c], cc, ev[j][c]);
+                    for (int c = 0; c < CH; ++c) { fma4(Macc[s][c], cc, ev[j][c]); if (GVW) fma4(gv[c], cc, t[s][c]); }
                 }
+                // gradient row of the corrupt entity of column col+j: sum_s c_{c,s} T'_u[s,:]  (zero if inactive);
+                // materialised here, where T' is in registers, so the entity pull reads ONE row per incident
+                if (GVW && j < nb) {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c)
+                        if (cv[c]) *reinterpret_cast<float4*>(a.GV + (size_t)(a.Nu + col + j) * dq + (lane + 32 * c) * 4) = gv[c];
+                }
+            }
         }
         float* Mrow = a.M + (size_t)u * a.Np;
+        float4 gvo[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) gvo[c] = zero4();
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
             float as = (float)cnt * tp[s];                            // positive side: one per active copy
@@ -453,9 +469,16 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 fma4(Macc[s][c], as, eo[c]);
+                if (GVW) fma4(gvo[c], as, t[s][c]);
                 if (cv[c]) *reinterpret_cast<float4*>(Mrow + s * dq + (lane + 32 * c) * 4) = Macc[s][c];
             }
             if (lane == 0) a.acoef[(size_t)u * KS + s] = as;
+        }
+        // gradient row of the non-anchor positive entity: sum_s a_{u,s} T'_u[s,:]
+        if (GVW) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                if (cv[c]) *reinterpret_cast<float4*>(a.GV + (size_t)u * dq + (lane + 32 * c) * 4) = gvo[c];
         }
         // coefficient sums ride in the k slots after the slices; zero the rest of the row
         for (int n = KS * dq + lane; n < a.Np; n += 32) {
@@ -489,12 +512,15 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
 // K7  entity-gradient pull (replaces the 8*k*R dense scatter products of Util.java:74-98 and the
 //     dense adds of NTN.java:372,388).  One thread per (entity, float4 chunk) walks the entity's
 //     incident list in a fixed order -- no float atomics, bit-reproducible.  An incident is a packed
-//     16-byte record {unique triple, coefficient row, role, relation}; hub entities (lists longer
-//     than NTN_HUB_SEG) are pre-reduced per segment by k_entity_pull_hub.
+//     16-byte record {unique triple, contribution row, role, relation} and costs ONE row read: the
+//     anchor role reads its GA row (entity-gradient contraction), every other role the row k_score
+//     materialised in GV.  Hub entities (lists longer than NTN_HUB_SEG) are pre-reduced per segment
+//     by k_entity_pull_hub.
 // ==========================================================================================
 struct PullArgs {
-    const float *T, *GA, *coef;          // coef: [acoef (Nu x k) | ccoef (N x k)]
-    const int4* inc;                     // {u, coef row, role (0: e1, 1: e2, 2: e3), rel}
+    const float *T, *coef;               // k-row variant: T' rows + coefficient rows [acoef (Nu x k) | ccoef (N x k)]
+    const float *GV, *GA;                // GV: (Nu + N) x dq contribution rows written by k_score; GA: anchor rows
+    const int4* inc;                     // {u, coefficient / GV row, role (0: e1, 1: e2, 2: e3), rel}
     const int* inc_off;
     const uint8_t* side;
     float* gE;
@@ -503,47 +529,68 @@ struct PullArgs {
     int Ne, dq, Kp, Np, n_segs;
 };
 
-template <int KS>
+// GVR = true : every non-anchor incident reads ONE materialised row (large batches: T' does not fit in L2)
+// GVR = false: it reads its coefficients and the k T' rows (small batches: T' is L2-resident, k_score stays lean)
+template <int KS, bool GVR>
 __device__ __forceinline__ float4 pull_range(const PullArgs& a, int j0, int j1, int c) {
-    constexpr int NB = (KS <= 4) ? 2 : 1;                            // incidents in flight (ILP)
     float4 acc = zero4();
-    for (int jb = j0; jb < j1; jb += NB) {
-        float co[NB][KS]; float4 rows[NB][KS];
+    if (GVR) {
+        constexpr int NB = 4;                                        // incidents in flight (ILP)
+        for (int jb = j0; jb < j1; jb += NB) {
+            float4 rows[NB];
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            const bool ok = jb + i < j1;
-            const int4 rec = ok ? __ldg(a.inc + jb + i) : make_int4(0, 0, 2, 0);
-            const bool tail = a.side[rec.w] != 0;
-            const bool anchor = ok && ((rec.z == 0 && tail) || (rec.z == 1 && !tail));
-            // coefficient and row loads are issued together: gating the rows on "any coefficient non-zero"
-            // (inactive column, NTN.java:229-239) would add one more dependent round trip to every incident
+            for (int i = 0; i < NB; ++i) {
+                const bool ok = jb + i < j1;
+                const int4 rec = ok ? __ldg(a.inc + jb + i) : make_int4(0, 0, 2, 0);
+                const bool tail = a.side[rec.w] != 0;
+                const bool anchor = (rec.z == 0 && tail) || (rec.z == 1 && !tail);
+                rows[i] = ok ? ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : a.GV + (size_t)rec.y * a.dq + c * 4) : zero4();
+            }
 #pragma unroll
-            for (int s = 0; s < KS; ++s) co[i][s] = (ok && !anchor) ? __ldg(a.coef + (size_t)rec.y * KS + s) : 0.f;
-            const float* Trow = a.T + (size_t)rec.x * a.Np + c * 4;
-            rows[i][0] = ok ? ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : Trow) : zero4();
-#pragma unroll
-            for (int s = 1; s < KS; ++s) rows[i][s] = (ok && !anchor) ? ldg4(Trow + s * a.dq) : zero4();
-            if (anchor) co[i][0] = 1.f;
+            for (int i = 0; i < NB; ++i) {                           // incident order: deterministic
+                acc.x += rows[i].x; acc.y += rows[i].y; acc.z += rows[i].z; acc.w += rows[i].w;
+            }
         }
+    } else {
+        constexpr int NB = (KS <= 4) ? 2 : 1;
+        for (int jb = j0; jb < j1; jb += NB) {
+            float co[NB][KS]; float4 rows[NB][KS];
 #pragma unroll
-        for (int i = 0; i < NB; ++i)                                 // incident order: deterministic
+            for (int i = 0; i < NB; ++i) {
+                const bool ok = jb + i < j1;
+                const int4 rec = ok ? __ldg(a.inc + jb + i) : make_int4(0, 0, 2, 0);
+                const bool tail = a.side[rec.w] != 0;
+                const bool anchor = ok && ((rec.z == 0 && tail) || (rec.z == 1 && !tail));
+                // coefficient and row loads are issued together: gating the rows on "any coefficient non-zero"
+                // (inactive column, NTN.java:229-239) would add one more dependent round trip to every incident
 #pragma unroll
-            for (int s = 0; s < KS; ++s) fma4(acc, co[i][s], rows[i][s]);
+                for (int s = 0; s < KS; ++s) co[i][s] = (ok && !anchor) ? __ldg(a.coef + (size_t)rec.y * KS + s) : 0.f;
+                const float* Trow = a.T + (size_t)rec.x * a.Np + c * 4;
+                rows[i][0] = ok ? ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : Trow) : zero4();
+#pragma unroll
+                for (int s = 1; s < KS; ++s) rows[i][s] = (ok && !anchor) ? ldg4(Trow + s * a.dq) : zero4();
+                if (anchor) co[i][0] = 1.f;
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i)                             // incident order: deterministic
+#pragma unroll
+                for (int s = 0; s < KS; ++s) fma4(acc, co[i][s], rows[i][s]);
+        }
     }
     return acc;
 }
 
-template <int KS>
+template <int KS, bool GVR>
 __global__ void __launch_bounds__(256) k_entity_pull_hub(PullArgs a) {
     const int cpr = a.dq >> 2;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int seg = (int)(gid / cpr), c = (int)(gid - (int64_t)seg * cpr);
     if (seg >= a.n_segs) return;
-    float4 acc = pull_range<KS>(a, a.eh_begin[seg], a.eh_end[seg], c);
+    float4 acc = pull_range<KS, GVR>(a, a.eh_begin[seg], a.eh_end[seg], c);
     *reinterpret_cast<float4*>(a.eh_part + (size_t)seg * a.dq + c * 4) = acc;
 }
 
-template <int KS>
+template <int KS, bool GVR>
 __global__ void __launch_bounds__(256, (KS <= 4) ? 6 : 2) k_entity_pull(PullArgs a) {
     const int cpr = a.dq >> 2;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -552,7 +599,7 @@ __global__ void __launch_bounds__(256, (KS <= 4) ? 6 : 2) k_entity_pull(PullArgs
     float4 acc;
     int nseg = a.eh_count ? a.eh_count[n] : 0;
     if (nseg == 0) {
-        acc = pull_range<KS>(a, __ldg(a.inc_off + n), __ldg(a.inc_off + n + 1), c);
+        acc = pull_range<KS, GVR>(a, __ldg(a.inc_off + n), __ldg(a.inc_off + n + 1), c);
     } else {
         acc = zero4();
         int s0 = a.eh_first[n];
@@ -950,14 +997,19 @@ void ntn_launch_gemm_dw_simt(ntn_handle* h, cudaStream_t st) {
 void ntn_launch_score(ntn_handle* h, const float* theta) {
     const NtnDims& dm = h->dm;
     if (h->b.ntiles == 0) return;
-    ScoreArgs a{theta, h->E, h->b.T, h->b.M, h->b.acoef, h->b.ccoef, h->b.st_rel, h->b.st_u0, h->b.st_n,
+    ScoreArgs a{theta, h->E, h->b.T, h->b.M, h->b.acoef, h->b.ccoef, h->b.GV, h->b.Nu, h->b.st_rel, h->b.st_u0, h->b.st_n,
                 h->b.u_e1, h->b.u_e2, h->b.c_off, h->b.c_e3, h->side, h->b.tp_cost, h->b.tp_nact, h->b.tp_dU,
                 dm.d, dm.dq, dm.Kp, dm.Np, dm.oU};
     int ch = cdiv(dm.dq / 4, 32);
     const bool tanh_act = h->cfg.activation == NTN_ACT_TANH;
     DISPATCH_KS(dm.k, DISPATCH_CH(ch, {
-        if (tanh_act) k_score<KS, CH, NTN_ACT_TANH><<<h->b.nstiles, 256, 0, h->stream>>>(a);
-        else k_score<KS, CH, NTN_ACT_SIGMOID><<<h->b.nstiles, 256, 0, h->stream>>>(a);
+        if (h->b.use_gv) {
+            if (tanh_act) k_score<KS, CH, NTN_ACT_TANH, true><<<h->b.nstiles, 256, 0, h->stream>>>(a);
+            else k_score<KS, CH, NTN_ACT_SIGMOID, true><<<h->b.nstiles, 256, 0, h->stream>>>(a);
+        } else {
+            if (tanh_act) k_score<KS, CH, NTN_ACT_TANH, false><<<h->b.nstiles, 256, 0, h->stream>>>(a);
+            else k_score<KS, CH, NTN_ACT_SIGMOID, false><<<h->b.nstiles, 256, 0, h->stream>>>(a);
+        }
     }));
     h->launches++;
 }
@@ -965,16 +1017,18 @@ void ntn_launch_score(ntn_handle* h, const float* theta) {
 void ntn_launch_entity_pull(ntn_handle* h) {
     const NtnDims& dm = h->dm;
     const DeviceBatch& b = h->b;
-    PullArgs a{b.T, b.GA, b.acoef, b.inc, b.inc_off, h->side, h->gE,
+    PullArgs a{b.T, b.acoef, b.GV, b.GA, b.inc, b.inc_off, h->side, h->gE,
                b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
                b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.n_ent_hub_segs};
     const int cpr = dm.dq / 4;
     DISPATCH_KS(dm.k, {
         if (b.n_ent_hub_segs) {
-            k_entity_pull_hub<KS><<<cdiv((int64_t)b.n_ent_hub_segs * cpr, 256), 256, 0, h->stream>>>(a);
+            if (b.use_gv) k_entity_pull_hub<KS, true><<<cdiv((int64_t)b.n_ent_hub_segs * cpr, 256), 256, 0, h->stream>>>(a);
+            else k_entity_pull_hub<KS, false><<<cdiv((int64_t)b.n_ent_hub_segs * cpr, 256), 256, 0, h->stream>>>(a);
             h->launches++;
         }
-        k_entity_pull<KS><<<cdiv((int64_t)dm.Ne * cpr, 256), 256, 0, h->stream>>>(a);
+        if (b.use_gv) k_entity_pull<KS, true><<<cdiv((int64_t)dm.Ne * cpr, 256), 256, 0, h->stream>>>(a);
+        else k_entity_pull<KS, false><<<cdiv((int64_t)dm.Ne * cpr, 256), 256, 0, h->stream>>>(a);
     });
     h->launches++;
 }
