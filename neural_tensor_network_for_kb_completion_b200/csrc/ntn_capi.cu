@@ -133,7 +133,7 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
     CKC(cudaMalloc((void**)&h->side, dm.R));
     CKC(cudaMallocHost((void**)&h->h_side, (size_t)dm.R * NTN_RING));
     for (int i = 0; i < NTN_RING; ++i) CKC(cudaEventCreateWithFlags(&h->side_ev[i], cudaEventDisableTiming));
-    h->n_reg_part = ntn_word_blocks(dm) + dm.Nw + ntn_small_blocks(dm);   // word blocks | hub words (<= Nw) | small blocks
+    h->n_reg_part = ntn_word_blocks(dm) + dm.Nw + ntn_small_blocks(dm) + dm.R * dm.k;   // word blocks | hub words (<= Nw) | small blocks | U
     CKC(cudaMalloc((void**)&h->reg_part, (size_t)h->n_reg_part * sizeof(double)));
     CKC(cudaMalloc((void**)&h->d_out, 4 * sizeof(double)));
     CKC(cudaMallocHost((void**)&h->h_out, 4 * sizeof(double)));

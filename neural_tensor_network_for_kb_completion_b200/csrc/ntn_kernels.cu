@@ -800,16 +800,7 @@ __global__ void __launch_bounds__(256) k_finalize_small(FinArgs a) {
             a.grad[idx] = fmaf(a.lam, th, sum * a.inv_B);
             th2 = th * th;
         }
-    } else if (i < nW + nU) {
-        int j = (int)(i - nW);
-        int r = j / k, s = j - r * k;
-        float sum = 0.f;
-        for (int t = a.rels_off[r]; t < a.rels_off[r + 1]; ++t) sum += a.tp_dU[(size_t)t * k + s];
-        int64_t idx = dm.oU + j;
-        float th = a.theta[idx];
-        a.grad[idx] = fmaf(a.lam, th, sum * a.inv_B);
-        th2 = th * th;
-    } else if (i < nW + nU + (dm.oWVint - (dm.oU + nU))) {
+    } else if (i >= nW + nU && i < nW + nU + (dm.oWVint - (dm.oU + nU))) {
         a.grad[dm.oU + nU + (i - nW - nU)] = 0.f;                     // alignment padding before the word block
     }
     float s = warp_sum(th2);
@@ -819,6 +810,24 @@ __global__ void __launch_bounds__(256) k_finalize_small(FinArgs a) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += s_reg[w];
         a.reg_part[blockIdx.x] = t;
+    }
+}
+
+// dU_r[s] = (1/B) sum over the relation's score tiles of the per-tile partial + lambda*theta   (NTN.java:273,401,438)
+// One block per (relation, slice): threads take interleaved tiles, then a fixed-order tree (deterministic).
+__global__ void __launch_bounds__(256) k_finalize_u(FinArgs a, double* reg_slot) {
+    __shared__ float sm[256];
+    const int k = a.dm.k, r = blockIdx.x / k, s = blockIdx.x - r * k;
+    float v = 0.f;
+    for (int t = a.rels_off[r] + threadIdx.x; t < a.rels_off[r + 1]; t += 256) v += a.tp_dU[(size_t)t * k + s];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) {
+        const int64_t idx = a.dm.oU + blockIdx.x;
+        const float th = a.theta[idx];
+        a.grad[idx] = fmaf(a.lam, th, sm[0] * a.inv_B);
+        reg_slot[blockIdx.x] = (double)th * (double)th;
     }
 }
 
@@ -1071,7 +1080,8 @@ void ntn_launch_finalize_small(ntn_handle* h, const float* theta, float* grad, c
     FinArgs a{theta, b.dWpart, b.tp_dU, grad, b.relch_off, b.rels_off, h->side, h->reg_part + wb, dm,
               1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale};
     k_finalize_small<<<nb, 256, 0, st>>>(a);
-    h->launches++;
+    k_finalize_u<<<dm.R * dm.k, 256, 0, st>>>(a, h->reg_part + wb + nb);
+    h->launches += 2;
 }
 
 void ntn_launch_final_reduce(ntn_handle* h, float* tail) {
@@ -1080,7 +1090,7 @@ void ntn_launch_final_reduce(ntn_handle* h, float* tail) {
     int nb = ntn_small_blocks(dm);
     int wb = word_pull_blocks(dm) + h->w.n_hub_words;
     double lam = (double)h->cfg.lambda * (double)h->cfg.reg_scale;
-    k_final_reduce<<<1, 256, 0, h->stream>>>(b.tp_cost, b.tp_nact, b.nstiles, h->reg_part, wb + nb,
+    k_final_reduce<<<1, 256, 0, h->stream>>>(b.tp_cost, b.tp_nact, b.nstiles, h->reg_part, wb + nb + dm.R * dm.k,
                                              1.0 / (double)h->cfg.batch_divisor, 0.5 * lam, h->d_out, tail);
     h->launches++;
 }
