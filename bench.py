@@ -390,13 +390,10 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
                 tr = json.load(f)
-            kmap = {"score": "k_score<3, 1, 0>", "gemm_fwd": "k_tc_gemm<0>", "gemm_dw": "k_tc_gemm<1>",
-                    "gemm_ge": "k_tc_gemm<2>", "entity_pull": "k_entity_pull<3>"}
-            if top == "word_pull":
-                roofline["traffic"] = tr["k_word_pull"]["dram_bytes_per_launch"] + tr["k_word_pull_hub"]["dram_bytes_per_launch"]
-            elif top in kmap:
-                roofline["traffic"] = tr[kmap[top]]["dram_bytes_per_launch"]
-            roofline["traffic_note"] = "dram__bytes_read+write per launch from profiles/r1_ncu_full_summary.txt (N=1 ncu capture)"
+            if args.config == "c3" and top in tr:
+                roofline["traffic"] = tr[top]["dram_bytes_per_eval"]
+                roofline["traffic_note"] = ("dram__bytes_read+write of this group's kernels, one evaluation, from the ncu --set full "
+                                            "capture in profiles/r1_ncu_full_summary.txt (N=1, same workload)")
         except Exception:
             pass
         roofline["algorithmic_bytes"] = groups[top]["bytes"]
