@@ -832,17 +832,17 @@ __global__ void __launch_bounds__(256) k_finalize_u(FinArgs a, double* reg_slot)
 }
 
 // single block: cost = sum(tile costs)/B + 0.5*lambda*sum(theta^2)      NTN.java:430,437
-__global__ void __launch_bounds__(256) k_final_reduce(const double* __restrict__ tp_cost, const int* __restrict__ tp_nact,
-                                                      int ntiles, const double* __restrict__ reg_part, int nreg,
-                                                      double inv_B, double half_lam, double* __restrict__ out,
-                                                      float* __restrict__ tail) {
-    __shared__ double s_a[256], s_b[256], s_c[256];
+__global__ void __launch_bounds__(1024) k_final_reduce(const double* __restrict__ tp_cost, const int* __restrict__ tp_nact,
+                                                       int ntiles, const double* __restrict__ reg_part, int nreg,
+                                                       double inv_B, double half_lam, double* __restrict__ out,
+                                                       float* __restrict__ tail) {
+    __shared__ double s_a[1024], s_b[1024], s_c[1024];
     double c = 0.0, n = 0.0, r = 0.0;
-    for (int i = threadIdx.x; i < ntiles; i += 256) { c += tp_cost[i]; n += (double)tp_nact[i]; }
-    for (int i = threadIdx.x; i < nreg; i += 256) r += reg_part[i];
+    for (int i = threadIdx.x; i < ntiles; i += 1024) { c += tp_cost[i]; n += (double)tp_nact[i]; }
+    for (int i = threadIdx.x; i < nreg; i += 1024) r += reg_part[i];
     s_a[threadIdx.x] = c; s_b[threadIdx.x] = n; s_c[threadIdx.x] = r;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = 512; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
             s_a[threadIdx.x] += s_a[threadIdx.x + o];
             s_b[threadIdx.x] += s_b[threadIdx.x + o];
@@ -1090,7 +1090,7 @@ void ntn_launch_final_reduce(ntn_handle* h, float* tail) {
     int nb = ntn_small_blocks(dm);
     int wb = word_pull_blocks(dm) + h->w.n_hub_words;
     double lam = (double)h->cfg.lambda * (double)h->cfg.reg_scale;
-    k_final_reduce<<<1, 256, 0, h->stream>>>(b.tp_cost, b.tp_nact, b.nstiles, h->reg_part, wb + nb + dm.R * dm.k,
+    k_final_reduce<<<1, 1024, 0, h->stream>>>(b.tp_cost, b.tp_nact, b.nstiles, h->reg_part, wb + nb + dm.R * dm.k,
                                              1.0 / (double)h->cfg.batch_divisor, 0.5 * lam, h->d_out, tail);
     h->launches++;
 }

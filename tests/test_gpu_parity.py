@@ -56,16 +56,21 @@ def check(h, p, theta, batch, side, wv_frozen=None, label="", atol=ATOL):
     dict(Ne=500, R=11, T=3000, Nw=400, d=100, k=3, batch=2000, corrupt=10),  # reference d,k,C
     dict(Ne=200, R=2, T=300, Nw=100, d=37, k=1, batch=200, corrupt=2),       # odd d, one slice
     dict(Ne=150, R=5, T=400, Nw=80, d=132, k=8, batch=300, corrupt=3),       # two chunks per lane, max k
+    dict(Ne=120, R=3, T=300, Nw=60, d=256, k=8, batch=260, corrupt=2),       # the scaled config's d and k (BASELINE configs[4])
 ])
 def test_cost_and_gradient_match_oracle(shape, gemm_path):
     kb, p, batch, side, theta0 = small_problem(**shape, seed=1)
     theta = f32(spread(perturbed(theta0, 0.05), p, u=4.0, w=10.0, wv=3.0))
     h = make_handle(p, "theta", gemm_path)
     h.set_batch(*batch)
-    # The d=132, k=8 stress shape contracts over K=1064 with a divisor of only B=300, so its gradient
+    # The d>=132, k=8 stress shapes contract over K>=1064 with a divisor of only B=300, so its gradient
     # entries are ~67x larger than at the reference B=20000; the 3xTF32 split represents each operand
     # to 2^-22, which shows as up to 7e-6 absolute there.  Everything else holds the reference-scale 1e-6.
-    atol = 1e-5 if (shape["d"] == 132 and h.gemm_path == "tcgen05") else ATOL
+    atol = 1e-5 if (shape["d"] >= 132 and h.gemm_path == "tcgen05") else ATOL
+    if shape["d"] == 256:
+        # k*d+k = 2056-term contractions and a divisor of 260: entries reach 1.5 and individual contributions cancel
+        # ~30x, so 1e-6 absolute is below what FP32 partial sums resolve (both contraction paths miss it by < 1e-5)
+        atol = 2e-5
     _, _, aux = check(h, p, theta, batch, side, label=str(shape), atol=atol)
     assert 0 < aux["n_active"] < len(batch[0])
     # the other corrupt side for every relation, same batch (NTN.java:146-156 both branches)
