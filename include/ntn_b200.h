@@ -191,6 +191,8 @@ int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, int64_t cap
 /* ---- C++ host layer test hooks (csrc/host/ntn_host.hpp; no GPU needed) ----------------------- */
 /* java.util.Random: n draws of nextInt(bound) (bound == 0: nextInt()), then m draws of nextDouble(). */
 int ntn_host_java_random(int64_t seed, int32_t bound, int64_t n, int32_t* ints, int64_t m, double* doubles);
+/* n consecutive java.util.Random.nextInt(bound) draws continuing from the 48-bit state *state (updated). */
+int ntn_host_random_ints(uint64_t* state, int32_t bound, int64_t n, int32_t* out);
 /* DataFactory name parsing: '\n'-separated entity names and vocabulary -> forward / backward CSRs. */
 int ntn_host_entity_word_maps(const char* names, const char* words, int32_t* fwd_off, int32_t* fwd_idx, int32_t* bwd_off,
                               int32_t* bwd_idx, int32_t* len_bwd, int64_t cap, int64_t* nf, int64_t* nb);

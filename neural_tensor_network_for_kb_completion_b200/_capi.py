@@ -80,6 +80,7 @@ SYMBOLS = {
     "ntn_phase_name": (C.c_char_p, [C.c_int]),
     "ntn_debug_fetch": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64]),
     "ntn_host_java_random": (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _P, C.c_int64, _P]),
+    "ntn_host_random_ints": (C.c_int, [C.POINTER(C.c_uint64), C.c_int32, C.c_int64, _P]),
     "ntn_host_entity_word_maps": (C.c_int, [C.c_char_p, C.c_char_p, _P, _P, _P, _P, _P, C.c_int64,
                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ntn_host_generate_batch": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),

@@ -18,6 +18,27 @@ int ntn_host_java_random(int64_t seed, int32_t bound, int64_t n, int32_t* ints, 
     } catch (...) { return NTN_EINVAL; }
 }
 
+// n consecutive nextInt(bound) draws continuing from *state (the 48-bit LCG state, as JavaRandom holds it); the advanced
+// state is written back.  Lets the Python DataFactory mirror draw 200k corrupt entities at native speed.
+int ntn_host_random_ints(uint64_t* state, int32_t bound, int64_t n, int32_t* out) {
+    if (!state || !out || bound <= 0) return NTN_EINVAL;
+    const uint64_t kMult = 0x5DEECE66DULL, kAdd = 0xBULL, kMask = (1ULL << 48) - 1;
+    uint64_t s = *state;
+    const int32_t m = bound - 1;
+    const bool pow2 = (bound & m) == 0;
+    for (int64_t i = 0; i < n; ++i) {
+        for (;;) {
+            s = (s * kMult + kAdd) & kMask;
+            const int32_t u = (int32_t)(s >> 17);
+            if (pow2) { out[i] = (int32_t)(((int64_t)bound * (int64_t)u) >> 31); break; }
+            const int32_t r = u % bound;
+            if ((int32_t)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) { out[i] = r; break; }
+        }
+    }
+    *state = s;
+    return NTN_OK;
+}
+
 // names / words: '\n'-separated.  Outputs sized by the caller: fwd_off, bwd_off (Ne+1), len_bwd (Ne),
 // fwd_idx / bwd_idx (cap entries each); *nf, *nb receive the used counts.
 int ntn_host_entity_word_maps(const char* names, const char* words, int32_t* fwd_off, int32_t* fwd_idx, int32_t* bwd_off,

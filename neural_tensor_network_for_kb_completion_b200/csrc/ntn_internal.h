@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ntn_b200.h"
@@ -30,7 +31,7 @@ struct NtnDims {
 
 #define NTN_TILE_ROWS   128      // unique triples per contraction tile (one relation per tile)
 #define NTN_CHUNK_ROWS  256      // unique triples per dW split-K chunk (one relation per chunk)
-#define NTN_SCORE_ROWS  32       // unique triples per score tile (8 warps x 4)
+#define NTN_SCORE_ROWS  32       // unique triples per score tile (8 warps x 4); 8-row tiles measured no faster
 #define NTN_HUB_SEG     32       // incident-list segment length for hub words / hub entities
 #define NTN_RING        8        // in-flight evaluations the host may enqueue without synchronising
 
@@ -98,6 +99,7 @@ struct ntn_handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_f0 = nullptr, ev_j0 = nullptr, ev_f1 = nullptr, ev_j1 = nullptr;
     std::string err;
+    std::unordered_map<void*, size_t> capacity;   // bytes behind the device buffers that dev_alloc may reuse
     DeviceWords w;
     DeviceBatch b;
     float *wv_frozen = nullptr;   // Nw x dq (internal word-major), or null

@@ -45,8 +45,19 @@ class JavaRandom:
         return ((self._next(26) << 27) + self._next(27)) * (1.0 / (1 << 53))
 
     def nextInts(self, n: int, bound: int) -> np.ndarray:
-        """n consecutive nextInt(bound) draws (same stream as n calls of nextInt)."""
+        """n consecutive nextInt(bound) draws (same stream as n calls of nextInt).  Uses the C++ host's
+        JavaRandom when the library is built (200k draws per batch job), else the Python loop below."""
         out = np.empty(n, np.int32)
+        try:
+            import ctypes as C
+            from . import _capi
+            lib = _capi.load()
+            st = C.c_uint64(self.s)
+            if lib.ntn_host_random_ints(C.byref(st), int(bound), int(n), out.ctypes.data) == 0:
+                self.s = int(st.value)
+                return out
+        except (ImportError, OSError, AttributeError):
+            pass
         s = self.s
         m = bound - 1
         pow2 = bound & m == 0
