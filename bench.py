@@ -35,7 +35,10 @@ SHAPE, D, K_SLICES, NW, BATCH, CORRUPT, LAMBDA = "freebase", 100, 3, 67447, 2000
 CONFIG_NAME = "BASELINE.json configs[2]"
 # headline = c3.  c1: Wordnet-shaped batch (configs[1]); c4: Freebase-shaped FULL batch, all 316,232 triples x 10 (configs[3])
 CONFIGS = {"c1": ("wordnet", 20000, "BASELINE.json configs[1]"), "c3": ("freebase", 20000, "BASELINE.json configs[2]"),
-           "c4": ("freebase", 316232, "BASELINE.json configs[3], per-GPU share of the full batch")}
+           "c4": ("freebase", 316232, "BASELINE.json configs[3], per-GPU share of the full batch"),
+           # configs[4]'s model shape (1M entities, 64 relations, d=256, k=8, 500k words) with a 200,000 x 10 batch job
+           "c5": ("scaled", 200000, "BASELINE.json configs[4] shape, 200,000-triple batch job")}
+SCALED = dict(Ne=1000000, R=64, d=256, k=8, Nw=500000)
 
 
 def peaks():
@@ -89,6 +92,8 @@ class ClockSampler:
 
 def build_problem(n_ranks):
     from neural_tensor_network_for_kb_completion_b200 import synth
+    if SHAPE == "scaled":
+        return synth.make_kb(SCALED["Ne"], SCALED["R"], max(BATCH * n_ranks, BATCH), SCALED["Nw"], SCALED["d"], seed=0)
     kb = synth.make_shaped(SHAPE, d=D, Nw=NW, T=max(BATCH * n_ranks, BATCH), seed=0)
     return kb
 
@@ -211,8 +216,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     args = ap.parse_args()
-    global SHAPE, BATCH, CONFIG_NAME
+    global SHAPE, BATCH, CONFIG_NAME, D, K_SLICES, NW
     SHAPE, BATCH, CONFIG_NAME = CONFIGS[args.config]
+    if SHAPE == "scaled":
+        D, K_SLICES, NW = SCALED["d"], SCALED["k"], SCALED["Nw"]
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup

@@ -131,15 +131,19 @@ extern "C" int ntn_lbfgs_minimize(ntn_handle* h, float* d_theta, const ntn_lbfgs
     const int64_t n = dm.Pint;                     // multiple of 4 by construction (oWVint % 4 == 0, dq % 4 == 0)
     if (n % 4) { h->err = "internal dimension not a multiple of 4"; return NTN_EUNSUP; }
     Lb lb{h, n / 4, nullptr, nullptr, h->stream};
-    float* buf = nullptr;                          // S[m] Y[m] g gnew dir trial
+    // workspace S[m] Y[m] g gnew dir trial + scalars, kept in the handle across calls (stable pointers also let the
+    // evaluation graphs of (theta, g) and (trial, gnew) be reused while the batch job stays the same)
     const size_t nvec = (size_t)2 * m + 4;
-    cudaError_t e;
-    if ((e = cudaMalloc((void**)&buf, nvec * n * sizeof(float))) || (e = cudaMalloc((void**)&lb.part, LB_BLOCKS * sizeof(double))) ||
-        (e = cudaMalloc((void**)&lb.sc, (2 * m + 8) * sizeof(double)))) {
-        cudaFree(buf); cudaFree(lb.part);
-        h->err = std::string("lbfgs alloc: ") + cudaGetErrorString(e);
-        return NTN_ECUDA;
+    const size_t need = nvec * n * sizeof(float) + LB_BLOCKS * sizeof(double) + (2 * m + 8) * sizeof(double);
+    if (h->lbfgs_ws_bytes < need) {
+        cudaFree(h->lbfgs_ws); h->lbfgs_ws = nullptr; h->lbfgs_ws_bytes = 0;
+        cudaError_t e = cudaMalloc(&h->lbfgs_ws, need);
+        if (e != cudaSuccess) { h->err = std::string("lbfgs alloc: ") + cudaGetErrorString(e); return NTN_ECUDA; }
+        h->lbfgs_ws_bytes = need;
     }
+    float* buf = (float*)h->lbfgs_ws;
+    lb.part = (double*)((char*)h->lbfgs_ws + nvec * n * sizeof(float));
+    lb.sc = lb.part + LB_BLOCKS;
     float* S = buf; float* Y = buf + (size_t)m * n;
     float* g = buf + (size_t)2 * m * n; float* gnew = g + n; float* dir = gnew + n; float* trial = dir + n;
     double* alpha = lb.sc; double* rho = lb.sc + m; double* tmp = lb.sc + 2 * m;
@@ -219,7 +223,6 @@ extern "C" int ntn_lbfgs_minimize(ntn_handle* h, float* d_theta, const ntn_lbfgs
     }
 done:
     cudaStreamSynchronize(lb.st);
-    cudaFree(buf); cudaFree(lb.part); cudaFree(lb.sc);
     res->min_obj_val = f; res->iters = iters; res->evals = evals; res->did_converge = converged ? 1 : 0;
     res->n_active_last = nact;
     return rc;

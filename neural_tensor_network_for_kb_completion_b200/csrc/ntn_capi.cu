@@ -179,6 +179,7 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     dev_free(h->wv_frozen); dev_free(h->E); dev_free(h->gE); dev_free(h->Waug); dev_free(h->side);
     dev_free(h->reg_part); dev_free(h->d_out); dev_free(h->d_ref_theta); dev_free(h->d_ref_grad);
     dev_free(h->d_int_theta); dev_free(h->d_int_grad);
+    if (h->lbfgs_ws) cudaFree(h->lbfgs_ws);
     if (h->h_side) cudaFreeHost(h->h_side);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_stage) cudaFreeHost(h->h_stage);

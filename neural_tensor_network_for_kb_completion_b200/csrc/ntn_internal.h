@@ -128,6 +128,8 @@ struct ntn_handle {
     double phase_acc[NTN_NUM_PHASES] = {};
     int phase_n = 0;
     void *tc = nullptr;           // tcgen05 path state (gemm_tcgen05.cu)
+    void *lbfgs_ws = nullptr;     // L-BFGS workspace (lbfgs.cu), grow-only
+    size_t lbfgs_ws_bytes = 0;
     // CUDA graphs of the evaluation, one per (theta, grad, stream) triple
     struct GraphEntry { const float* theta; float* grad; cudaStream_t stream; cudaGraphExec_t exec; int launches; };
     std::vector<GraphEntry> graphs;

@@ -36,9 +36,17 @@ class LBFGSMinimizer:
         opts = opts or Opts()
         fn._sync_batch()
         h = fn.handle
-        d_theta = torch.empty(h.Pint, dtype=torch.float32, device=f"cuda:{fn.device}")
-        h.upload_theta(np.asarray(theta, np.float64), d_theta.data_ptr())
+        # theta stays in HBM between calls: the device copy is reused when the caller passes back the very array the
+        # previous call returned (Run_NTN.java:124 does exactly that: theta = res.minArg)
+        cache = getattr(fn, "_lbfgs_dev", None)
+        if cache is None or cache[0].numel() != h.Pint:
+            cache = [torch.empty(h.Pint, dtype=torch.float32, device=f"cuda:{fn.device}"), None]
+            fn._lbfgs_dev = cache
+        d_theta = cache[0]
+        if cache[1] is None or cache[1] is not theta:
+            h.upload_theta(np.asarray(theta, np.float64), d_theta.data_ptr())
         r = h.lbfgs_minimize(d_theta.data_ptr(), fn.drawCorruptSides, opts.maxIters, opts.maxHistorySize, opts.tol)
         fn.update += int(r.n_active_last)
-        return Result(h.download_theta(d_theta.data_ptr()), r.min_obj_val, bool(r.did_converge), r.iters, r.evals,
-                      r.first_cost)
+        out = h.download_theta(d_theta.data_ptr())
+        cache[1] = out
+        return Result(out, r.min_obj_val, bool(r.did_converge), r.iters, r.evals, r.first_cost)
