@@ -13,8 +13,9 @@
 //   warp  4    TMEM allocation + the single-thread MMA issuer: per k-step of 8 it issues
 //              tcgen05.mma kind::tf32  hi*hi, lo*hi, hi*lo  into the same FP32 accumulator, then
 //              tcgen05.commit releases the stage ("empty" mbarrier) / signals the epilogue.
-// All operands are K-major SWIZZLE_128B tiles (row = M/N index, 128 bytes of K per row).  dw contracts
-// over the ROW index of both of its operands, so its producers transpose while they store.
+// fwd and ge use K-major SWIZZLE_128B tiles (row = M/N index, 128 bytes of K per row).  dw contracts over the ROW
+// index of both of its operands, so it uses MN-major tiles (SWIZZLE_128B_BASE32B, the only MN-major layout for 32-bit
+// types); a K-major variant whose producers transpose while they store is kept as NTN_TC_DW=k.
 // The weight operand Waug is written once per evaluation by k_tc_w_prep in both K-major orientations; in fwd and ge
 // it is fed by TMA (cp.async.bulk.tensor 2-D boxes from pre-split hi/lo arrays, SWIZZLE_128B tensor maps, completion
 // bytes on the stage's full mbarrier); NTN_TC_TMA=0 selects the software-loaded fallback.
@@ -39,6 +40,7 @@ struct TcState {
     float *W = nullptr;                         // [R][KpN][NpP]  Waug,   K(=n)-major rows      (ge  B)
     // TMA path: the same two arrays pre-split into TF32 hi/lo, and their tiled tensor maps (SWIZZLE_128B boxes)
     bool use_tma = false;
+    bool dw_mn = false;                         // dw with MN-major (SWIZZLE_128B_BASE32B) operand tiles
     float *WT_hi = nullptr, *WT_lo = nullptr, *W_hi = nullptr, *W_lo = nullptr;
     CUtensorMap mWT_hi, mWT_lo, mW_hi, mW_lo;
     int box_fwd = 0, box_ge = 0;                // rows per TMA box
@@ -121,9 +123,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
 }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32, M=128
 __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
@@ -172,7 +174,12 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float v[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int MODE, bool TMA_B>
+// DW_MN (dw only): both operands as MN-major tiles.  dw contracts over the ROW index u of E_anchor and M, i.e. its K
+// index is the slow dimension of both arrays; an MN-major UMMA operand takes the rows as they are (coalesced loads,
+// 16-byte stores).  For 32-bit types the only MN-major layout is SWIZZLE_128B_BASE32B: atoms of 4 K-rows x 128 bytes,
+// 32-byte chunks XOR-ed with (row & 3); tile = [32-float MN atom][32 rows][128 B] -> LBO = 4096, SBO = 512, a k-step
+// (8 rows) advances the start address by 1024.
+template <int MODE, bool TMA_B, bool DW_MN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __grid_constant__ CUtensorMap mapB_hi,
                                                            const __grid_constant__ CUtensorMap mapB_lo) {
     // SWIZZLE_128B tiles need 1024-byte alignment.  The array is used directly (no pointer arithmetic through
@@ -299,8 +306,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
                         }
                     }
                 }
+            } else if (DW_MN) {
+                // ---- dw, MN-major tiles: rows as they are.  Thread (rsub, j): rows ul = rsub, rsub+16 of the k-block,
+                //      16-byte chunk j of every 32-float atom.
+                float4 xa[2][4], xb[2][TC_NCH / 32];
+#pragma unroll
+                for (int i2 = 0; i2 < 2; ++i2) {
+                    const int u = k0 + rsub + 16 * i2;
+                    const int an = (u < rows) ? (tail ? __ldg(a.u_e1 + u0 + u) : __ldg(a.u_e2 + u0 + u)) : -1;
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const int p = m0 + mi * 32 + j * 4;
+                        xa[i2][mi] = (an >= 0 && p < a.Kp) ? ldg4g(a.E + (size_t)an * a.Kp + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int ni = 0; ni < TC_NCH / 32; ++ni) {
+                        const int n = ni * 32 + j * 4;
+                        xb[i2][ni] = (an >= 0 && n < nlen) ? ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int i2 = 0; i2 < 2; ++i2) {
+                    const int ul = rsub + 16 * i2;
+                    const uint32_t rowoff = ul * 128 + ((((uint32_t)j >> 1) ^ (ul & 3)) << 5) + (j & 1) * 16;
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        float4 hi, lo;
+                        split_tf32(xa[i2][mi], hi, lo);
+                        sts4(sA_hi, mi * 4096 + rowoff, hi); sts4(sA_lo, mi * 4096 + rowoff, lo);
+                    }
+#pragma unroll
+                    for (int ni = 0; ni < TC_NCH / 32; ++ni) {
+                        if (ni * 32 < nlen) {
+                            float4 hi, lo;
+                            split_tf32(xb[i2][ni], hi, lo);
+                            sts4(sB_hi, ni * 4096 + rowoff, hi); sts4(sB_lo, ni * 4096 + rowoff, lo);
+                        }
+                    }
+                }
             } else {
-                // ---- dw: the contraction runs over the ROW index u of both operands, so the producers
+                // ---- dw (K-major fallback): the contraction runs over the ROW index u of both operands, so the producers
                 //      transpose while storing: lane = u row of this k-block (K index), warps stride over the
                 //      16-byte column chunks.  For a fixed chunk and component the 32 lanes hit 32 different
                 //      banks (8 swizzled k-chunks x 4 words), so the 4-byte stores are conflict-free.
@@ -408,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
         tc_fence_before();
     } else {
         // ================================ MMA issuer ================================
-        const uint32_t idesc = make_idesc(nlen, 0, 0);
+        const uint32_t idesc = make_idesc(nlen, DW_MN ? 1 : 0, DW_MN ? 1 : 0);
         bool alive = true;
         for (int kb = 0; kb < nkb && alive; ++kb) {
             const int s = kb % TC_STAGES;
@@ -422,9 +467,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
                 const int kleft = kext - kb * TC_BK;
                 const int nks = (kleft >= TC_BK) ? 4 : (kleft + 7) / 8;
                 for (int ks = 0; ks < nks; ++ks) {
-                    // K-major: a k-step is 32 bytes inside the 128-byte swizzle row; 8-row groups are 1024 B apart
-                    const uint64_t dAh = make_desc(sA_hi + ks * 32, 16, 1024), dAl = make_desc(sA_lo + ks * 32, 16, 1024);
-                    const uint64_t dBh = make_desc(sB_hi + ks * 32, 16, 1024), dBl = make_desc(sB_lo + ks * 32, 16, 1024);
+                    uint64_t dAh, dAl, dBh, dBl;
+                    if (DW_MN) {     // MN-major SWIZZLE_128B_BASE32B: k-step = 8 rows = 1024 B; MN atoms 4096 B apart; 4-row K groups 512 B apart
+                        dAh = make_desc(sA_hi + ks * 1024, 4096, 512, 1); dAl = make_desc(sA_lo + ks * 1024, 4096, 512, 1);
+                        dBh = make_desc(sB_hi + ks * 1024, 4096, 512, 1); dBl = make_desc(sB_lo + ks * 1024, 4096, 512, 1);
+                    } else {         // K-major: a k-step is 32 bytes inside the 128-byte swizzle row; 8-row groups are 1024 B apart
+                        dAh = make_desc(sA_hi + ks * 32, 16, 1024); dAl = make_desc(sA_lo + ks * 32, 16, 1024);
+                        dBh = make_desc(sB_hi + ks * 32, 16, 1024); dBl = make_desc(sB_lo + ks * 32, 16, 1024);
+                    }
                     const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
                     umma_tf32(tmem_base, dAl, dBh, idesc, first);      // small terms first
                     umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
@@ -570,7 +620,10 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
                 return NTN_ECUDA;
             }
         }
-        if ((e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+        const char* dw_env = getenv("NTN_TC_DW");
+        st->dw_mn = dw_env ? (dw_env[0] == 'm') : true;      // NTN_TC_DW=k selects the K-major transposing producers
+        if ((e = cudaFuncSetAttribute(k_tc_gemm<TC_DW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
             (e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
             (e = cudaFuncSetAttribute(k_tc_gemm<TC_DW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
             (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
@@ -619,7 +672,8 @@ int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t stq) {
     TcArgs a = tc_args(h, true);
     dim3 g(h->b.nchunks, cdivi(h->dm.Np, TC_NCH), cdivi(h->dm.Kp, 128));
     TcState* st = (TcState*)h->tc;
-    k_tc_gemm<TC_DW, false><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo);
+    if (st->dw_mn) k_tc_gemm<TC_DW, false, true><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo);
+    else k_tc_gemm<TC_DW, false><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo);
     h->launches++;
     return NTN_OK;
 }
