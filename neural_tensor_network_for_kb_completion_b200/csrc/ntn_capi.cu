@@ -238,17 +238,17 @@ extern "C" int ntn_set_profiling(ntn_handle* h, int on) {
 // Split the lists longer than NTN_HUB_SEG into segments (hub words like "unknown", hub entities).
 static void build_hub_segments(const std::vector<int>& off, int nrows, std::vector<int>& seg_row,
                                std::vector<int>& seg_begin, std::vector<int>& seg_end, std::vector<int>& first,
-                               std::vector<int>& count) {
+                               std::vector<int>& count, int seg_len = NTN_HUB_SEG, int hub_threshold = NTN_HUB_SEG) {
     first.assign(nrows, -1);
     count.assign(nrows, 0);
     for (int r = 0; r < nrows; ++r) {
         int n = off[r + 1] - off[r];
-        if (n <= NTN_HUB_SEG) continue;
+        if (n <= hub_threshold) continue;
         first[r] = (int)seg_row.size();
-        for (int b = off[r]; b < off[r + 1]; b += NTN_HUB_SEG) {
+        for (int b = off[r]; b < off[r + 1]; b += seg_len) {
             seg_row.push_back(r);
             seg_begin.push_back(b);
-            seg_end.push_back(std::min(b + NTN_HUB_SEG, off[r + 1]));
+            seg_end.push_back(std::min(b + seg_len, off[r + 1]));
             count[r]++;
         }
     }
@@ -288,7 +288,7 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
     std::vector<float> lb(dm.Ne);
     for (int n = 0; n < dm.Ne; ++n) lb[n] = (float)len_bwd[n];
     std::vector<int> sr, sb, se, first, count;
-    build_hub_segments(woff, dm.Nw, sr, sb, se, first, count);
+    build_hub_segments(woff, dm.Nw, sr, sb, se, first, count, NTN_WORD_HUB_SEG, NTN_HUB_SEG);
     w.n_hub_segs = (int)sr.size();
     std::vector<int> hub_words;
     for (int i = 0; i < dm.Nw; ++i) if (count[i] > 0) hub_words.push_back(i);

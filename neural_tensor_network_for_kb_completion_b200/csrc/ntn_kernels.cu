@@ -636,19 +636,20 @@ struct WordArgs {
     float inv_B, lam;
 };
 
+template <int NB>                                                    // entities in flight (ILP)
 __device__ __forceinline__ float4 word_range(const WordArgs& a, int j0, int j1, int c) {
     float4 acc = zero4();
-    for (int jb = j0; jb < j1; jb += 4) {
-        float4 v[4]; float len[4];
+    for (int jb = j0; jb < j1; jb += NB) {
+        float4 v[NB]; float len[NB];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NB; ++i) {
             const bool ok = jb + i < j1;
             const int n = ok ? __ldg(a.w_ent + jb + i) : 0;
             len[i] = ok ? __ldg(a.len_bwd + n) : 1.f;
             v[i] = ok ? ldg4(a.gE + (size_t)n * a.dq + c * 4) : zero4();
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                                 // entity order, like NTN.java:414-426
+        for (int i = 0; i < NB; ++i) {                                // entity order, like NTN.java:414-426
             acc.x += v[i].x / len[i]; acc.y += v[i].y / len[i];       // :420
             acc.z += v[i].z / len[i]; acc.w += v[i].w / len[i];
         }
@@ -669,7 +670,7 @@ __global__ void __launch_bounds__(256) k_word_pull_hub(WordArgs a) {
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int seg = (int)(gid / cpr), c = (int)(gid - (int64_t)seg * cpr);
     if (seg >= a.n_segs) return;
-    float4 acc = word_range(a, a.wh_begin[seg], a.wh_end[seg], c);
+    float4 acc = word_range<8>(a, a.wh_begin[seg], a.wh_end[seg], c);   // short latency-bound branch: 8 rows in flight
     *reinterpret_cast<float4*>(a.wh_part + (size_t)seg * a.dq + c * 4) = acc;
 }
 
@@ -739,7 +740,7 @@ __global__ void __launch_bounds__(256, 6) k_word_pull(WordArgs a) {
                 float4 v = ldg4(a.gE + (size_t)rec.z * a.dq + c * 4);
                 acc = make_float4(v.x / len, v.y / len, v.z / len, v.w / len);
             } else if (rec.y > rec.x) {
-                acc = word_range(a, rec.x, rec.y, c);
+                acc = word_range<4>(a, rec.x, rec.y, c);                // main kernel: keep registers (occupancy) low
             }
             reg = word_store(a, o, th, acc);
         }
