@@ -152,10 +152,16 @@ void* ntn_get_stream(ntn_handle* h);
  * point is one ntn_eval_dev on the current batch job; sides_fn is called once per evaluation to draw that
  * evaluation's corrupt sides (the reference draws Math.random() inside computeAt, NTN.java:146). */
 typedef void (*ntn_sides_fn)(void* ctx, uint8_t* corrupt_side /* R, to fill */);
+/* Data parallel: called after every evaluation with the DEVICE gradient of this rank's shard followed by the 4-float
+ * {cost, n_active} tail (see ntn_set_grad_tail); must SUM all-reduce those n floats in place across the ranks (on the
+ * handle's stream or synchronised with it).  Every rank then continues with identical numbers. */
+typedef void (*ntn_reduce_fn)(void* ctx, float* d_grad_and_tail, int64_t n);
 typedef struct ntn_lbfgs_opts {
     int32_t max_iters;      /* LBFGSMinimizer.Opts.maxIters; Run_NTN sets 5 (batch_iterations)   */
     int32_t history;        /* curvature pairs kept (0 = default 6)                              */
     double  tol;            /* relative function-change tolerance (0 = default 1e-4)             */
+    ntn_reduce_fn reduce_fn;   /* NULL for a single process                                      */
+    void*   reduce_ctx;
 } ntn_lbfgs_opts;
 typedef struct ntn_lbfgs_result {
     double  min_obj_val;    /* IOptimizer.Result.minObjVal */

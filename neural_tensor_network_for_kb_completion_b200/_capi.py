@@ -35,8 +35,12 @@ class Config(C.Structure):
                 ("reg_scale", C.c_float)]
 
 
+REDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64)
+
+
 class LbfgsOpts(C.Structure):
-    _fields_ = [("max_iters", C.c_int32), ("history", C.c_int32), ("tol", C.c_double)]
+    _fields_ = [("max_iters", C.c_int32), ("history", C.c_int32), ("tol", C.c_double),
+                ("reduce_fn", REDUCE_FN), ("reduce_ctx", C.c_void_p)]
 
 
 class LbfgsResult(C.Structure):
@@ -254,9 +258,10 @@ class Handle:
         self._ck(self.lib.ntn_score(self.h, _ptr(theta), len(e1), _ptr(e1), _ptr(rel), _ptr(e2), m, _ptr(out)))
         return out
 
-    def lbfgs_minimize(self, d_theta: int, draw_sides, max_iters=5, history=0, tol=0.0):
+    def lbfgs_minimize(self, d_theta: int, draw_sides, max_iters=5, history=0, tol=0.0, reduce=None):
         """Device-resident L-BFGS on the current batch job; ``draw_sides()`` returns this evaluation's
-        corrupt sides (uint8[R]).  Returns the LbfgsResult; theta is updated in place on the device."""
+        corrupt sides (uint8[R]).  Returns the LbfgsResult; theta is updated in place on the device.
+        Data parallel: ``reduce(ptr, n)`` must SUM all-reduce the n device floats at ``ptr`` in place."""
         R = self.R
 
         def _cb(_ctx, out):
@@ -264,7 +269,8 @@ class Handle:
             for r in range(R):
                 out[r] = int(s[r])
         cb = SIDES_FN(_cb)
-        opts, res = LbfgsOpts(max_iters, history, tol), LbfgsResult()
+        rcb = REDUCE_FN(lambda _ctx, ptr, n: reduce(int(ptr), int(n))) if reduce is not None else REDUCE_FN()
+        opts, res = LbfgsOpts(max_iters, history, tol, rcb, None), LbfgsResult()
         self._ck(self.lib.ntn_lbfgs_minimize(self.h, d_theta, C.byref(opts), cb, None, C.byref(res)))
         return res
 

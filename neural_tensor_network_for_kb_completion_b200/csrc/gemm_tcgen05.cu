@@ -6,13 +6,13 @@
 //   ge   GA[u, p]      = sum_n  M[u, n] * Waug_r[p, n]                     NTN.java:352-388
 //
 // One CTA = one 128-row accumulator tile in TMEM (tcgen05.alloc), N <= 160 columns, 288 threads.
-//   warps 0-3 and 5-8  two producer groups taking alternate k-blocks: gather / load FP32 operand rows, split x = hi + lo (hi = rna-tf32(x),
-//              lo = rna-tf32(x - hi)), store both into 128B-swizzled UMMA shared-memory tiles,
-//              fence.proxy.async, arrive on the stage's "full" mbarrier; afterwards the same warps
-//              run the epilogue (tcgen05.ld -> registers -> global).
-//   warp  4    TMEM allocation + the single-thread MMA issuer: per k-step of 8 it issues
-//              tcgen05.mma kind::tf32  hi*hi, lo*hi, hi*lo  into the same FP32 accumulator, then
-//              tcgen05.commit releases the stage ("empty" mbarrier) / signals the epilogue.
+//   warps 0-3, 5-8  two producer groups taking alternate k-blocks: gather / load FP32 operand rows, split x = hi + lo
+//                   (both exactly representable in TF32), store both into swizzled UMMA shared-memory tiles,
+//                   fence.proxy.async, arrive on the stage's "full" mbarrier; warps 0-3 then run the epilogue
+//                   (tcgen05.ld -> registers -> staged in shared memory -> coalesced global stores).
+//   warp 4          TMEM allocation + the single-thread MMA issuer: per k-step of 8 it issues tcgen05.mma kind::tf32
+//                   lo*hi, hi*lo, hi*hi into the same FP32 accumulator, then tcgen05.commit releases the stage
+//                   ("empty" mbarrier) / signals the epilogue.
 // fwd and ge use K-major SWIZZLE_128B tiles (row = M/N index, 128 bytes of K per row).  dw contracts over the ROW
 // index of both of its operands, so it uses MN-major tiles (SWIZZLE_128B_BASE32B, the only MN-major layout for 32-bit
 // types); a K-major variant whose producers transpose while they store is kept as NTN_TC_DW=k.
@@ -47,7 +47,6 @@ struct TcState {
     int KpP = 0, KpN = 0, NpP = 0;
     int* err = nullptr;                         // device flag: a bounded wait expired
     long long* dbg = nullptr;                   // 3 x 256 cycle stamps of CTA (0,0,0) per mode (debug timeline)
-    bool attr_set = false;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -146,7 +145,7 @@ __device__ __forceinline__ void sts4(uint8_t* base, uint32_t off, const float4& 
 
 // ------------------------------------------------------------------------------------------
 struct TcArgs {
-    const int *t_rel, *t_u0, *t_n;     // tile table (fwd/ge: <=128 rows) or chunk table (dw: <=512 rows)
+    const int *t_rel, *t_u0, *t_n;     // tile table (fwd/ge: <=128 rows) or split-K chunk table (dw)
     const int *u_e1, *u_e2;
     const uint8_t* side;
     const float *E, *M;

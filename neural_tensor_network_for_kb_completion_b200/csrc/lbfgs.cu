@@ -134,7 +134,8 @@ extern "C" int ntn_lbfgs_minimize(ntn_handle* h, float* d_theta, const ntn_lbfgs
     // workspace S[m] Y[m] g gnew dir trial + scalars, kept in the handle across calls (stable pointers also let the
     // evaluation graphs of (theta, g) and (trial, gnew) be reused while the batch job stays the same)
     const size_t nvec = (size_t)2 * m + 4;
-    const size_t need = nvec * n * sizeof(float) + LB_BLOCKS * sizeof(double) + (2 * m + 8) * sizeof(double);
+    const int64_t ns = n + 4;                      // vector stride: room for the {cost, n_active} tail after a gradient
+    const size_t need = nvec * ns * sizeof(float) + LB_BLOCKS * sizeof(double) + (2 * m + 8) * sizeof(double);
     if (h->lbfgs_ws_bytes < need) {
         cudaFree(h->lbfgs_ws); h->lbfgs_ws = nullptr; h->lbfgs_ws_bytes = 0;
         cudaError_t e = cudaMalloc(&h->lbfgs_ws, need);
@@ -142,20 +143,33 @@ extern "C" int ntn_lbfgs_minimize(ntn_handle* h, float* d_theta, const ntn_lbfgs
         h->lbfgs_ws_bytes = need;
     }
     float* buf = (float*)h->lbfgs_ws;
-    lb.part = (double*)((char*)h->lbfgs_ws + nvec * n * sizeof(float));
+    lb.part = (double*)((char*)h->lbfgs_ws + nvec * ns * sizeof(float));
     lb.sc = lb.part + LB_BLOCKS;
-    float* S = buf; float* Y = buf + (size_t)m * n;
-    float* g = buf + (size_t)2 * m * n; float* gnew = g + n; float* dir = gnew + n; float* trial = dir + n;
+    float* S = buf; float* Y = buf + (size_t)m * ns;
+    float* g = buf + (size_t)2 * m * ns; float* gnew = g + ns; float* dir = gnew + ns; float* trial = dir + ns;
     double* alpha = lb.sc; double* rho = lb.sc + m; double* tmp = lb.sc + 2 * m;
     std::vector<uint8_t> side(dm.R);
     int rc = NTN_OK, evals = 0, iters = 0, hist = 0, head = 0;     // ring: newest pair at (head-1) mod m
     bool converged = false;
     double f = 0.0, fnew = 0.0;
     int64_t nact = 0;
+    // single process: plain evaluation.  Data parallel: the evaluation writes the {cost, n_active} tail after the
+    // gradient, the caller's reduce_fn all-reduces gradient + tail, and cost / n_active are read back from the tail.
+    const bool saved_tail = h->grad_tail;
+    if (h->grad_tail != (o->reduce_fn != nullptr)) ntn_set_grad_tail(h, o->reduce_fn != nullptr);
     auto evaluate = [&](const float* th, float* gr, double* cost) {
         sides_fn(ctx, side.data());
         ++evals;
-        return ntn_eval_dev(h, th, side.data(), gr, cost, &nact);
+        if (!o->reduce_fn) return ntn_eval_dev(h, th, side.data(), gr, cost, &nact);
+        int rc2 = ntn_eval_dev(h, th, side.data(), gr, nullptr, nullptr);
+        if (rc2) return rc2;
+        o->reduce_fn(o->reduce_ctx, gr, n + 4);
+        float tail[4];
+        cudaMemcpyAsync(tail, gr + n, sizeof(tail), cudaMemcpyDeviceToHost, lb.st);
+        if (cudaStreamSynchronize(lb.st) != cudaSuccess) { h->err = "lbfgs: stream error after the gradient exchange"; return (int)NTN_ECUDA; }
+        *cost = (double)tail[0] + (double)tail[1];
+        nact = (int64_t)llround((double)tail[2]) * 4096 + (int64_t)llround((double)tail[3]);
+        return (int)NTN_OK;
     };
     if ((rc = evaluate(d_theta, g, &f))) goto done;
     res->first_cost = f;
@@ -164,12 +178,12 @@ extern "C" int ntn_lbfgs_minimize(ntn_handle* h, float* d_theta, const ntn_lbfgs
         cudaMemcpyAsync(dir, g, n * sizeof(float), cudaMemcpyDeviceToDevice, lb.st);
         for (int i = 0; i < hist; ++i) {                           // newest to oldest
             int j = (head - 1 - i + 2 * m) % m;
-            lb.dot(S + (size_t)j * n, dir, alpha + j, 1, rho + j);                                      // alpha_j = rho_j s_j.q
-            k_axpby<<<LB_BLOCKS, LB_THREADS, 0, lb.st>>>(dir, Y + (size_t)j * n, lb.n4, alpha + j, -1.0, 1.0);   // q -= alpha_j y_j
+            lb.dot(S + (size_t)j * ns, dir, alpha + j, 1, rho + j);                                      // alpha_j = rho_j s_j.q
+            k_axpby<<<LB_BLOCKS, LB_THREADS, 0, lb.st>>>(dir, Y + (size_t)j * ns, lb.n4, alpha + j, -1.0, 1.0);   // q -= alpha_j y_j
         }
         if (hist > 0) {
             int j = (head - 1 + m) % m;                            // H0 = (s.y / y.y) I = 1 / (rho_j * y_j.y_j)
-            lb.dot(Y + (size_t)j * n, Y + (size_t)j * n, tmp, 1, rho + j);
+            lb.dot(Y + (size_t)j * ns, Y + (size_t)j * ns, tmp, 1, rho + j);
             k_dot_final<<<1, 256, 0, lb.st>>>(tmp, 1, tmp + 1, 3, nullptr, nullptr);                    // tmp[1] = 1/(rho y.y)
             // r = gamma * q
             double gamma = lb.fetch(tmp + 1);
@@ -177,8 +191,8 @@ extern "C" int ntn_lbfgs_minimize(ntn_handle* h, float* d_theta, const ntn_lbfgs
         }
         for (int i = hist - 1; i >= 0; --i) {                      // oldest to newest
             int j = (head - 1 - i + 2 * m) % m;
-            lb.dot(Y + (size_t)j * n, dir, tmp, 2, rho + j, alpha + j);                                 // tmp = alpha_j - rho_j y_j.r
-            k_axpby<<<LB_BLOCKS, LB_THREADS, 0, lb.st>>>(dir, S + (size_t)j * n, lb.n4, tmp, 1.0, 1.0); // r += (alpha_j - beta) s_j
+            lb.dot(Y + (size_t)j * ns, dir, tmp, 2, rho + j, alpha + j);                                 // tmp = alpha_j - rho_j y_j.r
+            k_axpby<<<LB_BLOCKS, LB_THREADS, 0, lb.st>>>(dir, S + (size_t)j * ns, lb.n4, tmp, 1.0, 1.0); // r += (alpha_j - beta) s_j
         }
         double gd;                                                 // directional derivative of -dir
         lb.dot(g, dir, tmp);
@@ -209,9 +223,9 @@ extern "C" int ntn_lbfgs_minimize(ntn_handle* h, float* d_theta, const ntn_lbfgs
         // ---- curvature pair s = trial - theta, y = gnew - g
         {
             int j = head;
-            k_diff<<<LB_BLOCKS, LB_THREADS, 0, lb.st>>>(S + (size_t)j * n, trial, d_theta, lb.n4);
-            k_diff<<<LB_BLOCKS, LB_THREADS, 0, lb.st>>>(Y + (size_t)j * n, gnew, g, lb.n4);
-            lb.dot(S + (size_t)j * n, Y + (size_t)j * n, rho + j, 3);                                   // rho_j = 1 / y.s
+            k_diff<<<LB_BLOCKS, LB_THREADS, 0, lb.st>>>(S + (size_t)j * ns, trial, d_theta, lb.n4);
+            k_diff<<<LB_BLOCKS, LB_THREADS, 0, lb.st>>>(Y + (size_t)j * ns, gnew, g, lb.n4);
+            lb.dot(S + (size_t)j * ns, Y + (size_t)j * ns, rho + j, 3);                                   // rho_j = 1 / y.s
             double rj = lb.fetch(rho + j);
             if (rj > 0 && isfinite(rj)) { head = (head + 1) % m; if (hist < m) ++hist; }              // skip pairs with y.s <= 0
         }
@@ -223,6 +237,7 @@ extern "C" int ntn_lbfgs_minimize(ntn_handle* h, float* d_theta, const ntn_lbfgs
     }
 done:
     cudaStreamSynchronize(lb.st);
+    if (h->grad_tail != saved_tail) ntn_set_grad_tail(h, saved_tail);
     res->min_obj_val = f; res->iters = iters; res->evals = evals; res->did_converge = converged ? 1 : 0;
     res->n_active_last = nact;
     return rc;

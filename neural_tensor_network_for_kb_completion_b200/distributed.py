@@ -149,3 +149,31 @@ class GradientExchange:
 
     def all_reduce(self, t):
         self._ops()[self.variant](t)
+
+
+def device_view(ptr: int, n: int, device):
+    """torch float32 view of n device floats at ``ptr`` (memory owned by the library)."""
+    import torch
+
+    class _Buf:
+        pass
+    b = _Buf()
+    b.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2, "strides": None}
+    return torch.as_tensor(b, device=device)
+
+
+def make_lbfgs_reduce(exchange: GradientExchange, device, stream):
+    """reduce(ptr, n) for Handle.lbfgs_minimize.  ``stream`` is the torch stream the handle was bound to with
+    Handle.set_stream, so the copies and the collective are ordered after the evaluation that produced the gradient
+    and before the optimiser's next kernel.  The library-owned gradient is copied into the exchange buffer (symmetric
+    memory when available), all-reduced with the autotuned variant, and copied back."""
+    import torch
+
+    def reduce(ptr, n):
+        with torch.cuda.stream(stream):
+            g = device_view(ptr, n, device)
+            buf = exchange.buffers[0]
+            buf[:n].copy_(g)
+            exchange.all_reduce(buf)
+            g.copy_(buf[:n])
+    return reduce

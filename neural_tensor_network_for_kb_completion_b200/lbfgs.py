@@ -30,8 +30,10 @@ class Result:
 class LBFGSMinimizer:
     Opts = Opts
 
-    def minimize(self, fn, theta, opts: Opts | None = None) -> Result:
-        """fn: the NTN function object (neural_tensor_network_for_kb_completion_b200.ntn.NTN)."""
+    def minimize(self, fn, theta, opts: Opts | None = None, reduce=None) -> Result:
+        """fn: the NTN function object (neural_tensor_network_for_kb_completion_b200.ntn.NTN).  Data parallel: ``reduce``
+        (distributed.make_lbfgs_reduce) all-reduces every evaluation's gradient + {cost, n_active} tail, so the replicated
+        optimisers of all ranks take identical steps."""
         import torch
         opts = opts or Opts()
         fn._sync_batch()
@@ -45,7 +47,8 @@ class LBFGSMinimizer:
         d_theta = cache[0]
         if cache[1] is None or cache[1] is not theta:
             h.upload_theta(np.asarray(theta, np.float64), d_theta.data_ptr())
-        r = h.lbfgs_minimize(d_theta.data_ptr(), fn.drawCorruptSides, opts.maxIters, opts.maxHistorySize, opts.tol)
+        r = h.lbfgs_minimize(d_theta.data_ptr(), fn.drawCorruptSides, opts.maxIters, opts.maxHistorySize, opts.tol,
+                             reduce=reduce)
         fn.update += int(r.n_active_last)
         out = h.download_theta(d_theta.data_ptr())
         cache[1] = out

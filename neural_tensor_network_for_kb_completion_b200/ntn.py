@@ -48,6 +48,7 @@ class NTN:
         assert self.dimension_for_minimizer == self.handle.P
         self._batch_id = None
         self.last_corrupt_side = None
+        self.global_relations = None     # data parallel: relation ids of the GLOBAL batch job (see drawCorruptSides)
 
     # ---- DataFactory hand-off ----------------------------------------------------------------
     def connectDatafactory(self, tbj):
@@ -68,8 +69,10 @@ class NTN:
             self._batch_id = bj
 
     def drawCorruptSides(self):
-        """One Math.random() > 0.5 per non-empty relation, increasing r (NTN.java:120,146)."""
-        rel = self.tbj.batchjob[1]
+        """One Math.random() > 0.5 per non-empty relation, increasing r (NTN.java:120,146).  A data-parallel rank holds
+        a shard that may miss a rare relation: ``global_relations`` (the global batch job's relation column) keeps the
+        number of draws -- hence the seeded stream -- identical on every rank."""
+        rel = self.tbj.batchjob[1] if self.global_relations is None else self.global_relations
         present = np.zeros(self.numberOfRelations, bool)
         present[np.unique(rel)] = True
         side = np.zeros(self.numberOfRelations, np.uint8)
