@@ -206,6 +206,11 @@ int ntn_host_entity_word_maps(const char* names, const char* words, int32_t* fwd
 int ntn_host_generate_batch(const int32_t* train, int64_t ntrain, int32_t batch, int32_t corrupt, int32_t num_entities,
                             int64_t seed, int32_t calls, int32_t* e1, int32_t* rel, int32_t* e2, int32_t* e3);
 
+/* The staging conversions of the host-buffer entry points (double[] theta -> float, float gradient -> double[];
+ * Util.java:49-55 rounding), exposed so that the CPU tests can check them on unaligned and ragged ranges. */
+int ntn_host_convert_f64_f32(const double* src, float* dst, int64_t n);
+int ntn_host_convert_f32_f64(const float* src, double* dst, int64_t n);
+
 const char* ntn_version(void);
 
 #ifdef __cplusplus

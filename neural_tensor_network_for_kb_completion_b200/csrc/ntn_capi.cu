@@ -312,6 +312,7 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
         return rc;
     CK(cudaStreamSynchronize(h->stream));     // host vectors go out of scope
     w.set = true;
+    h->E_frozen_valid = false;
     return NTN_OK;
 }
 
@@ -324,6 +325,7 @@ extern "C" int ntn_set_frozen_wv(ntn_handle* h, const float* wv) {
     float* tmp = nullptr;
     size_t n = (size_t)dm.d * dm.Nw;
     CK(cudaMalloc((void**)&tmp, n * sizeof(float)));
+    h->E_frozen_valid = false;
     int rc = dev_alloc(h, &h->wv_frozen, (size_t)dm.Nw * dm.dq);
     if (rc) { cudaFree(tmp); return rc; }
     cudaError_t e = cudaMemcpyAsync(tmp, wv, n * sizeof(float), cudaMemcpyHostToDevice, h->stream);
@@ -486,7 +488,9 @@ static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_gr
     if (tc) { if ((rc = ntn_tc_w_prep(h, d_theta, s1))) return rc; } else ntn_launch_w_prep(h, d_theta, s1);
     end(P_WP, s1);
     CK(cudaEventRecord(h->ev_j0, s1));
-    begin(P_EB, s0); ntn_launch_entity_build(h, wvt); end(P_EB, s0);                         // NTN.java:103
+    // NTN.java:103 rebuilds the entity vectors on every call; from frozen word vectors the result never changes, so
+    // it is built once (eval_internal) and only the theta-sourced variant pays for it per evaluation
+    begin(P_EB, s0); if (h->cfg.wv_source != NTN_WV_FROZEN) ntn_launch_entity_build(h, wvt); end(P_EB, s0);
     CK(cudaStreamWaitEvent(s0, h->ev_j0, 0));
     begin(P_FWD, s0);
     if (tc) { if ((rc = ntn_tc_gemm_fwd(h))) return rc; } else ntn_launch_gemm_fwd_simt(h);   // :163-197
@@ -541,6 +545,10 @@ static int eval_internal(ntn_handle* h, const float* d_theta, const uint8_t* cor
     CK(cudaMemcpyAsync(h->side, hs, dm.R, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->side_ev[slot], h->stream));
     int rc;
+    if (h->cfg.wv_source == NTN_WV_FROZEN && !h->E_frozen_valid) {
+        ntn_launch_entity_build(h, wvt);
+        h->E_frozen_valid = true;
+    }
     if (prof || !h->use_graph || h->stream == nullptr /* legacy default stream cannot be captured */) {
         h->launches = 0;
         if ((rc = enqueue_eval_kernels(h, d_theta, d_grad, wvt, prof, slot))) return rc;
@@ -628,23 +636,27 @@ extern "C" int ntn_from_internal_dev(ntn_handle* h, const float* d_int, float* d
 
 // host <-> pinned staging with type conversion.  The arrays are ~57 MB; conversion runs on an OpenMP pool and is
 // pipelined against the PCIe copies in NTN_XFER_CHUNK-element chunks (convert chunk i+1 while chunk i is in flight).
-#define NTN_XFER_CHUNK (1 << 21)
-// torchrun exports OMP_NUM_THREADS=1 to every rank; the staging loops size their own team: the host cores divided
-// among the ranks of this box (LOCAL_WORLD_SIZE), at most 16.
-static int convert_threads() {
-    static int nt = [] {
-        unsigned hw = std::thread::hardware_concurrency();
-        const char* lws = getenv("LOCAL_WORLD_SIZE");
-        int ranks = lws ? std::max(1, atoi(lws)) : 1;
-        return (int)std::max(1u, std::min(16u, (hw ? hw : 1u) / (unsigned)ranks));
+static int64_t xfer_chunk() {
+    static int64_t c = [] {
+        const char* e = getenv("NTN_XFER_CHUNK_LOG2");
+        int l = e ? atoi(e) : 21;
+        return (int64_t)1 << std::min(24, std::max(16, l));
     }();
-    return nt;
+    return c;
 }
-template <typename S, typename D> static void convert_range(const S* src, D* dst, int64_t n) {
-#pragma omp parallel for schedule(static) num_threads(convert_threads())
-    for (int64_t i = 0; i < n; ++i) dst[i] = (D)src[i];          // double -> float rounds like Util.java:49-55
-}
+#define NTN_XFER_CHUNK xfer_chunk()
+#include "host/convert.hpp"
 template <typename S, typename D> static void convert_parallel(const S* src, D* dst, int64_t n) { convert_range(src, dst, n); }
+extern "C" int ntn_host_convert_f64_f32(const double* src, float* dst, int64_t n) {
+    if ((!src || !dst) && n > 0) return NTN_EINVAL;
+    convert_range(src, dst, n);
+    return NTN_OK;
+}
+extern "C" int ntn_host_convert_f32_f64(const float* src, double* dst, int64_t n) {
+    if ((!src || !dst) && n > 0) return NTN_EINVAL;
+    convert_range(src, dst, n);
+    return NTN_OK;
+}
 
 // theta (host, S) -> pinned float staging -> device, chunk-pipelined
 template <typename S> static cudaError_t upload_pipelined(ntn_handle* h, const S* src, float* d_dst, int64_t n) {

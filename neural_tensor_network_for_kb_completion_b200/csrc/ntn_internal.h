@@ -104,6 +104,7 @@ struct ntn_handle {
     DeviceWords w;
     DeviceBatch b;
     float *wv_frozen = nullptr;   // Nw x dq (internal word-major), or null
+    bool E_frozen_valid = false;  // NTN_WV_FROZEN: E was built from wv_frozen and is reused (invariant across evaluations)
     float *E = nullptr;           // Ne x Kp
     float *gE = nullptr;          // Ne x dq
     float *Waug = nullptr;        // R x Kp x Np   (row p, column n)

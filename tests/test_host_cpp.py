@@ -69,3 +69,24 @@ def test_cpp_batch_job_matches_oracle_across_consecutive_jobs(lib):
         want = data_ref.generate_batch_job(train[:, 0], train[:, 1], train[:, 2], B, Cc, kb.Ne, r)
     for a, b in zip(out, want):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 17, 4096, 4099, 70001, 300007])
+@pytest.mark.parametrize("shift", [0, 1, 3])
+def test_staging_conversions_on_ragged_unaligned_ranges(n, shift):
+    """double[] theta -> float staging and float gradient -> double[] (Util.java:49-55 rounding): the threaded,
+    non-temporal-store loops must equal the plain casts for every length and destination alignment."""
+    lib = _capi.load()
+    rng = np.random.default_rng(n + shift)
+    src64 = np.empty(n + shift + 8, np.float64)[shift:shift + n]
+    src64[:] = rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, size=n)
+    dst32 = np.full(n + shift + 8, np.float32(7.0))
+    assert lib.ntn_host_convert_f64_f32(src64.ctypes.data, dst32[shift:].ctypes.data, n) == 0
+    with np.errstate(over="ignore"):
+        np.testing.assert_array_equal(dst32[shift:shift + n], src64.astype(np.float32))
+    assert np.all(dst32[:shift] == 7.0) and np.all(dst32[shift + n:] == 7.0)
+    src32 = dst32[shift:shift + n].copy()
+    dst64 = np.full(n + shift + 8, 7.0)
+    assert lib.ntn_host_convert_f32_f64(src32.ctypes.data, dst64[shift:].ctypes.data, n) == 0
+    np.testing.assert_array_equal(dst64[shift:shift + n], src32.astype(np.float64))
+    assert np.all(dst64[:shift] == 7.0) and np.all(dst64[shift + n:] == 7.0)
