@@ -101,6 +101,11 @@ int ntn_set_frozen_wv(ntn_handle* h, const float* wv /* d*Nw */);
  * summation order. */
 int ntn_set_batch(ntn_handle* h, int64_t n,
                   const int32_t* e1, const int32_t* rel, const int32_t* e2, const int32_t* e3);
+/* The same with the columns already in device memory (e.g. corrupt entities sampled on the GPU).  The per-relation
+ * grouping the reference redoes on every evaluation (DataFactory.getBatchJobTripplesOfRelation, DataFactory.java:89-98;
+ * index vectors :614-645) is done here once per batch job, on the device; the arrays may be released on return. */
+int ntn_set_batch_dev(ntn_handle* h, int64_t n,
+                      const int32_t* d_e1, const int32_t* d_rel, const int32_t* d_e2, const int32_t* d_e3);
 
 /* ---- the hot path --------------------------------------------------------------------- */
 /* computeAt (NTN.java:92-443).  theta and grad are host arrays of P doubles in the reference's

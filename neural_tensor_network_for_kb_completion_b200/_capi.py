@@ -61,6 +61,7 @@ SYMBOLS = {
     "ntn_set_entity_words": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ntn_set_frozen_wv": (C.c_int, [_P, _P]),
     "ntn_set_batch": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
+    "ntn_set_batch_dev": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     "ntn_eval": (C.c_int, [_P, _P, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int64)]),
     "ntn_eval_f32": (C.c_int, [_P, _P, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int64)]),
     "ntn_eval_dev": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -169,6 +170,10 @@ class Handle:
         e1, rel, e2, e3 = _i32(e1), _i32(rel), _i32(e2), _i32(e3)
         assert len(e1) == len(rel) == len(e2) == len(e3)
         self._ck(self.lib.ntn_set_batch(self.h, len(e1), _ptr(e1), _ptr(rel), _ptr(e2), _ptr(e3)))
+
+    def set_batch_dev(self, n: int, d_e1: int, d_rel: int, d_e2: int, d_e3: int):
+        """The batch columns as int32 device pointers (e.g. torch tensors' data_ptr())."""
+        self._ck(self.lib.ntn_set_batch_dev(self.h, int(n), d_e1, d_rel, d_e2, d_e3))
 
     # ---- hot path ----
     def _side(self, corrupt_side):
@@ -282,7 +287,7 @@ class Handle:
             raise KeyError(name)
         out = np.empty(n, np.float32)
         self.lib.ntn_debug_fetch(self.h, name.encode(), _ptr(out), n)
-        return out
+        return out.view(np.int32) if name.startswith("i:") else out
 
     # ---- introspection ----
     @property

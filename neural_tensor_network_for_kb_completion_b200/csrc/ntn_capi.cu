@@ -1,6 +1,7 @@
 // C-ABI entry points (include/ntn_b200.h): handle lifetime, DataFactory state upload and batch
 // indexing, and the evaluation driver that strings the kernels together.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -180,6 +181,10 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     dev_free(h->reg_part); dev_free(h->d_out); dev_free(h->d_ref_theta); dev_free(h->d_ref_grad);
     dev_free(h->d_int_theta); dev_free(h->d_int_grad);
     if (h->lbfgs_ws) cudaFree(h->lbfgs_ws);
+    if (h->bi_ws) cudaFree(h->bi_ws);
+    if (h->h_meta) cudaFreeHost(h->h_meta);
+    if (h->h_cols) cudaFreeHost(h->h_cols);
+    if (h->d_cols) cudaFree(h->d_cols);
     if (h->h_side) cudaFreeHost(h->h_side);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -335,61 +340,12 @@ extern "C" int ntn_set_frozen_wv(ntn_handle* h, const float* wv) {
     return NTN_OK;
 }
 
-extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const int32_t* rel, const int32_t* e2,
-                             const int32_t* e3) {
-    if (!h) return NTN_EINVAL;
-    if (n < 0 || (n > 0 && (!e1 || !rel || !e2 || !e3))) FAIL(NTN_EINVAL, "null argument");
-    if (n > (int64_t)1 << 30) FAIL(NTN_EUNSUP, "batch too large");
-    CK(cudaSetDevice(h->device));
+// Tile / chunk tables from the per-relation unique-triple counts, per-evaluation intermediates, contraction path.
+// The unique-triple tables, the incident CSR and the hub segments are already in h->b (device- or host-built).
+static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>& rel_count, int n_hub_segs) {
     const NtnDims& dm = h->dm;
-    for (int64_t j = 0; j < n; ++j) {
-        if (e1[j] < 0 || e1[j] >= dm.Ne || e2[j] < 0 || e2[j] >= dm.Ne || e3[j] < 0 || e3[j] >= dm.Ne)
-            FAIL(NTN_EINVAL, "entity index out of range in column " + std::to_string(j));
-        if (rel[j] < 0 || rel[j] >= dm.R) FAIL(NTN_EINVAL, "relation index out of range in column " + std::to_string(j));
-    }
-    // group the columns by (rel, e1, e2): the C corrupt copies of one training triple
-    // (DataFactory.java:123-129) become one unique triple with a list of e3.
-    // Stable LSD radix sort of the column ids by the packed key (rel, e1, e2): O(n) per 16-bit digit, and stability
-    // keeps a triple's corrupt copies in batch order (the old comparison sort cost 15 ms at 200k columns).
-    std::vector<int> order((size_t)n);
-    std::iota(order.begin(), order.end(), 0);
-    {
-        int eb = 1; while ((1 << eb) < dm.Ne) ++eb;
-        int rb = 1; while ((1 << rb) < dm.R) ++rb;
-        if (2 * eb + rb <= 64) {
-            std::vector<uint64_t> key((size_t)n), key2((size_t)n);
-            std::vector<int> order2((size_t)n);
-            for (int64_t j = 0; j < n; ++j) key[j] = ((uint64_t)rel[j] << (2 * eb)) | ((uint64_t)e1[j] << eb) | (uint64_t)e2[j];
-            for (int shift = 0; shift < 2 * eb + rb; shift += 16) {
-                size_t cnt[65537] = {0};
-                for (int64_t i = 0; i < n; ++i) cnt[((key[i] >> shift) & 0xffff) + 1]++;
-                for (int b2 = 0; b2 < 65536; ++b2) cnt[b2 + 1] += cnt[b2];
-                for (int64_t i = 0; i < n; ++i) { size_t p2 = cnt[(key[i] >> shift) & 0xffff]++; key2[p2] = key[i]; order2[p2] = order[i]; }
-                key.swap(key2); order.swap(order2);
-            }
-        } else {
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-                if (rel[a] != rel[b]) return rel[a] < rel[b];
-                if (e1[a] != e1[b]) return e1[a] < e1[b];
-                return e2[a] < e2[b];
-            });
-        }
-    }
-    std::vector<int> u_e1, u_e2, u_rel, c_off, c_e3((size_t)n), col_u((size_t)n);
-    for (int64_t i = 0; i < n; ++i) {
-        int j = order[i];
-        if (i == 0 || rel[j] != u_rel.back() || e1[j] != u_e1.back() || e2[j] != u_e2.back()) {
-            u_e1.push_back(e1[j]); u_e2.push_back(e2[j]); u_rel.push_back(rel[j]);
-            c_off.push_back((int)i);
-        }
-        c_e3[i] = e3[j];
-        col_u[i] = (int)u_e1.size() - 1;
-    }
-    c_off.push_back((int)n);
-    int Nu = (int)u_e1.size();
     std::vector<int> rel_off(dm.R + 1, 0);
-    for (int u = 0; u < Nu; ++u) rel_off[u_rel[u] + 1]++;
-    for (int r = 0; r < dm.R; ++r) rel_off[r + 1] += rel_off[r];
+    for (int r = 0; r < dm.R; ++r) rel_off[r + 1] = rel_off[r] + rel_count[r];
     std::vector<int> t_rel, t_u0, t_n, ch_rel, ch_u0, ch_n, relch_off(dm.R + 1, 0), reltile_off(dm.R + 1, 0);
     std::vector<int> st_rel, st_u0, st_n, rels_off(dm.R + 1, 0);
     // split-K chunk of the dW contraction: about two chunks per SM (every chunk costs a Kp x Np partial that the
@@ -409,6 +365,88 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
         reltile_off[r + 1] = (int)t_rel.size();
         relch_off[r + 1] = (int)ch_rel.size();
     }
+    // entity-gradient pull variant: while T' (Nu x Np floats) stays L2-resident every incident re-reads its k T' rows;
+    // beyond that k_score materialises one contribution row per incident (measured: C3 0.256 vs 0.278 ms with rows,
+    // C4 2.89 vs 2.42 ms).  NTN_GV=0/1 overrides.
+    bool use_gv = (size_t)Nu * dm.Np * sizeof(float) > ((size_t)48 << 20);
+    if (const char* e = getenv("NTN_GV")) use_gv = e[0] == '1';
+    DeviceBatch& b = h->b;
+    b.N = n; b.Nu = Nu; b.ntiles = (int)t_rel.size(); b.nchunks = (int)ch_rel.size(); b.n_inc = 2 * Nu + (int)n;
+    b.nstiles = (int)st_rel.size();
+    b.use_gv = use_gv;
+    b.n_ent_hub_segs = n_hub_segs;
+    int rc;
+    if ((rc = dev_upload(h, &b.t_rel, t_rel)) || (rc = dev_upload(h, &b.t_u0, t_u0)) || (rc = dev_upload(h, &b.t_n, t_n)) ||
+        (rc = dev_upload(h, &b.st_rel, st_rel)) || (rc = dev_upload(h, &b.st_u0, st_u0)) || (rc = dev_upload(h, &b.st_n, st_n)) ||
+        (rc = dev_upload(h, &b.rels_off, rels_off)) ||
+        (rc = dev_upload(h, &b.ch_rel, ch_rel)) || (rc = dev_upload(h, &b.ch_u0, ch_u0)) || (rc = dev_upload(h, &b.ch_n, ch_n)) ||
+        (rc = dev_upload(h, &b.relch_off, relch_off)) || (rc = dev_upload(h, &b.reltile_off, reltile_off)) ||
+        (rc = dev_alloc(h, &b.T, (size_t)Nu * dm.Np)) || (rc = dev_alloc(h, &b.M, (size_t)Nu * dm.Np)) ||
+        (rc = dev_alloc(h, &b.GA, (size_t)Nu * dm.Kp)) || (rc = dev_alloc(h, &b.GV, use_gv ? ((size_t)Nu + (size_t)n) * dm.dq : 1)) || (rc = dev_alloc(h, &b.acoef, ((size_t)Nu + (size_t)n) * dm.k)) ||
+        (rc = dev_alloc(h, &b.dWpart, (size_t)b.nchunks * dm.Kp * dm.Np)) ||
+        (rc = dev_alloc(h, &b.tp_cost, (size_t)b.nstiles)) || (rc = dev_alloc(h, &b.tp_nact, (size_t)b.nstiles)) ||
+        (rc = dev_alloc(h, &b.tp_dU, (size_t)b.nstiles * dm.k)) ||
+        (rc = dev_alloc(h, &b.eh_part, (size_t)b.n_ent_hub_segs * dm.dq)))
+        return rc;
+    b.ccoef = b.acoef + (size_t)Nu * dm.k;
+    CK(cudaStreamSynchronize(h->stream));            // the small tables above come from host vectors that die here
+    // contraction path for this batch
+    h->gemm_path_active = NTN_GEMM_SIMT;
+    if (h->cfg.gemm_path != NTN_GEMM_SIMT) {
+        if (ntn_tc_supported(h)) {
+            rc = ntn_tc_prepare_batch(h);
+            if (rc) return rc;
+            h->gemm_path_active = NTN_GEMM_TCGEN05;
+        } else if (h->cfg.gemm_path == NTN_GEMM_TCGEN05) {
+            FAIL(NTN_EUNSUP, "tcgen05 contraction path does not support this shape");
+        }
+    }
+    return NTN_OK;
+}
+
+// Host builder of the batch tables: the same tables batch_index.cu builds on the device, element for element.  Kept as
+// the cross-check of the device builder (NTN_SET_BATCH_HOST=1, tests/test_gpu_parity.py); not the default.
+static int set_batch_host_tables(ntn_handle* h, int64_t n, const int32_t* e1, const int32_t* rel, const int32_t* e2,
+                                 const int32_t* e3) {
+    const NtnDims& dm = h->dm;
+    for (int64_t j = 0; j < n; ++j) {
+        if (e1[j] < 0 || e1[j] >= dm.Ne || e2[j] < 0 || e2[j] >= dm.Ne || e3[j] < 0 || e3[j] >= dm.Ne || rel[j] < 0 || rel[j] >= dm.R)
+            FAIL(NTN_EINVAL, "entity or relation index out of range in column " + std::to_string(j));
+    }
+    // stable LSD radix sort of the column ids by the packed key (rel, e1, e2): stability keeps a triple's corrupt
+    // copies in batch order
+    std::vector<int> order((size_t)n);
+    std::iota(order.begin(), order.end(), 0);
+    {
+        int eb = 1; while ((1 << eb) < dm.Ne) ++eb;
+        int rb = 1; while ((1 << rb) < dm.R) ++rb;
+        if (2 * eb + rb > 63) FAIL(NTN_EUNSUP, "key (rel, e1, e2) does not fit 63 bits");
+        std::vector<uint64_t> key((size_t)n), key2((size_t)n);
+        std::vector<int> order2((size_t)n);
+        for (int64_t j = 0; j < n; ++j) key[j] = ((uint64_t)rel[j] << (2 * eb)) | ((uint64_t)e1[j] << eb) | (uint64_t)e2[j];
+        std::vector<size_t> cnt(2049);
+        for (int shift = 0; shift < 2 * eb + rb; shift += 11) {
+            std::fill(cnt.begin(), cnt.end(), 0);
+            for (int64_t i = 0; i < n; ++i) cnt[((key[i] >> shift) & 0x7ff) + 1]++;
+            for (int b2 = 0; b2 < 2048; ++b2) cnt[b2 + 1] += cnt[b2];
+            for (int64_t i = 0; i < n; ++i) { size_t p2 = cnt[(key[i] >> shift) & 0x7ff]++; key2[p2] = key[i]; order2[p2] = order[i]; }
+            key.swap(key2); order.swap(order2);
+        }
+    }
+    std::vector<int> u_e1, u_e2, u_rel, c_off, c_e3((size_t)n), col_u((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        int j = order[i];
+        if (i == 0 || rel[j] != u_rel.back() || e1[j] != u_e1.back() || e2[j] != u_e2.back()) {
+            u_e1.push_back(e1[j]); u_e2.push_back(e2[j]); u_rel.push_back(rel[j]);
+            c_off.push_back((int)i);
+        }
+        c_e3[i] = e3[j];
+        col_u[i] = (int)u_e1.size() - 1;
+    }
+    c_off.push_back((int)n);
+    int Nu = (int)u_e1.size();
+    std::vector<int> rel_count(dm.R, 0);
+    for (int u = 0; u < Nu; ++u) rel_count[u_rel[u]]++;
     // entity -> incidents: (e1 role, e2 role, corrupt columns), stable counting sort by entity
     int n_inc = 2 * Nu + (int)n;
     std::vector<int> inc_off(dm.Ne + 1, 0);
@@ -424,52 +462,60 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
     }
     std::vector<int> sr, sb, se, first, count;
     build_hub_segments(inc_off, dm.Ne, sr, sb, se, first, count);
-
-    CK(cudaStreamSynchronize(h->stream));
-    ntn_drop_graphs(h);                     // graphs bake buffer pointers and grid sizes; device buffers are reused when large enough
-    // entity-gradient pull variant: while T' (Nu x Np floats) stays L2-resident every incident re-reads its k T' rows;
-    // beyond that k_score materialises one contribution row per incident (measured: C3 0.256 vs 0.278 ms with rows,
-    // C4 2.89 vs 2.42 ms).  NTN_GV=0/1 overrides.
-    bool use_gv = (size_t)Nu * dm.Np * sizeof(float) > ((size_t)48 << 20);
-    if (const char* e = getenv("NTN_GV")) use_gv = e[0] == '1';
     DeviceBatch& b = h->b;
-    b.N = n; b.Nu = Nu; b.ntiles = (int)t_rel.size(); b.nchunks = (int)ch_rel.size(); b.n_inc = n_inc;
-    b.nstiles = (int)st_rel.size();
-    b.use_gv = use_gv;
-    b.n_ent_hub_segs = (int)sr.size();
     int rc;
     if ((rc = dev_upload(h, &b.u_e1, u_e1)) || (rc = dev_upload(h, &b.u_e2, u_e2)) || (rc = dev_upload(h, &b.u_rel, u_rel)) ||
         (rc = dev_upload(h, &b.c_off, c_off)) || (rc = dev_upload(h, &b.c_e3, c_e3)) ||
-        (rc = dev_upload(h, &b.t_rel, t_rel)) || (rc = dev_upload(h, &b.t_u0, t_u0)) || (rc = dev_upload(h, &b.t_n, t_n)) ||
-        (rc = dev_upload(h, &b.st_rel, st_rel)) || (rc = dev_upload(h, &b.st_u0, st_u0)) || (rc = dev_upload(h, &b.st_n, st_n)) ||
-        (rc = dev_upload(h, &b.rels_off, rels_off)) ||
-        (rc = dev_upload(h, &b.ch_rel, ch_rel)) || (rc = dev_upload(h, &b.ch_u0, ch_u0)) || (rc = dev_upload(h, &b.ch_n, ch_n)) ||
-        (rc = dev_upload(h, &b.relch_off, relch_off)) || (rc = dev_upload(h, &b.reltile_off, reltile_off)) ||
         (rc = dev_upload(h, &b.inc_off, inc_off)) || (rc = dev_upload(h, &b.inc, inc)) ||
-        (rc = dev_upload(h, &b.eh_ent, sr)) ||
-        (rc = dev_upload(h, &b.eh_begin, sb)) || (rc = dev_upload(h, &b.eh_end, se)) ||
-        (rc = dev_upload(h, &b.eh_first, first)) || (rc = dev_upload(h, &b.eh_count, count)) ||
-        (rc = dev_alloc(h, &b.T, (size_t)Nu * dm.Np)) || (rc = dev_alloc(h, &b.M, (size_t)Nu * dm.Np)) ||
-        (rc = dev_alloc(h, &b.GA, (size_t)Nu * dm.Kp)) || (rc = dev_alloc(h, &b.GV, use_gv ? ((size_t)Nu + (size_t)n) * dm.dq : 1)) || (rc = dev_alloc(h, &b.acoef, ((size_t)Nu + (size_t)n) * dm.k)) ||
-        (rc = dev_alloc(h, &b.dWpart, (size_t)b.nchunks * dm.Kp * dm.Np)) ||
-        (rc = dev_alloc(h, &b.tp_cost, (size_t)b.nstiles)) || (rc = dev_alloc(h, &b.tp_nact, (size_t)b.nstiles)) ||
-        (rc = dev_alloc(h, &b.tp_dU, (size_t)b.nstiles * dm.k)) ||
-        (rc = dev_alloc(h, &b.eh_part, (size_t)b.n_ent_hub_segs * dm.dq)))
+        (rc = dev_upload(h, &b.eh_ent, sr)) || (rc = dev_upload(h, &b.eh_begin, sb)) || (rc = dev_upload(h, &b.eh_end, se)) ||
+        (rc = dev_upload(h, &b.eh_first, first)) || (rc = dev_upload(h, &b.eh_count, count)))
         return rc;
-    b.ccoef = b.acoef + (size_t)Nu * dm.k;
     CK(cudaStreamSynchronize(h->stream));
-    // contraction path for this batch
-    h->gemm_path_active = NTN_GEMM_SIMT;
-    if (h->cfg.gemm_path != NTN_GEMM_SIMT) {
-        if (ntn_tc_supported(h)) {
-            rc = ntn_tc_prepare_batch(h);
-            if (rc) return rc;
-            h->gemm_path_active = NTN_GEMM_TCGEN05;
-        } else if (h->cfg.gemm_path == NTN_GEMM_TCGEN05) {
-            FAIL(NTN_EUNSUP, "tcgen05 contraction path does not support this shape");
-        }
+    return finish_batch(h, n, Nu, rel_count, (int)sr.size());
+}
+
+static int set_batch_dev_columns(ntn_handle* h, int64_t n, const int* d_e1, const int* d_rel, const int* d_e2, const int* d_e3) {
+    std::vector<int> rel_count(h->dm.R, 0);
+    int counts[2] = {0, 0};
+    int rc = ntn_index_batch_dev(h, n, d_e1, d_rel, d_e2, d_e3, counts, rel_count.data());
+    if (rc) return rc;
+    return finish_batch(h, n, counts[0], rel_count, counts[1]);
+}
+
+extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const int32_t* rel, const int32_t* e2,
+                             const int32_t* e3) {
+    if (!h) return NTN_EINVAL;
+    if (n < 0 || (n > 0 && (!e1 || !rel || !e2 || !e3))) FAIL(NTN_EINVAL, "null argument");
+    if (n > ((int64_t)1 << 30) / 3) FAIL(NTN_EUNSUP, "batch too large");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    ntn_drop_graphs(h);                     // graphs bake buffer pointers and grid sizes; device buffers are reused when large enough
+    if (getenv("NTN_SET_BATCH_HOST")) return set_batch_host_tables(h, n, e1, rel, e2, e3);
+    // columns -> pinned staging -> device; everything else happens there (batch_index.cu)
+    if (h->cols_cap < (size_t)n || !h->h_cols) {
+        if (h->h_cols) cudaFreeHost(h->h_cols);
+        if (h->d_cols) cudaFree(h->d_cols);
+        h->h_cols = nullptr; h->d_cols = nullptr; h->cols_cap = 0;
+        const size_t cap = std::max<size_t>((size_t)n, 1);
+        CK(cudaMallocHost((void**)&h->h_cols, 4 * cap * sizeof(int)));
+        CK(cudaMalloc((void**)&h->d_cols, 4 * cap * sizeof(int)));
+        h->cols_cap = cap;
     }
-    return NTN_OK;
+    const int32_t* src[4] = {e1, rel, e2, e3};
+    for (int c = 0; c < 4 && n > 0; ++c) memcpy(h->h_cols + (size_t)c * n, src[c], (size_t)n * sizeof(int));
+    if (n > 0) CK(cudaMemcpyAsync(h->d_cols, h->h_cols, 4 * (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    return set_batch_dev_columns(h, n, h->d_cols, h->d_cols + n, h->d_cols + 2 * n, h->d_cols + 3 * n);
+}
+
+extern "C" int ntn_set_batch_dev(ntn_handle* h, int64_t n, const int32_t* d_e1, const int32_t* d_rel, const int32_t* d_e2,
+                                 const int32_t* d_e3) {
+    if (!h) return NTN_EINVAL;
+    if (n < 0 || (n > 0 && (!d_e1 || !d_rel || !d_e2 || !d_e3))) FAIL(NTN_EINVAL, "null argument");
+    if (n > ((int64_t)1 << 30) / 3) FAIL(NTN_EUNSUP, "batch too large");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    ntn_drop_graphs(h);
+    return set_batch_dev_columns(h, n, d_e1, d_rel, d_e2, d_e3);
 }
 
 // Enqueue the kernels of one evaluation on h->stream with its forked branches (also what gets captured
@@ -639,7 +685,7 @@ extern "C" int ntn_from_internal_dev(ntn_handle* h, const float* d_int, float* d
 static int64_t xfer_chunk() {
     static int64_t c = [] {
         const char* e = getenv("NTN_XFER_CHUNK_LOG2");
-        int l = e ? atoi(e) : 21;
+        int l = e ? atoi(e) : 20;       // 4 MB of floats per chunk: measured best of 2^18..2^22 on the B200 host
         return (int64_t)1 << std::min(24, std::max(16, l));
     }();
     return c;
@@ -772,6 +818,25 @@ extern "C" int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, 
     else if (s == "E") { src = h->E; n = (int64_t)dm.Ne * dm.Kp; }
     else if (s == "gE") { src = h->gE; n = (int64_t)dm.Ne * dm.dq; }
     else if (s == "tc_timeline") return ntn_tc_fetch_timeline(h, out, cap);
+    else if (s.rfind("i:", 0) == 0) {
+        // integer batch tables, copied bit for bit (the caller views the buffer as int32)
+        const int* isrc = nullptr;
+        const std::string t = s.substr(2);
+        if (t == "u_e1") { isrc = b.u_e1; n = b.Nu; }
+        else if (t == "u_e2") { isrc = b.u_e2; n = b.Nu; }
+        else if (t == "u_rel") { isrc = b.u_rel; n = b.Nu; }
+        else if (t == "c_off") { isrc = b.c_off; n = b.Nu + 1; }
+        else if (t == "c_e3") { isrc = b.c_e3; n = b.N; }
+        else if (t == "inc_off") { isrc = b.inc_off; n = dm.Ne + 1; }
+        else if (t == "inc") { isrc = (const int*)b.inc; n = 4 * (int64_t)b.n_inc; }
+        else if (t == "eh_first") { isrc = b.eh_first; n = dm.Ne; }
+        else if (t == "eh_count") { isrc = b.eh_count; n = dm.Ne; }
+        else if (t == "eh_begin") { isrc = b.eh_begin; n = b.n_ent_hub_segs; }
+        else if (t == "eh_end") { isrc = b.eh_end; n = b.n_ent_hub_segs; }
+        else return -1;
+        if (out && cap >= n && n > 0) cudaMemcpy(out, isrc, n * sizeof(int), cudaMemcpyDeviceToHost);
+        return n;
+    }
     else return -1;
     if (out && cap >= n && n > 0) cudaMemcpy(out, src, n * sizeof(float), cudaMemcpyDeviceToHost);
     return n;

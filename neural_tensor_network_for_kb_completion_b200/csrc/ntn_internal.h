@@ -130,6 +130,12 @@ struct ntn_handle {
     double phase_acc[NTN_NUM_PHASES] = {};
     int phase_n = 0;
     void *tc = nullptr;           // tcgen05 path state (gemm_tcgen05.cu)
+    void *bi_ws = nullptr;        // batch-index workspace (batch_index.cu), grow-only
+    size_t bi_ws_bytes = 0;
+    int *h_meta = nullptr;        // pinned: counters read back by the batch index
+    int *h_cols = nullptr;        // pinned staging of the batch columns (ntn_set_batch with host pointers)
+    int *d_cols = nullptr;        // their device copy, 4 x n
+    size_t cols_cap = 0;
     void *lbfgs_ws = nullptr;     // L-BFGS workspace (lbfgs.cu), grow-only
     size_t lbfgs_ws_bytes = 0;
     // CUDA graphs of the evaluation, one per (theta, grad, stream) triple
@@ -138,6 +144,10 @@ struct ntn_handle {
     bool use_graph = true;
     bool grad_tail = false;       // the caller's gradient buffer has 4 extra floats for {cost, n_active}
 };
+
+// ---- batch indexing on the device (batch_index.cu)
+int ntn_index_batch_dev(ntn_handle* h, int64_t n, const int* d_e1, const int* d_rel, const int* d_e2, const int* d_e3,
+                        int* counts /* Nu, hub segments */, int* rel_count /* R */);
 
 // ---- kernel launchers (ntn_kernels.cu) ---------------------------------------------------
 void ntn_launch_entity_build(ntn_handle* h, const float* wvt);

@@ -48,6 +48,7 @@ class NTN:
         assert self.dimension_for_minimizer == self.handle.P
         self._batch_id = None
         self.last_corrupt_side = None
+        self._present_for, self._present = None, None
         self.global_relations = None     # data parallel: relation ids of the GLOBAL batch job (see drawCorruptSides)
 
     # ---- DataFactory hand-off ----------------------------------------------------------------
@@ -73,12 +74,12 @@ class NTN:
         a shard that may miss a rare relation: ``global_relations`` (the global batch job's relation column) keeps the
         number of draws -- hence the seeded stream -- identical on every rank."""
         rel = self.tbj.batchjob[1] if self.global_relations is None else self.global_relations
-        present = np.zeros(self.numberOfRelations, bool)
-        present[np.unique(rel)] = True
+        if self._present_for is not rel:                           # one pass per batch job, not per evaluation
+            self._present = np.bincount(np.asarray(rel), minlength=self.numberOfRelations)[:self.numberOfRelations] > 0
+            self._present_for = rel
         side = np.zeros(self.numberOfRelations, np.uint8)
-        for r in range(self.numberOfRelations):
-            if present[r]:
-                side[r] = 1 if self.side_rand.nextDouble() > 0.5 else 0
+        for r in np.nonzero(self._present)[0]:
+            side[r] = 1 if self.side_rand.nextDouble() > 0.5 else 0
         return side
 
     # ---- IDifferentiableFn (NTN.java:92-448) ----------------------------------------------------

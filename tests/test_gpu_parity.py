@@ -356,3 +356,75 @@ def test_device_lbfgs_matches_numpy_definition():
     # the returned argument really has the returned objective value
     assert ntn_ref.compute_at(res.minArg, p, *batch, side)[0] == pytest.approx(res.minObjVal, rel=1e-4)
     h.close()
+
+
+_TABLES = ("u_e1", "u_e2", "u_rel", "c_off", "c_e3", "inc_off", "inc", "eh_first", "eh_count", "eh_begin", "eh_end")
+
+
+def _ragged_batch(seed):
+    kb, p, batch, side, theta0 = small_problem(Ne=1200, R=6, T=900, Nw=60, d=16, batch=700, corrupt=3, seed=seed, oov_frac=0.4)
+    e1, rel, e2, e3 = (x.copy() for x in batch)
+    rel[rel == 2] = 0
+    e1[::7] = e1[0]; e2[::7] = e2[0]; rel[::7] = rel[0]
+    e3[::2] = 5
+    e1[1::3] = 9
+    keep = np.ones(len(e1), bool)
+    keep[5::11] = False
+    return kb, p, tuple(x[keep] for x in (e1, rel, e2, e3)), side, theta0
+
+
+@pytest.mark.parametrize("case", ["small", "ragged", "single_column", "one_relation", "wordnet_like"])
+def test_device_batch_index_equals_host_builder(case, monkeypatch):
+    """batch_index.cu (the default: stable radix sorts on the device) against the host builder kept for this purpose
+    (NTN_SET_BATCH_HOST=1): every integer table identical, hence bit-identical cost and gradient.  Replaces the
+    per-evaluation relation filtering of DataFactory.java:89-98 / :614-645."""
+    if case == "small":
+        kb, p, batch, side, theta0 = small_problem(seed=3)
+    elif case == "ragged":
+        kb, p, batch, side, theta0 = _ragged_batch(5)
+    elif case == "single_column":
+        kb, p, batch, side, theta0 = small_problem(seed=4)
+        batch = tuple(x[:1] for x in batch)
+    elif case == "one_relation":
+        kb, p, batch, side, theta0 = small_problem(Ne=300, R=1, T=400, Nw=100, d=8, batch=300, corrupt=4, seed=6)
+    else:
+        kb, p, batch, side, theta0 = small_problem(Ne=5000, R=11, T=6000, Nw=3000, d=20, batch=5000, corrupt=10, seed=8)
+    theta = f32(perturbed(theta0, 0.05))
+    out = {}
+    for mode in ("host", "device"):
+        if mode == "host":
+            monkeypatch.setenv("NTN_SET_BATCH_HOST", "1")
+        else:
+            monkeypatch.delenv("NTN_SET_BATCH_HOST", raising=False)
+        h = make_handle(p, "theta")
+        h.set_batch(*batch)
+        tables = {t: h.debug_fetch("i:" + t).copy() for t in _TABLES}
+        out[mode] = (tables, h.eval(theta, side))
+        h.close()
+    for t in _TABLES:
+        np.testing.assert_array_equal(out["host"][0][t], out["device"][0][t], err_msg=t)
+    (c_h, g_h, n_h), (c_d, g_d, n_d) = out["host"][1], out["device"][1]
+    assert c_h == c_d and n_h == n_d and np.array_equal(g_h, g_d)
+
+
+def test_set_batch_from_device_columns():
+    """ntn_set_batch_dev: the batch columns already live in HBM (torch tensors here)."""
+    import torch
+    kb, p, batch, side, theta0 = _ragged_batch(7)
+    theta = f32(perturbed(theta0, 0.05))
+    h = make_handle(p, "theta")
+    h.set_batch(*batch)
+    ref = h.eval(theta, side)
+    cols = [torch.from_numpy(np.ascontiguousarray(x, np.int32)).cuda() for x in batch]
+    torch.cuda.synchronize()
+    h2 = make_handle(p, "theta")
+    h2.set_batch_dev(len(batch[0]), *(c.data_ptr() for c in cols))
+    got = h2.eval(theta, side)
+    assert ref[0] == got[0] and ref[2] == got[2] and np.array_equal(ref[1], got[1])
+    # an out-of-range index is found on the device and reported with its column
+    cols[3][17] = p.Ne
+    torch.cuda.synchronize()
+    with pytest.raises(_capi.NTNError) as ei:
+        h2.set_batch_dev(len(batch[0]), *(c.data_ptr() for c in cols))
+    assert ei.value.code == _capi.NTN_EINVAL and "column 17" in str(ei.value)
+    h.close(); h2.close()
