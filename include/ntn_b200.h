@@ -107,6 +107,21 @@ int ntn_set_batch(ntn_handle* h, int64_t n,
 int ntn_set_batch_dev(ntn_handle* h, int64_t n,
                       const int32_t* d_e1, const int32_t* d_rel, const int32_t* d_e2, const int32_t* d_e3);
 
+/* ---- batch-job generation on the device (sampler variants of DataFactory.generateNewTrainingBatchJob) ------------
+ * The reference draws e3 = rand.nextInt(numOfentities) on the host, h-major, always from the first batch_size training
+ * triples (DataFactory.java:116-136; the shuffle is commented out at :118).  ntn_set_batch with a host-generated job
+ * (seeded java.util.Random, csrc/host/ntn_host.hpp) is the parity mode.  The calls below are the fast mode: the
+ * training triples live in HBM, column j = h*batch + i copies training triple first+i, and its corrupt entity is the
+ * counter-based draw  e3 = (mix(seed, job, j, attempt) >> 32) * Ne >> 32  (mix: a splitmix64-style finaliser, restated
+ * in oracle/data_ref.py) -- reproducible anywhere, no host round trip.  filter_true != 0 redraws (attempt = 1..15) while
+ * (e1, rel, e3) or (e3, rel, e2) is a known training triple.  The job is indexed like ntn_set_batch_dev. */
+int ntn_set_training_triples(ntn_handle* h, int64_t T, const int32_t* e1, const int32_t* rel, const int32_t* e2);
+int ntn_generate_batch_dev(ntn_handle* h, int64_t first, int32_t batch, int32_t corrupt, uint64_t seed, uint64_t job,
+                           int32_t filter_true);
+/* Download the columns of the current batch job when the library holds them (after ntn_set_batch with host pointers
+ * or ntn_generate_batch_dev); n must be the job's column count. */
+int ntn_get_batch_columns(ntn_handle* h, int64_t n, int32_t* e1, int32_t* rel, int32_t* e2, int32_t* e3);
+
 /* ---- the hot path --------------------------------------------------------------------- */
 /* computeAt (NTN.java:92-443).  theta and grad are host arrays of P doubles in the reference's
  * flattening order W | V | b | U | wordvectors (NTN.java:450-526); values are rounded to FP32
@@ -211,6 +226,9 @@ int ntn_host_entity_word_maps(const char* names, const char* words, int32_t* fwd
 int ntn_host_generate_batch(const int32_t* train, int64_t ntrain, int32_t batch, int32_t corrupt, int32_t num_entities,
                             int64_t seed, int32_t calls, int32_t* e1, int32_t* rel, int32_t* e2, int32_t* e3);
 
+/* java.util.Collections.shuffle(list, new Random(seed)) applied to [0, n) (the shuffle commented out at
+ * DataFactory.java:118). */
+int ntn_host_collections_shuffle(int64_t seed, int32_t n, int32_t* perm);
 /* The staging conversions of the host-buffer entry points (double[] theta -> float, float gradient -> double[];
  * Util.java:49-55 rounding), exposed so that the CPU tests can check them on unaligned and ragged ranges. */
 int ntn_host_convert_f64_f32(const double* src, float* dst, int64_t n);

@@ -62,6 +62,9 @@ SYMBOLS = {
     "ntn_set_frozen_wv": (C.c_int, [_P, _P]),
     "ntn_set_batch": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     "ntn_set_batch_dev": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
+    "ntn_set_training_triples": (C.c_int, [_P, C.c_int64, _P, _P, _P]),
+    "ntn_generate_batch_dev": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32]),
+    "ntn_get_batch_columns": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     "ntn_eval": (C.c_int, [_P, _P, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int64)]),
     "ntn_eval_f32": (C.c_int, [_P, _P, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int64)]),
     "ntn_eval_dev": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -88,6 +91,7 @@ SYMBOLS = {
     "ntn_host_random_ints": (C.c_int, [C.POINTER(C.c_uint64), C.c_int32, C.c_int64, _P]),
     "ntn_host_entity_word_maps": (C.c_int, [C.c_char_p, C.c_char_p, _P, _P, _P, _P, _P, C.c_int64,
                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ntn_host_collections_shuffle": (C.c_int, [C.c_int64, C.c_int32, _P]),
     "ntn_host_convert_f64_f32": (C.c_int, [_P, _P, C.c_int64]),
     "ntn_host_convert_f32_f64": (C.c_int, [_P, _P, C.c_int64]),
     "ntn_host_generate_batch": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),
@@ -174,6 +178,22 @@ class Handle:
     def set_batch_dev(self, n: int, d_e1: int, d_rel: int, d_e2: int, d_e3: int):
         """The batch columns as int32 device pointers (e.g. torch tensors' data_ptr())."""
         self._ck(self.lib.ntn_set_batch_dev(self.h, int(n), d_e1, d_rel, d_e2, d_e3))
+
+    def set_training_triples(self, train):
+        """DataFactory.trainingTripples (T x 3: e1, rel, e2) into HBM, for generate_batch_dev."""
+        t = np.asarray(train)
+        e1, rel, e2 = _i32(t[:, 0]), _i32(t[:, 1]), _i32(t[:, 2])
+        self._ck(self.lib.ntn_set_training_triples(self.h, len(e1), _ptr(e1), _ptr(rel), _ptr(e2)))
+
+    def generate_batch_dev(self, first, batch, corrupt, seed, job, filter_true=False):
+        """Batch job from training triples [first, first+batch) with corrupt entities sampled on the device."""
+        self._ck(self.lib.ntn_generate_batch_dev(self.h, int(first), int(batch), int(corrupt), int(seed) & (2**64 - 1),
+                                                 int(job), 1 if filter_true else 0))
+
+    def get_batch_columns(self, n):
+        cols = [np.empty(n, np.int32) for _ in range(4)]
+        self._ck(self.lib.ntn_get_batch_columns(self.h, int(n), *(_ptr(c) for c in cols)))
+        return tuple(cols)
 
     # ---- hot path ----
     def _side(self, corrupt_side):

@@ -127,6 +127,51 @@ __global__ void k_bi_hub_fill(const int* __restrict__ inc_off, const int* __rest
     }
 }
 
+// ---- on-device batch-job generator ---------------------------------------------------------------
+// Counter-based corrupt sampler: e3 of column j of batch job `job` is a pure function of (seed, job, j, attempt), so a
+// batch job can be regenerated anywhere (tests restate it in NumPy, oracle/data_ref.py: device_corrupt_sample).
+__host__ __device__ inline uint64_t bs_mix(uint64_t seed, uint64_t job, uint64_t j, uint64_t attempt) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (1ull + job);
+    z ^= j * 0xBF58476D1CE4E5B9ull;
+    z += attempt * 0x94D049BB133111EBull;
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return z;
+}
+__device__ inline bool bs_contains(const uint64_t* __restrict__ keys, int64_t n, uint64_t k) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
+    return lo < n && keys[lo] == k;
+}
+// columns h-major like DataFactory.java:123-129: column j = h*batch + i copies training triple first+i
+__global__ void k_bs_generate(const int* __restrict__ tr_e1, const int* __restrict__ tr_rel, const int* __restrict__ tr_e2,
+                              int64_t first, int batch, int64_t n, int Ne, int eb, uint64_t seed, uint64_t job,
+                              const uint64_t* __restrict__ true_keys, int64_t n_true, int max_attempts,
+                              int* __restrict__ e1, int* __restrict__ rel, int* __restrict__ e2, int* __restrict__ e3) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int64_t t = first + (j % batch);
+    const int a = tr_e1[t], r = tr_rel[t], b = tr_e2[t];
+    int c = 0;
+    for (int att = 0; att < max_attempts; ++att) {
+        c = (int)(((bs_mix(seed, job, (uint64_t)j, (uint64_t)att) >> 32) * (uint64_t)Ne) >> 32);
+        if (!true_keys) break;
+        // filtered mode: neither (e1, rel, c) nor (c, rel, e2) may be a known true triple (the corrupt side is only
+        // drawn at evaluation time, NTN.java:146, so both readings are excluded)
+        const uint64_t kt = ((uint64_t)r << (2 * eb)) | ((uint64_t)a << eb) | (uint64_t)c;
+        const uint64_t kh = ((uint64_t)r << (2 * eb)) | ((uint64_t)c << eb) | (uint64_t)b;
+        if (!bs_contains(true_keys, n_true, kt) && !bs_contains(true_keys, n_true, kh)) break;
+    }
+    e1[j] = a; rel[j] = r; e2[j] = b; e3[j] = c;
+}
+
+__global__ void k_bs_true_keys(const int* __restrict__ e1, const int* __restrict__ rel, const int* __restrict__ e2, int64_t n,
+                               int eb, uint64_t* __restrict__ key) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) key[i] = ((uint64_t)rel[i] << (2 * eb)) | ((uint64_t)e1[i] << eb) | (uint64_t)e2[i];
+}
+
 template <typename T> int grow(ntn_handle* h, T** p, size_t n) {
     if (n == 0) n = 1;
     const size_t bytes = n * sizeof(T);
@@ -232,5 +277,43 @@ int ntn_index_batch_dev(ntn_handle* h, int64_t n, const int* d_e1, const int* d_
     BCK(cudaGetLastError());
     counts[0] = Nu;
     counts[1] = h->h_meta[2];
+    return NTN_OK;
+}
+
+// Sorted key set of the training triples (for the filtered sampler).  d_train = [e1 | rel | e2], T each, validated by the caller.
+int ntn_build_true_keys_dev(ntn_handle* h, int64_t T, const int* d_train, uint64_t** d_keys) {
+    const NtnDims& dm = h->dm;
+    cudaStream_t st = h->stream;
+    int eb = 1; while ((1 << eb) < dm.Ne) ++eb;
+    int rb = 1; while ((1 << rb) < dm.R) ++rb;
+    if (2 * eb + rb > 63) { h->err = "batch index: key (rel, e1, e2) does not fit 63 bits"; return NTN_EUNSUP; }
+    uint64_t* tmp_keys = nullptr; void* tmp = nullptr; size_t tb = 0;
+    const size_t nn = (size_t)std::max<int64_t>(T, 1);
+    if (*d_keys) { cudaFree(*d_keys); *d_keys = nullptr; }
+    BCK(cudaMalloc((void**)d_keys, nn * 8));
+    BCK(cudaMalloc((void**)&tmp_keys, nn * 8));
+    cub::DeviceRadixSort::SortKeys(nullptr, tb, tmp_keys, *d_keys, (int)T, 0, 2 * eb + rb, st);
+    cudaError_t e = cudaMalloc(&tmp, std::max<size_t>(tb, 1));
+    if (e == cudaSuccess && T > 0) {
+        k_bs_true_keys<<<cdiv64(T, 256), 256, 0, st>>>(d_train, d_train + T, d_train + 2 * T, T, eb, tmp_keys);
+        e = cub::DeviceRadixSort::SortKeys(tmp, tb, tmp_keys, *d_keys, (int)T, 0, 2 * eb + rb, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tmp_keys); cudaFree(tmp);
+    if (e != cudaSuccess) { h->err = std::string("batch index: true-triple keys: ") + cudaGetErrorString(e); return NTN_ECUDA; }
+    return NTN_OK;
+}
+
+// Fill d_cols = [e1 | rel | e2 | e3] (n = batch*corrupt each) from training triples [first, first+batch).
+int ntn_generate_columns_dev(ntn_handle* h, const int* d_train, int64_t T, int64_t first, int batch, int corrupt, uint64_t seed,
+                             uint64_t job, const uint64_t* d_true_keys, int64_t n_true, int* d_cols) {
+    const NtnDims& dm = h->dm;
+    int eb = 1; while ((1 << eb) < dm.Ne) ++eb;
+    const int64_t n = (int64_t)batch * corrupt;
+    if (n > 0)
+        k_bs_generate<<<cdiv64(n, 256), 256, 0, h->stream>>>(d_train, d_train + T, d_train + 2 * T, first, batch, n, dm.Ne, eb, seed,
+                                                            job, d_true_keys, n_true, d_true_keys ? 16 : 1,
+                                                            d_cols, d_cols + n, d_cols + 2 * n, d_cols + 3 * n);
+    BCK(cudaGetLastError());
     return NTN_OK;
 }

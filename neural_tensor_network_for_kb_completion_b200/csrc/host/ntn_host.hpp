@@ -55,6 +55,7 @@ public:
     int batch_size, corrupt_size, embeddings_size;
     bool reduced_RelationSize;
     JavaRandom rand;
+    JavaRandom shuffle_rand;                          // Collections.shuffle has its own Random in the JDK
     std::vector<std::string> entitiesNumWord, relationsNumWord, vocabNumWord;
     std::unordered_map<std::string, int> entitiesWordNum, relationsWordNum, vocabWordNum;
     std::vector<Tripple> trainingTripples, devTripples, testTripples;
@@ -62,7 +63,8 @@ public:
     std::vector<int32_t> bj_e1, bj_rel, bj_e2, bj_e3; // the batch job columns
 
     DataFactory(int batch, int corrupt, int d, bool reduced = false, int64_t seed = 42)
-        : batch_size(batch), corrupt_size(corrupt), embeddings_size(d), reduced_RelationSize(reduced), rand(seed) {}
+        : batch_size(batch), corrupt_size(corrupt), embeddings_size(d), reduced_RelationSize(reduced), rand(seed),
+          shuffle_rand(seed + 1) {}
 
     void setEntities(const std::vector<std::string>& names) {
         entitiesNumWord = names; entitiesWordNum.clear();
@@ -160,8 +162,15 @@ public:
         }
     }
 
+    // Collections.shuffle(trainingTripples): the line commented out at DataFactory.java:118, JDK algorithm
+    // (for i = size..2: swap(i-1, rnd.nextInt(i))), seeded stream
+    void shuffleTrainingTripples() {
+        for (int i = (int)trainingTripples.size(); i > 1; --i) std::swap(trainingTripples[i - 1], trainingTripples[shuffle_rand.nextInt(i)]);
+    }
+
     // ---- batch job (DataFactory.java:116-136): h-major, first batch_size training triples ----
-    void generateNewTrainingBatchJob() {
+    void generateNewTrainingBatchJob(bool shuffle = false) {
+        if (shuffle) shuffleTrainingTripples();
         const int n = std::min<int>(batch_size, (int)trainingTripples.size());
         bj_e1.clear(); bj_rel.clear(); bj_e2.clear(); bj_e3.clear();
         for (int h = 0; h < corrupt_size; ++h)
@@ -179,6 +188,9 @@ class NTN {
     DataFactory* tbj_;
     JavaRandom side_rand_;
     int R_;
+    bool train_uploaded_ = false, present_valid_ = false;
+    size_t present_n_ = 0;
+    std::vector<char> present_;
     void check(int rc) const { if (rc != NTN_OK) throw std::runtime_error(ntn_last_error(h_)); }
 public:
     int64_t update = 0;
@@ -199,11 +211,31 @@ public:
     ~NTN() { ntn_destroy(h_); }
     ntn_handle* handle() { return h_; }
     int getDimension() const { return (int)ntn_dimension(h_); }                  // NTN.java:445-448
-    void syncBatch() { check(ntn_set_batch(h_, (int64_t)tbj_->bj_e1.size(), tbj_->bj_e1.data(), tbj_->bj_rel.data(), tbj_->bj_e2.data(), tbj_->bj_e3.data())); }
+    void syncBatch() { present_valid_ = false; check(ntn_set_batch(h_, (int64_t)tbj_->bj_e1.size(), tbj_->bj_e1.data(), tbj_->bj_rel.data(), tbj_->bj_e2.data(), tbj_->bj_e3.data())); }
+    // sampler variant: batch job generated and indexed in HBM (ntn_generate_batch_dev); only the relation column of the
+    // first batch_size training triples is kept on the host (for drawCorruptSides)
+    void generateBatchJobOnDevice(uint64_t seed, uint64_t job, bool filter_true) {
+        const auto& tr = tbj_->trainingTripples;
+        if (!train_uploaded_) {
+            std::vector<int32_t> e1, rel, e2;
+            for (auto& x : tr) { e1.push_back(x.e1); rel.push_back(x.rel); e2.push_back(x.e2); }
+            check(ntn_set_training_triples(h_, (int64_t)tr.size(), e1.data(), rel.data(), e2.data()));
+            train_uploaded_ = true;
+        }
+        const int n = std::min<int>(tbj_->batch_size, (int)tr.size());
+        check(ntn_generate_batch_dev(h_, 0, n, tbj_->corrupt_size, seed, job, filter_true ? 1 : 0));
+        tbj_->bj_e1.clear(); tbj_->bj_e2.clear(); tbj_->bj_e3.clear(); tbj_->bj_rel.clear();
+        for (int i = 0; i < n; ++i) tbj_->bj_rel.push_back(tr[i].rel);
+        present_valid_ = false;
+    }
     // one Math.random() > 0.5 per non-empty relation, increasing r (NTN.java:120,146)
     void drawCorruptSides(uint8_t* side) {
-        std::vector<char> present(R_, 0);
-        for (int32_t r : tbj_->bj_rel) present[r] = 1;
+        if (!present_valid_ || present_n_ != tbj_->bj_rel.size()) {
+            present_.assign(R_, 0);
+            for (int32_t r : tbj_->bj_rel) present_[r] = 1;
+            present_valid_ = true; present_n_ = tbj_->bj_rel.size();
+        }
+        const std::vector<char>& present = present_;
         for (int r = 0; r < R_; ++r) side[r] = present[r] ? (side_rand_.nextDouble() > 0.5 ? 1 : 0) : 0;
     }
     // IPair<Double,double[]> computeAt(double[] theta)  (NTN.java:92-443)

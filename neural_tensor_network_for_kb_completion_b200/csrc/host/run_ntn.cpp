@@ -1,5 +1,8 @@
 // run_ntn: the reference's driver (/root/reference/src/Run_NTN.java:38-150) as a compiled host over the C-ABI.
-//   run_ntn <data_path> <theta_load_path> <theta_save_path> [numIterations]
+//   run_ntn <data_path> <theta_load_path> <theta_save_path> [numIterations] [sampler]
+// sampler: "reference" (default: host java.util.Random stream, first batch_size triples, DataFactory.java:116-136),
+// "shuffle" (re-enables the Collections.shuffle commented out at :118), "device" / "device-filter" (batch job generated
+// and indexed in HBM by the counter-based sampler, ntn_generate_batch_dev; with "-filter" known true triples are redrawn).
 // data_path holds entities.txt, relations.txt, train.txt, dev.txt, test.txt (Socher layout) and wordvectors.txt
 // ("word v0 ... v{d-1}" per line; export of initEmbed.mat).  Training runs the device L-BFGS with maxIters = 5
 // per batch job (Run_NTN.java:119-124), checkpoints theta as comma-separated text (:133-139), then thresholds and
@@ -27,6 +30,11 @@ int main(int argc, char** argv) {
     const int batchSize = 20000, numWVdimensions = 100, batch_iterations = 5, sliceSize = 3, corrupt_size = 10;
     const int numIterations = argc > 4 ? atoi(argv[4]) : 500;
     const float lamda = 0.0001f;
+    const std::string sampler = argc > 5 ? argv[5] : "reference";
+    if (sampler != "reference" && sampler != "shuffle" && sampler != "device" && sampler != "device-filter") {
+        fprintf(stderr, "run_ntn: unknown sampler '%s'\n", sampler.c_str());
+        return 2;
+    }
     try {
         DataFactory tbj(batchSize, corrupt_size, numWVdimensions);
         tbj.loadEntitiesFromSocherFile(data_path + "/entities.txt");
@@ -52,8 +60,12 @@ int main(int argc, char** argv) {
         if (cudaMalloc((void**)&d_theta, (size_t)ntn_internal_dimension(t.handle()) * sizeof(float)) != cudaSuccess) throw std::runtime_error("cudaMalloc");
         if (ntn_upload_theta(t.handle(), theta.data(), d_theta)) throw std::runtime_error(ntn_last_error(t.handle()));
         for (int i = 0; i < numIterations; ++i) {                                   // Run_NTN.java:113
-            tbj.generateNewTrainingBatchJob();                                      // :115
-            t.syncBatch();
+            if (sampler == "device" || sampler == "device-filter") {
+                t.generateBatchJobOnDevice(/*seed*/ 42, /*job*/ (uint64_t)i, sampler == "device-filter");
+            } else {
+                tbj.generateNewTrainingBatchJob(sampler == "shuffle");                  // :115
+                t.syncBatch();
+            }
             ntn_lbfgs_opts opts{batch_iterations, 0, 0.0};
             ntn_lbfgs_result res{};
             if (ntn_lbfgs_minimize(t.handle(), d_theta, &opts, &NTN::sidesThunk, &t, &res)) throw std::runtime_error(ntn_last_error(t.handle()));

@@ -1,5 +1,6 @@
 // C-ABI test hooks over the C++ host layer (csrc/host/ntn_host.hpp): the CPU test-suite checks these
 // bit-exactly against the oracle (java.util.Random stream, entity/word maps, batch job order).
+#include <algorithm>
 #include <cstring>
 
 #include "host/ntn_host.hpp"
@@ -76,4 +77,13 @@ int ntn_host_generate_batch(const int32_t* train, int64_t ntrain, int32_t batch,
     } catch (...) { return NTN_EINVAL; }
 }
 
+
+// java.util.Collections.shuffle(list, new Random(seed)) of the list [0, n): perm[p] = element now at position p
+int ntn_host_collections_shuffle(int64_t seed, int32_t n, int32_t* perm) {
+    if (n < 0 || (n > 0 && !perm)) return NTN_EINVAL;
+    JavaRandom r(seed);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    for (int i = n; i > 1; --i) std::swap(perm[i - 1], perm[r.nextInt(i)]);
+    return NTN_OK;
+}
 }  // extern "C"

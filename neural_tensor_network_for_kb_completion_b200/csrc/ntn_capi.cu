@@ -185,6 +185,8 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     if (h->h_meta) cudaFreeHost(h->h_meta);
     if (h->h_cols) cudaFreeHost(h->h_cols);
     if (h->d_cols) cudaFree(h->d_cols);
+    if (h->d_train) cudaFree(h->d_train);
+    if (h->d_true_keys) cudaFree(h->d_true_keys);
     if (h->h_side) cudaFreeHost(h->h_side);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -482,6 +484,18 @@ static int set_batch_dev_columns(ntn_handle* h, int64_t n, const int* d_e1, cons
     return finish_batch(h, n, counts[0], rel_count, counts[1]);
 }
 
+static int ensure_cols(ntn_handle* h, int64_t n) {
+    if (h->cols_cap >= (size_t)n && h->h_cols) return NTN_OK;
+    if (h->h_cols) cudaFreeHost(h->h_cols);
+    if (h->d_cols) cudaFree(h->d_cols);
+    h->h_cols = nullptr; h->d_cols = nullptr; h->cols_cap = 0;
+    const size_t cap = std::max<size_t>((size_t)n, 1);
+    CK(cudaMallocHost((void**)&h->h_cols, 4 * cap * sizeof(int)));
+    CK(cudaMalloc((void**)&h->d_cols, 4 * cap * sizeof(int)));
+    h->cols_cap = cap;
+    return NTN_OK;
+}
+
 extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const int32_t* rel, const int32_t* e2,
                              const int32_t* e3) {
     if (!h) return NTN_EINVAL;
@@ -492,19 +506,67 @@ extern "C" int ntn_set_batch(ntn_handle* h, int64_t n, const int32_t* e1, const 
     ntn_drop_graphs(h);                     // graphs bake buffer pointers and grid sizes; device buffers are reused when large enough
     if (getenv("NTN_SET_BATCH_HOST")) return set_batch_host_tables(h, n, e1, rel, e2, e3);
     // columns -> pinned staging -> device; everything else happens there (batch_index.cu)
-    if (h->cols_cap < (size_t)n || !h->h_cols) {
-        if (h->h_cols) cudaFreeHost(h->h_cols);
-        if (h->d_cols) cudaFree(h->d_cols);
-        h->h_cols = nullptr; h->d_cols = nullptr; h->cols_cap = 0;
-        const size_t cap = std::max<size_t>((size_t)n, 1);
-        CK(cudaMallocHost((void**)&h->h_cols, 4 * cap * sizeof(int)));
-        CK(cudaMalloc((void**)&h->d_cols, 4 * cap * sizeof(int)));
-        h->cols_cap = cap;
-    }
+    { int rc0 = ensure_cols(h, n); if (rc0) return rc0; }
+    h->cols_n = n;
     const int32_t* src[4] = {e1, rel, e2, e3};
     for (int c = 0; c < 4 && n > 0; ++c) memcpy(h->h_cols + (size_t)c * n, src[c], (size_t)n * sizeof(int));
     if (n > 0) CK(cudaMemcpyAsync(h->d_cols, h->h_cols, 4 * (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     return set_batch_dev_columns(h, n, h->d_cols, h->d_cols + n, h->d_cols + 2 * n, h->d_cols + 3 * n);
+}
+
+extern "C" int ntn_set_training_triples(ntn_handle* h, int64_t T, const int32_t* e1, const int32_t* rel, const int32_t* e2) {
+    if (!h) return NTN_EINVAL;
+    if (T < 0 || (T > 0 && (!e1 || !rel || !e2))) FAIL(NTN_EINVAL, "null argument");
+    if (T > ((int64_t)1 << 31) - 1) FAIL(NTN_EUNSUP, "too many training triples");
+    const NtnDims& dm = h->dm;
+    for (int64_t j = 0; j < T; ++j)
+        if (e1[j] < 0 || e1[j] >= dm.Ne || e2[j] < 0 || e2[j] >= dm.Ne || rel[j] < 0 || rel[j] >= dm.R)
+            FAIL(NTN_EINVAL, "index out of range in training triple " + std::to_string(j));
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_train) { cudaFree(h->d_train); h->d_train = nullptr; }
+    h->n_train = 0;
+    const size_t nn = (size_t)std::max<int64_t>(T, 1);
+    CK(cudaMalloc((void**)&h->d_train, 3 * nn * sizeof(int)));
+    if (T > 0) {
+        CK(cudaMemcpy(h->d_train, e1, (size_t)T * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_train + T, rel, (size_t)T * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_train + 2 * T, e2, (size_t)T * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    int rc = ntn_build_true_keys_dev(h, T, h->d_train, &h->d_true_keys);
+    if (rc) return rc;
+    h->n_train = T;
+    return NTN_OK;
+}
+
+extern "C" int ntn_generate_batch_dev(ntn_handle* h, int64_t first, int32_t batch, int32_t corrupt, uint64_t seed, uint64_t job,
+                                      int32_t filter_true) {
+    if (!h) return NTN_EINVAL;
+    if (!h->d_train) FAIL(NTN_ESTATE, "ntn_set_training_triples has not been called");
+    if (batch < 0 || corrupt < 0 || first < 0 || first + batch > h->n_train) FAIL(NTN_EINVAL, "batch range outside the training triples");
+    const int64_t n = (int64_t)batch * corrupt;
+    if (n > ((int64_t)1 << 30) / 3) FAIL(NTN_EUNSUP, "batch too large");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    ntn_drop_graphs(h);
+    int rc = ensure_cols(h, n);
+    if (rc) return rc;
+    rc = ntn_generate_columns_dev(h, h->d_train, h->n_train, first, batch, corrupt, seed, job,
+                                  filter_true ? h->d_true_keys : nullptr, h->n_train, h->d_cols);
+    if (rc) return rc;
+    h->cols_n = n;
+    return set_batch_dev_columns(h, n, h->d_cols, h->d_cols + n, h->d_cols + 2 * n, h->d_cols + 3 * n);
+}
+
+extern "C" int ntn_get_batch_columns(ntn_handle* h, int64_t n, int32_t* e1, int32_t* rel, int32_t* e2, int32_t* e3) {
+    if (!h) return NTN_EINVAL;
+    if (n != h->cols_n) FAIL(NTN_EINVAL, "no staged batch job of this size (columns are kept for ntn_set_batch with host pointers and ntn_generate_batch_dev)");
+    if (n > 0 && (!e1 || !rel || !e2 || !e3)) FAIL(NTN_EINVAL, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    int32_t* dst[4] = {e1, rel, e2, e3};
+    for (int c = 0; c < 4 && n > 0; ++c) CK(cudaMemcpy(dst[c], h->d_cols + (size_t)c * n, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    return NTN_OK;
 }
 
 extern "C" int ntn_set_batch_dev(ntn_handle* h, int64_t n, const int32_t* d_e1, const int32_t* d_rel, const int32_t* d_e2,
@@ -515,6 +577,7 @@ extern "C" int ntn_set_batch_dev(ntn_handle* h, int64_t n, const int32_t* d_e1, 
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     ntn_drop_graphs(h);
+    h->cols_n = -1;
     return set_batch_dev_columns(h, n, d_e1, d_rel, d_e2, d_e3);
 }
 

@@ -136,6 +136,10 @@ struct ntn_handle {
     int *h_cols = nullptr;        // pinned staging of the batch columns (ntn_set_batch with host pointers)
     int *d_cols = nullptr;        // their device copy, 4 x n
     size_t cols_cap = 0;
+    int64_t cols_n = -1;          // columns currently staged in d_cols (-1: none)
+    int *d_train = nullptr;       // training triples [e1 | rel | e2] (ntn_set_training_triples), for the device batch generator
+    int64_t n_train = 0;
+    uint64_t *d_true_keys = nullptr;   // their packed keys, sorted (filtered corrupt sampling)
     void *lbfgs_ws = nullptr;     // L-BFGS workspace (lbfgs.cu), grow-only
     size_t lbfgs_ws_bytes = 0;
     // CUDA graphs of the evaluation, one per (theta, grad, stream) triple
@@ -148,6 +152,10 @@ struct ntn_handle {
 // ---- batch indexing on the device (batch_index.cu)
 int ntn_index_batch_dev(ntn_handle* h, int64_t n, const int* d_e1, const int* d_rel, const int* d_e2, const int* d_e3,
                         int* counts /* Nu, hub segments */, int* rel_count /* R */);
+
+int ntn_build_true_keys_dev(ntn_handle* h, int64_t T, const int* d_train, uint64_t** d_keys);
+int ntn_generate_columns_dev(ntn_handle* h, const int* d_train, int64_t T, int64_t first, int batch, int corrupt, uint64_t seed,
+                             uint64_t job, const uint64_t* d_true_keys, int64_t n_true, int* d_cols);
 
 // ---- kernel launchers (ntn_kernels.cu) ---------------------------------------------------
 void ntn_launch_entity_build(ntn_handle* h, const float* wvt);

@@ -89,10 +89,13 @@ class DataFactory:
     """DataFactory.getInstance(batch_size, corrupt_size, embedding_size, reduce_RelationSize, german)
     (DataFactory.java:70-84).  ``seed`` replaces the reference's unseeded ``new Random()``."""
 
-    def __init__(self, batch_size, corrupt_size, embedding_size, reduce_RelationSize=False, german=False, seed=42):
+    def __init__(self, batch_size, corrupt_size, embedding_size, reduce_RelationSize=False, german=False, seed=42,
+                 shuffle_seed=None):
         self.batch_size, self.corrupt_size, self.embeddings_size = batch_size, corrupt_size, embedding_size
         self.reduced_RelationSize, self.german = reduce_RelationSize, german
         self.rand = JavaRandom(seed)
+        # Collections.shuffle draws from its own Random in the JDK, so the shuffle has its own seeded stream here
+        self.shuffle_rand = JavaRandom(seed + 1 if shuffle_seed is None else shuffle_seed)
         self.entitiesNumWord: list[str] = []
         self.entitiesWordNum: dict[str, int] = {}
         self.relationsNumWord: list[str] = []
@@ -246,11 +249,24 @@ class DataFactory:
         return self._maps
 
     # ---- batch job (DataFactory.java:116-136) -----------------------------------------------
-    def generateNewTrainingBatchJob(self, first=0):
+    def shuffleTrainingTripples(self):
+        """Collections.shuffle(trainingTripples) -- the line the reference has commented out (DataFactory.java:118,
+        "TODO wieder zulassen") -- in place, JDK algorithm: for i = size..2: swap(i-1, rnd.nextInt(i))."""
+        n = len(self.trainingTripples)
+        draws = [self.shuffle_rand.nextInt(i) for i in range(n, 1, -1)]
+        perm = np.arange(n)
+        for i, j in zip(range(n, 1, -1), draws):
+            perm[i - 1], perm[j] = perm[j], perm[i - 1]
+        self.trainingTripples = np.ascontiguousarray(self.trainingTripples[perm])
+        return perm
+
+    def generateNewTrainingBatchJob(self, first=0, shuffle=False):
         """h-major: for h < corrupt_size, for i < batch_size: e3 = rand.nextInt(numOfentities);
         always training triples [first, first+batch_size) -- first = 0 in the reference (the
         shuffle is commented out, :118); a non-zero ``first`` is how a data-parallel rank takes
-        its shard of a larger batch."""
+        its shard of a larger batch.  ``shuffle=True`` re-enables the commented-out shuffle."""
+        if shuffle:
+            self.shuffleTrainingTripples()
         tr = self.trainingTripples[first:first + self.batch_size]
         n = len(tr)
         e3 = self.rand.nextInts(n * self.corrupt_size, self.getNumOfentities())

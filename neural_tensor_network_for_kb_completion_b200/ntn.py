@@ -49,6 +49,7 @@ class NTN:
         self._batch_id = None
         self.last_corrupt_side = None
         self._present_for, self._present = None, None
+        self._train_id = None
         self.global_relations = None     # data parallel: relation ids of the GLOBAL batch job (see drawCorruptSides)
 
     # ---- DataFactory hand-off ----------------------------------------------------------------
@@ -68,6 +69,25 @@ class NTN:
         if self._batch_id is not bj:                               # DataFactory mutated its batch job
             self.handle.set_batch(*bj)
             self._batch_id = bj
+
+    def generateBatchJobOnDevice(self, seed, job, first=0, filter_true=False, fetch=False):
+        """Sampler variant: the batch job over training triples [first, first+batch) is generated and
+        indexed in HBM -- corrupt entities from the counter-based device sampler, optionally redrawn while they
+        reproduce a known training triple.  Not the parity mode (that is DataFactory.generateNewTrainingBatchJob with its
+        seeded java.util.Random).  ``fetch`` downloads the columns into tbj.batchjob (tests, inspection)."""
+        tr = self.tbj.getAllTrainingTripples()
+        if self._train_id is not tr:
+            self.handle.set_training_triples(tr)
+            self._train_id = tr
+        B, C = self.tbj.batch_size, self.tbj.corrupt_size
+        B = min(B, len(tr) - first)
+        self.handle.generate_batch_dev(first, B, C, seed, job, filter_true)
+        if fetch:
+            self.tbj.batchjob = self.handle.get_batch_columns(B * C)
+        else:                                                      # only the relation column is needed on the host
+            self.tbj.batchjob = (None, np.ascontiguousarray(tr[first:first + B, 1]), None, None)
+        self._batch_id = self.tbj.batchjob                         # already on the device: nothing to sync
+        return self.tbj.batchjob
 
     def drawCorruptSides(self):
         """One Math.random() > 0.5 per non-empty relation, increasing r (NTN.java:120,146).  A data-parallel rank holds

@@ -130,6 +130,61 @@ def generate_batch_job(train_e1, train_rel, train_e2, batch_size: int, corrupt_s
     return e1, rel, e2, e3
 
 
+def collections_shuffle(n: int, rng: JavaRandom) -> np.ndarray:
+    """java.util.Collections.shuffle(list, rnd) (JDK spec: ``for (int i = size; i > 1; i--) swap(list, i-1,
+    rnd.nextInt(i))``) as the permutation it applies: result[p] = original index now at position p.  This is the
+    shuffle the reference has commented out at DataFactory.java:118 ("TODO wieder zulassen"), with a seeded stream."""
+    perm = np.arange(n, dtype=np.int64)
+    for i in range(n, 1, -1):
+        j = rng.next_int(i)
+        perm[i - 1], perm[j] = perm[j], perm[i - 1]
+    return perm
+
+
+_M64 = (1 << 64) - 1
+
+
+def device_corrupt_mix(seed: int, job: int, j, attempt: int = 0) -> np.ndarray:
+    """The counter-based 64-bit mix of the device sampler (csrc/batch_index.cu: bs_mix), vectorised over columns j."""
+    with np.errstate(over="ignore"):
+        j = np.asarray(j, dtype=np.uint64)
+        z = np.uint64((seed + 0x9E3779B97F4A7C15 * (1 + job)) & _M64)
+        z = z ^ (j * np.uint64(0xBF58476D1CE4E5B9))
+        z = z + np.uint64((attempt * 0x94D049BB133111EB) & _M64)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def device_corrupt_sample(seed: int, job: int, j, num_entities: int, attempt: int = 0) -> np.ndarray:
+    """e3 = ((mix >> 32) * Ne) >> 32 (multiply-shift range reduction of the high 32 bits)."""
+    hi = device_corrupt_mix(seed, job, j, attempt) >> np.uint64(32)
+    return ((hi * np.uint64(num_entities)) >> np.uint64(32)).astype(np.int32)
+
+
+def generate_batch_job_device(train, first: int, batch_size: int, corrupt_size: int, num_entities: int,
+                              seed: int, job: int, filter_true: bool = False, max_attempts: int = 16):
+    """The device batch-job generator (ntn_generate_batch_dev) restated: h-major columns like
+    DataFactory.java:123-129 over training triples [first, first+batch), corrupt entities from the counter-based
+    sampler; in filtered mode a draw is repeated (attempt 1..15) while (e1, rel, e3) or (e3, rel, e2) is a training
+    triple, the last draw standing if all are rejected."""
+    train = np.asarray(train)
+    n = batch_size * corrupt_size
+    j = np.arange(n, dtype=np.int64)
+    t = first + (j % max(batch_size, 1))
+    e1, rel, e2 = (train[t, c].astype(np.int32) for c in range(3))
+    e3 = device_corrupt_sample(seed, job, j, num_entities, 0)
+    if filter_true:
+        true = set(map(tuple, train[:, :3].tolist()))
+        for col in range(n):
+            for att in range(max_attempts):
+                c = int(device_corrupt_sample(seed, job, col, num_entities, att))
+                e3[col] = c
+                if (int(e1[col]), int(rel[col]), c) not in true and (c, int(rel[col]), int(e2[col])) not in true:
+                    break
+    return e1, rel, e2, e3
+
+
 def draw_corrupt_sides(rel, num_relations: int, rng: JavaRandom) -> np.ndarray:
     """NTN.java:120,146: one ``Math.random() > 0.5`` per evaluation per *non-empty*
     relation, in increasing r; True => negatives are (e1, e3) ("corrupt tail").

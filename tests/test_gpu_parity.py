@@ -428,3 +428,58 @@ def test_set_batch_from_device_columns():
         h2.set_batch_dev(len(batch[0]), *(c.data_ptr() for c in cols))
     assert ei.value.code == _capi.NTN_EINVAL and "column 17" in str(ei.value)
     h.close(); h2.close()
+
+
+@pytest.mark.parametrize("filter_true", [False, True])
+def test_device_batch_job_generator(filter_true):
+    """ntn_generate_batch_dev (sampler variants): the job generated in HBM equals the NumPy restatement
+    column for column, and its evaluation matches the oracle on those columns.  A tiny entity set makes true-triple
+    collisions frequent so the filtered redraws are exercised."""
+    kb, p, _, side, theta0 = small_problem(Ne=60, R=3, T=900, Nw=40, d=8, batch=300, corrupt=6, seed=9)
+    first, B, C, seed, job = 100, 300, 6, 2024, 5
+    want = data_ref.generate_batch_job_device(kb.train, first, B, C, p.Ne, seed, job, filter_true)
+    h = make_handle(p, "theta")
+    h.set_training_triples(kb.train)
+    h.generate_batch_dev(first, B, C, seed, job, filter_true)
+    got = h.get_batch_columns(B * C)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    plain = data_ref.generate_batch_job_device(kb.train, first, B, C, p.Ne, seed, job, False)
+    true = set(map(tuple, kb.train.tolist()))
+    hits = lambda cols: sum(((int(a), int(r), int(c)) in true) or ((int(c), int(r), int(b)) in true) for a, r, b, c in zip(*cols))
+    assert hits(plain) > 20                                           # the unfiltered job does hit true triples ...
+    if filter_true:
+        assert hits(got) < hits(plain) / 10                           # ... the filtered one (almost) never
+    theta = f32(perturbed(theta0, 0.05))
+    side = data_ref.draw_corrupt_sides(got[1], p.R, JavaRandom(3))
+    check(h, p, theta, got, side, label="device job")
+    # a second job: different counter, different columns
+    h.generate_batch_dev(first, B, C, seed, job + 1, filter_true)
+    assert not np.array_equal(h.get_batch_columns(B * C)[3], got[3])
+    with pytest.raises(_capi.NTNError):
+        h.generate_batch_dev(700, B, C, seed, job, filter_true)      # range outside the training triples
+    h.close()
+
+
+def test_training_loop_with_device_sampler():
+    """NTN.generateBatchJobOnDevice + device L-BFGS: the Run_NTN loop without any host batch job."""
+    from neural_tensor_network_for_kb_completion_b200 import synth
+    from neural_tensor_network_for_kb_completion_b200.data_factory import DataFactory
+    from neural_tensor_network_for_kb_completion_b200.lbfgs import LBFGSMinimizer, Opts
+    from neural_tensor_network_for_kb_completion_b200.ntn import NTN
+    kb = synth.make_structured_kb(Ne=300, R=3, T=1500, d=12, seed=2)
+    tbj = DataFactory.from_kb(kb, 500, 4, seed=42)
+    t = NTN(kb.d, kb.Ne, kb.R, kb.Nw, 500, 2, "tanh", tbj, 1e-4, wv_source="theta")
+    theta = np.asarray(t.getTheta_inital(), np.float64)
+    costs = []
+    for it in range(4):
+        t.generateBatchJobOnDevice(seed=11, job=it, filter_true=True)
+        res = LBFGSMinimizer().minimize(t, theta, Opts(maxIters=5))
+        theta = res.minArg
+        costs.append((res.firstObjVal, res.minObjVal))
+    assert all(b <= a for a, b in costs) and costs[-1][1] < costs[0][0]
+    cols = t.generateBatchJobOnDevice(seed=11, job=0, filter_true=True, fetch=True)
+    want = data_ref.generate_batch_job_device(kb.train, 0, 500, 4, kb.Ne, 11, 0, True)
+    for a, b in zip(cols, want):
+        np.testing.assert_array_equal(a, b)
+    t.close()

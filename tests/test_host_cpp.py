@@ -90,3 +90,34 @@ def test_staging_conversions_on_ragged_unaligned_ranges(n, shift):
     assert lib.ntn_host_convert_f32_f64(src32.ctypes.data, dst64[shift:].ctypes.data, n) == 0
     np.testing.assert_array_equal(dst64[shift:shift + n], src32.astype(np.float64))
     assert np.all(dst64[:shift] == 7.0) and np.all(dst64[shift + n:] == 7.0)
+
+
+@pytest.mark.parametrize("n,seed", [(0, 1), (1, 1), (2, 5), (17, 42), (1000, 7)])
+def test_collections_shuffle_three_ways(n, seed):
+    """The shuffle commented out at DataFactory.java:118, re-enabled with a seeded stream: oracle restatement of
+    java.util.Collections.shuffle == C++ host == Python DataFactory mirror."""
+    from neural_tensor_network_for_kb_completion_b200.data_factory import DataFactory
+    ref = data_ref.collections_shuffle(n, JavaRandom(seed))
+    assert sorted(ref.tolist()) == list(range(n))
+    lib = _capi.load()
+    perm = np.empty(max(n, 1), np.int32)
+    assert lib.ntn_host_collections_shuffle(seed, n, perm.ctypes.data) == 0
+    np.testing.assert_array_equal(perm[:n], ref)
+    f = DataFactory(4, 2, 3, seed=0, shuffle_seed=seed)
+    f.trainingTripples = np.stack([np.arange(n), np.zeros(n, int), np.arange(n)], 1).astype(np.int32).reshape(-1, 3)
+    got = f.shuffleTrainingTripples()
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(f.trainingTripples[:, 0], ref)
+
+
+def test_device_sampler_restatement_is_uniform_and_counter_based():
+    """oracle/data_ref.py: device_corrupt_sample is a pure function of (seed, job, column, attempt)."""
+    j = np.arange(200000)
+    a = data_ref.device_corrupt_sample(42, 3, j, 1000)
+    assert a.min() >= 0 and a.max() < 1000
+    cnt = np.bincount(a, minlength=1000)
+    assert cnt.min() > 120 and cnt.max() < 290                      # 200 +- 5.7 sigma
+    np.testing.assert_array_equal(a[1234:1240], data_ref.device_corrupt_sample(42, 3, j[1234:1240], 1000))
+    assert not np.array_equal(a, data_ref.device_corrupt_sample(42, 4, j, 1000))
+    assert not np.array_equal(a, data_ref.device_corrupt_sample(43, 3, j, 1000))
+    assert not np.array_equal(a, data_ref.device_corrupt_sample(42, 3, j, 1000, attempt=1))
