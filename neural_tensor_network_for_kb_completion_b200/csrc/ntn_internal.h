@@ -31,7 +31,7 @@ struct NtnDims {
 
 #define NTN_TILE_ROWS   128      // unique triples per contraction tile (one relation per tile)
 #define NTN_CHUNK_ROWS  256      // unique triples per dW split-K chunk (one relation per chunk)
-#define NTN_SCORE_ROWS  32       // unique triples per score tile (8 warps x 4); 8-row tiles measured no faster
+#define NTN_SCORE_ROWS  32       // default unique triples per score tile (8 warps x 4); finish_batch picks per batch job
 #define NTN_HUB_SEG     32       // incident-list segment length for hub entities
 #define NTN_WORD_HUB_SEG 16      // ... and for hub words (their branch is a short, latency-bound tail: more, shorter segments)
 #define NTN_RING        8        // in-flight evaluations the host may enqueue without synchronising

@@ -331,6 +331,9 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
     const float my_U = U[0] * (my_s == 0) + [&] { float t = 0.f;
 #pragma unroll
         for (int s = 1; s < KS; ++s) t += U[s] * (my_s == s); return t; }();
+    // entity rows carry the augmentation 1.0 at index d (and padding after it): when d is not a multiple of 4 the last
+    // float4 chunk of a row reaches into it and is masked; otherwise (d = 100) no chunk does
+    const bool masked = dq != d;
     bool cv[CH]; float4 cm[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -341,10 +344,21 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
     // lane-local accumulators, reduced once at the end of the tile
     float cost_l = 0.f, dU_l = 0.f; int nact_w = 0;
 
+    // the index data of a warp's NEXT triple (other entity, corrupt range, the first 32 corrupt ids -- one per lane) is
+    // fetched while the current one is computed: the dependent chain per triple is then one round trip (rows of E and
+    // T'), not c_off -> c_e3 -> rows
+    const int* oth = tail ? a.u_e2 : a.u_e1;
+    int nx_other = 0, nx_c0 = 0, nx_c1 = 0, nx_e3 = 0;
+    if (warp < rows) {
+        nx_other = __ldg(oth + u0 + warp); nx_c0 = __ldg(a.c_off + u0 + warp); nx_c1 = __ldg(a.c_off + u0 + warp + 1);
+        nx_e3 = (nx_c0 + lane < nx_c1) ? __ldg(a.c_e3 + nx_c0 + lane) : 0;
+    }
     for (int i = warp; i < rows; i += 8) {
         const int u = u0 + i;
-        const int other = tail ? __ldg(a.u_e2 + u) : __ldg(a.u_e1 + u);
-        const int c0 = __ldg(a.c_off + u), c1 = __ldg(a.c_off + u + 1);
+        const int other = nx_other, c0 = nx_c0, c1 = nx_c1, my_e3 = nx_e3;
+        if (i + 8 < rows) {
+            nx_other = __ldg(oth + u + 8); nx_c0 = __ldg(a.c_off + u + 8); nx_c1 = __ldg(a.c_off + u + 9);
+        }
         const float* Trow = a.T + (size_t)u * a.Np;
         float4 t[KS][CH]; float beta[KS];
 #pragma unroll
@@ -360,7 +374,7 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             eo[c] = cv[c] ? ldg4(a.E + (size_t)other * a.Kp + (lane + 32 * c) * 4) : zero4();
-            eo[c].x *= cm[c].x; eo[c].y *= cm[c].y; eo[c].z *= cm[c].z; eo[c].w *= cm[c].w;
+            if (masked) { eo[c].x *= cm[c].x; eo[c].y *= cm[c].y; eo[c].z *= cm[c].z; eo[c].w *= cm[c].w; }
         }
         // positive column (shared by all corrupt copies of this triple)
         float zp[KS], tp[KS], sp = 0.f;
@@ -405,7 +419,9 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
 #pragma unroll
             for (int j = 0; j < COLB; ++j) {
                 const bool ok = j < nb;
-                const int e3 = ok ? __ldg(a.c_e3 + col + j) : 0;
+                const int ci = col + j - c0;                              // warp-uniform
+                const int e3s = __shfl_sync(FULL, my_e3, ci & 31);
+                const int e3 = ok ? (ci < 32 ? e3s : __ldg(a.c_e3 + col + j)) : 0;
 #pragma unroll
                 for (int c = 0; c < CH; ++c)
                     ev[j][c] = (ok && cv[c]) ? ldg4(a.E + (size_t)e3 * a.Kp + (lane + 32 * c) * 4) : zero4();
@@ -417,7 +433,7 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
             for (int j = 0; j < COLB; ++j)
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
-                    ev[j][c].x *= cm[c].x; ev[j][c].y *= cm[c].y; ev[j][c].z *= cm[c].z; ev[j][c].w *= cm[c].w;
+                    if (masked) { ev[j][c].x *= cm[c].x; ev[j][c].y *= cm[c].y; ev[j][c].z *= cm[c].z; ev[j][c].w *= cm[c].w; }
 #pragma unroll
                     for (int s = 0; s < KS; ++s) v[j * KS + s] += dot4(t[s][c], ev[j][c]);
                 }
@@ -458,6 +474,7 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
                 }
             }
         }
+        if (i + 8 < rows) nx_e3 = (nx_c0 + lane < nx_c1) ? __ldg(a.c_e3 + nx_c0 + lane) : 0;
         float* Mrow = a.M + (size_t)u * a.Np;
         float4 gvo[CH];
 #pragma unroll
