@@ -20,6 +20,7 @@
 // it is fed by TMA (cp.async.bulk.tensor 2-D boxes from pre-split hi/lo arrays, SWIZZLE_128B tensor maps, completion
 // bytes on the stage's full mbarrier); NTN_TC_TMA=0 selects the software-loaded fallback.
 #include <cuda.h>
+#include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -31,8 +32,10 @@
 #define TC_A_BYTES (128 * 128)    // one split of the A tile per stage
 #define TC_B_BYTES (TC_NCH * 128) // one split of the B tile per stage
 #define TC_STAGE_BYTES (2 * TC_A_BYTES + 2 * TC_B_BYTES)
-#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 256 /*barriers*/)
-#define TC_TMEM_COLS 256
+#define TC_EPI_BYTES (4 * 32 * 16 * 4)   // epilogue staging: one 32 x 16 float slab per epilogue warp
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES + 256 /*barriers*/)
+#define TC_ACC_COLS 256            // TMEM columns per accumulator buffer (N <= 160)
+#define TC_TMEM_COLS 512           // two accumulators: the epilogue of item i overlaps the main loop of item i+1
 #define TC_SPIN_LIMIT (1u << 22)
 
 struct TcState {
@@ -45,6 +48,8 @@ struct TcState {
     CUtensorMap mWT_hi, mWT_lo, mW_hi, mW_lo;
     int box_fwd = 0, box_ge = 0;                // rows per TMA box
     int KpP = 0, KpN = 0, NpP = 0;
+    int* t_anchor = nullptr;                    // [Nu] anchor entity per unique triple, rewritten per evaluation (grow-only)
+    size_t anchor_cap = 0;
     int* err = nullptr;                         // device flag: a bounded wait expired
     long long* dbg = nullptr;                   // 3 x 256 cycle stamps of CTA (0,0,0) per mode (debug timeline)
 };
@@ -147,6 +152,7 @@ __device__ __forceinline__ void sts4(uint8_t* base, uint32_t off, const float4& 
 struct TcArgs {
     const int *t_rel, *t_u0, *t_n;     // tile table (fwd/ge: <=128 rows) or split-K chunk table (dw)
     const int *u_e1, *u_e2;
+    const int* t_anchor;               // anchor entity of every unique triple for this evaluation's corrupt sides (k_tc_w_prep)
     const uint8_t* side;
     const float *E, *M;
     const float *WT, *W;
@@ -156,11 +162,12 @@ struct TcArgs {
     long long* dbg;                    // cycle-stamp timeline of CTA (0,0,0), or null
     int b_rows_per_rel;                // TMA path: rows of the weight tensor per relation (Np resp. KpN)
     int b_box_rows;                    // TMA path: rows per box (expect_tx bytes = 2 * rows * 128)
+    int nitems, ny, nz;                // work items = nitems x ny (N chunks) x nz (M chunks, dw)
 };
 
 enum { TC_FWD = 0, TC_DW = 1, TC_GE = 2 };
 
-#define TC_THREADS 288            // warps 0-3: producer group 0 + epilogue, warp 4: MMA issuer, warps 5-8: producer group 1
+#define TC_THREADS 416            // warps 0-3, 5-8: producer groups, warp 4: MMA issuer, warps 9-12: epilogue
 
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float v[16]) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -171,7 +178,6 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float v[16]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // DW_MN (dw only): both operands as MN-major tiles.  dw contracts over the ROW index u of E_anchor and M, i.e. its K
 // index is the slow dimension of both arrays; an MN-major UMMA operand takes the rows as they are (coalesced loads,
@@ -185,36 +191,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
     // integers) so that the stores below stay in the shared state space (STS): with generic stores the compiler
     // cannot hoist the global loads above them and every load round trip is exposed.
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-    // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready; then the TMEM base address
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    uint8_t* epi_stage = smem + TC_STAGES * TC_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES);
+    // bars[0..S) full, bars[S..2S) empty, then accumulator full[2], accumulator empty[2]; then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
-    const uint32_t acc_bar = bar0 + 8u * (2 * TC_STAGES);
+    auto acc_full = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + 2 + b); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int item = blockIdx.x;
     // debug timeline: thread 0 (producer group 0) stamps slots [0,128), thread 128 (MMA issuer) slots [128,256)
-    long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 0 || threadIdx.x == 128))
+    long long* dbg = (a.dbg && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 128))
                          ? a.dbg + MODE * 256 + (threadIdx.x == 128 ? 128 : 0) : nullptr;
     int dbg_n = 0;
     auto stamp = [&]() { if (dbg && dbg_n < 128) dbg[dbg_n++] = clock64(); };
     stamp();
-    const int r = a.t_rel[item], u0 = a.t_u0[item], rows = a.t_n[item];
-    const bool tail = a.side[r] != 0;
-
-    // problem geometry of this CTA
-    int n0, nlen, m0 = 0, kext;
-    if (MODE == TC_GE) { n0 = blockIdx.y * TC_NCH; nlen = min(TC_NCH, a.KpN - n0); kext = a.Np; }
-    else { n0 = blockIdx.y * TC_NCH; nlen = min(TC_NCH, a.Np - n0); kext = (MODE == TC_FWD) ? a.Kp : rows; }
-    if (MODE == TC_DW) m0 = blockIdx.z * 128;
-    const int nkb = (kext + TC_BK - 1) / TC_BK;
 
     if (threadIdx.x == 0) {
         // full: 128 producer arrivals (+ the TMA issuer's arrive.expect_tx when the weight tile comes by TMA)
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), TMA_B ? 129 : 128); mbar_init(empty_bar(s), 1); }
-        mbar_init(acc_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
         fence_barrier_init();
         if (TMA_B) { tma_prefetch_desc(&mapB_hi); tma_prefetch_desc(&mapB_lo); }
     }
@@ -225,184 +223,285 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
     const uint32_t tmem_base = *tmem_slot;
     stamp();
 
-    if (warp != 4) {
+    // Work items: (tile or chunk) x N-chunk x M-chunk, taken round-robin by the CTAs of a persistent grid.  Every role
+    // walks the same sequence and derives the same geometry; the pipeline (stage ring, the two TMEM accumulators)
+    // runs across item boundaries: while the epilogue warps drain accumulator b, the producers and the MMA issuer
+    // are already on the next item in accumulator b^1.
+    const int nyz = a.ny * a.nz, nwork = a.nitems * nyz;
+#define TC_ITEM_GEOMETRY(w)                                                                              \
+    const int item = (w) / nyz, yz_ = (w) - item * nyz, by_ = yz_ % a.ny, bz_ = yz_ / a.ny;              \
+    const int r = a.t_rel[item], u0 = a.t_u0[item], rows = a.t_n[item];                                  \
+    int n0, nlen, m0 = 0, kext;                                                                          \
+    if (MODE == TC_GE) { n0 = by_ * TC_NCH; nlen = min(TC_NCH, a.KpN - n0); kext = a.Np; }               \
+    else { n0 = by_ * TC_NCH; nlen = min(TC_NCH, a.Np - n0); kext = (MODE == TC_FWD) ? a.Kp : rows; }    \
+    if (MODE == TC_DW) m0 = bz_ * 128;                                                                   \
+    const int nkb = (kext + TC_BK - 1) / TC_BK;                                                          \
+    (void)bz_; (void)r; (void)m0; (void)u0; (void)n0; (void)nlen;
+
+    if (warp < 9 && warp != 4) {
         // ================================ producers ================================
-        // two groups of 128 threads take alternate k-blocks, so two k-blocks' global loads are in flight
+        // two groups of 128 threads take alternate k-blocks (of the CTA's whole item sequence), so two k-blocks'
+        // global loads are in flight
         const int group = warp > 4 ? 1 : 0;
         const int t = threadIdx.x - (group ? 160 : 0);   // 0..127 inside the group
         const int gw = t >> 5;                           // warp inside the group
         const int j = t & 7;                             // 16-byte chunk inside a 128-byte swizzle row
         const int rsub = t >> 3;                         // 0..15
-        int anchor[8];                                   // fwd: gathered entity of this thread's 8 rows
-        if (MODE == TC_FWD) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int row = rsub + 16 * i;
-                anchor[i] = (row < rows) ? (tail ? __ldg(a.u_e1 + u0 + row) : __ldg(a.u_e2 + u0 + row)) : -1;
-            }
-        }
-        const float* Bw = (MODE == TC_FWD) ? a.WT + (size_t)r * a.Np * a.KpP
-                         : (MODE == TC_GE) ? a.W + (size_t)r * a.KpN * a.NpP : nullptr;
-        const int ldb = (MODE == TC_FWD) ? a.KpP : a.NpP;
+        (void)gw;
         bool alive = true;
-        for (int kb = group; kb < nkb && alive; kb += 2) {
-            const int s = kb % TC_STAGES;
-            const uint32_t ph = (kb / TC_STAGES) & 1;
-            alive = mbar_wait(empty_bar(s), ph ^ 1, a.err);
-            stamp();
-            uint8_t* sA_hi = smem + s * TC_STAGE_BYTES;
-            uint8_t* sA_lo = sA_hi + TC_A_BYTES;
-            uint8_t* sB_hi = sA_lo + TC_A_BYTES;
-            uint8_t* sB_lo = sB_hi + TC_B_BYTES;
-            const int k0 = kb * TC_BK;
-            constexpr int BROWS = TC_NCH / 16;                                       // B rows per thread (K-major loads)
-            if (TMA_B && t == 0) {
-                // weight tile by TMA: two boxes (hi, lo) of 32 floats x b_box_rows rows land directly in the swizzled
-                // UMMA layout; their bytes complete on the stage's full barrier
-                mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)a.b_box_rows * 128u);
-                const int y = r * a.b_rows_per_rel + n0;
-                tma_load_2d(smem_u32(sB_hi), &mapB_hi, k0, y, full_bar(s));
-                tma_load_2d(smem_u32(sB_lo), &mapB_lo, k0, y, full_bar(s));
+        int g = 0;                                       // k-blocks issued so far by this CTA (all items)
+        // The tables of the NEXT item (and, fwd, the anchor entities of this thread's 8 rows) are fetched while the
+        // current item is produced, so that an item starts with a single round trip (its operand rows) instead of
+        // the chain  tile table -> anchor index -> rows.
+        int w = blockIdx.x;
+        int nx_r = 0, nx_u0 = 0, nx_rows = 0;
+        int nx_anchor[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nx_anchor[i] = -1;
+        auto fetch_tables = [&](int ww) {
+            if (ww < nwork) { const int it = ww / nyz; nx_r = __ldg(a.t_rel + it); nx_u0 = __ldg(a.t_u0 + it); nx_rows = __ldg(a.t_n + it); }
+        };
+        auto fetch_anchors = [&](int ww) {
+            if (MODE == TC_FWD && ww < nwork) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = rsub + 16 * i;
+                    nx_anchor[i] = (row < nx_rows) ? __ldg(a.t_anchor + nx_u0 + row) : -1;
+                }
             }
-            if (MODE == TC_FWD || MODE == TC_GE) {
-                // all global loads of this k-block are issued first (latency overlaps), then split + store
-                float4 xa[8], xb[BROWS];
-                const int kk = k0 + j * 4;
+        };
+        fetch_tables(w);
+        fetch_anchors(w);
+        for (; w < nwork && alive; w += gridDim.x) {
+            const int item = w / nyz, yz_ = w - item * nyz, by_ = yz_ % a.ny, bz_ = yz_ / a.ny;
+            const int r = nx_r, u0 = nx_u0, rows = nx_rows;
+            int anchor[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = rsub + 16 * i;
-                    xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (MODE == TC_FWD) { if (anchor[i] >= 0 && kk < a.Kp) xa[i] = ldg4g(a.E + (size_t)anchor[i] * a.Kp + kk); }
-                    else { if (row < rows && kk < a.Np) xa[i] = ldg4g(a.M + (size_t)(u0 + row) * a.Np + kk); }
+            for (int i = 0; i < 8; ++i) anchor[i] = nx_anchor[i];
+            fetch_tables(w + (int)gridDim.x);            // lands during this item
+            bool anchors_fetched = false;
+            int n0, nlen, m0 = 0, kext;
+            if (MODE == TC_GE) { n0 = by_ * TC_NCH; nlen = min(TC_NCH, a.KpN - n0); kext = a.Np; }
+            else { n0 = by_ * TC_NCH; nlen = min(TC_NCH, a.Np - n0); kext = (MODE == TC_FWD) ? a.Kp : rows; }
+            if (MODE == TC_DW) m0 = bz_ * 128;
+            const int nkb = (kext + TC_BK - 1) / TC_BK;
+            (void)bz_; (void)m0; (void)item; (void)anchor;
+            const float* Bw = (MODE == TC_FWD) ? a.WT + (size_t)r * a.Np * a.KpP
+                             : (MODE == TC_GE) ? a.W + (size_t)r * a.KpN * a.NpP : nullptr;
+            const int ldb = (MODE == TC_FWD) ? a.KpP : a.NpP;
+            (void)Bw; (void)ldb;
+            for (int kb = 0; kb < nkb && alive; ++kb, ++g) {
+                if ((g & 1) != group) continue;
+                const int s = g % TC_STAGES;
+                const uint32_t ph = (g / TC_STAGES) & 1;
+                alive = mbar_wait(empty_bar(s), ph ^ 1, a.err);
+                stamp();
+                uint8_t* sA_hi = smem + s * TC_STAGE_BYTES;
+                uint8_t* sA_lo = sA_hi + TC_A_BYTES;
+                uint8_t* sB_hi = sA_lo + TC_A_BYTES;
+                uint8_t* sB_lo = sB_hi + TC_B_BYTES;
+                const int k0 = kb * TC_BK;
+                constexpr int BROWS = TC_NCH / 16;                                       // B rows per thread (K-major loads)
+                if (TMA_B && t == 0) {
+                    // weight tile by TMA: two boxes (hi, lo) of 32 floats x b_box_rows rows land directly in the swizzled
+                    // UMMA layout; their bytes complete on the stage's full barrier
+                    mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)a.b_box_rows * 128u);
+                    const int y = r * a.b_rows_per_rel + n0;
+                    tma_load_2d(smem_u32(sB_hi), &mapB_hi, k0, y, full_bar(s));
+                    tma_load_2d(smem_u32(sB_lo), &mapB_lo, k0, y, full_bar(s));
                 }
-                if (!TMA_B) {
-#pragma unroll
-                    for (int i = 0; i < BROWS; ++i) {
+                if (MODE == TC_FWD || MODE == TC_GE) {
+                    // all global loads of this k-block are issued first (latency overlaps), then split + store
+                    float4 xa[8], xb[BROWS];
+                    const int kk = k0 + j * 4;
+    #pragma unroll
+                    for (int i = 0; i < 8; ++i) {
                         const int row = rsub + 16 * i;
-                        xb[i] = (row < nlen) ? ldg4g(Bw + (size_t)(n0 + row) * ldb + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (MODE == TC_FWD) { if (anchor[i] >= 0 && kk < a.Kp) xa[i] = ldg4g(a.E + (size_t)anchor[i] * a.Kp + kk); }
+                        else { if (row < rows && kk < a.Np) xa[i] = ldg4g(a.M + (size_t)(u0 + row) * a.Np + kk); }
                     }
-                }
-                // ---- A: K-major, 128 rows x 128 bytes, chunk j of row `row` at row*128 + ((j ^ (row&7))<<4)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = rsub + 16 * i;
-                    float4 hi, lo;
-                    split_tf32(xa[i], hi, lo);
-                    const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
-                    sts4(sA_hi, off, hi); sts4(sA_lo, off, lo);
-                }
-                // ---- B: K-major, nlen rows (n resp. p) x 128 bytes of Waug, split here as well: reading one FP32
-                //      copy instead of pre-split hi/lo arrays halves the L2 traffic of the operand every CTA re-reads
-                if (!TMA_B) {
-#pragma unroll
-                    for (int i = 0; i < BROWS; ++i) {
+                    if (!TMA_B) {
+    #pragma unroll
+                        for (int i = 0; i < BROWS; ++i) {
+                            const int row = rsub + 16 * i;
+                            xb[i] = (row < nlen) ? ldg4g(Bw + (size_t)(n0 + row) * ldb + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    // ---- A: K-major, 128 rows x 128 bytes, chunk j of row `row` at row*128 + ((j ^ (row&7))<<4)
+    #pragma unroll
+                    for (int i = 0; i < 8; ++i) {
                         const int row = rsub + 16 * i;
-                        if (row < nlen) {
+                        float4 hi, lo;
+                        split_tf32(xa[i], hi, lo);
+                        const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+                        sts4(sA_hi, off, hi); sts4(sA_lo, off, lo);
+                    }
+                    // ---- B: K-major, nlen rows (n resp. p) x 128 bytes of Waug, split here as well: reading one FP32
+                    //      copy instead of pre-split hi/lo arrays halves the L2 traffic of the operand every CTA re-reads
+                    if (!TMA_B) {
+    #pragma unroll
+                        for (int i = 0; i < BROWS; ++i) {
+                            const int row = rsub + 16 * i;
+                            if (row < nlen) {
+                                float4 hi, lo;
+                                split_tf32(xb[i], hi, lo);
+                                const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+                                sts4(sB_hi, off, hi); sts4(sB_lo, off, lo);
+                            }
+                        }
+                    }
+                } else if (DW_MN) {
+                    // ---- dw, MN-major tiles: rows as they are.  Thread (rsub, j): rows ul = rsub, rsub+16 of the k-block,
+                    //      16-byte chunk j of every 32-float atom.
+                    float4 xa[2][4], xb[2][TC_NCH / 32];
+    #pragma unroll
+                    for (int i2 = 0; i2 < 2; ++i2) {
+                        const int u = k0 + rsub + 16 * i2;
+                        const int an = (u < rows) ? __ldg(a.t_anchor + u0 + u) : -1;
+    #pragma unroll
+                        for (int mi = 0; mi < 4; ++mi) {
+                            const int p = m0 + mi * 32 + j * 4;
+                            xa[i2][mi] = (an >= 0 && p < a.Kp) ? ldg4g(a.E + (size_t)an * a.Kp + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+    #pragma unroll
+                        for (int ni = 0; ni < TC_NCH / 32; ++ni) {
+                            const int n = ni * 32 + j * 4;
+                            xb[i2][ni] = (an >= 0 && n < nlen) ? ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+    #pragma unroll
+                    for (int i2 = 0; i2 < 2; ++i2) {
+                        const int ul = rsub + 16 * i2;
+                        const uint32_t rowoff = ul * 128 + ((((uint32_t)j >> 1) ^ (ul & 3)) << 5) + (j & 1) * 16;
+    #pragma unroll
+                        for (int mi = 0; mi < 4; ++mi) {
+                            float4 hi, lo;
+                            split_tf32(xa[i2][mi], hi, lo);
+                            sts4(sA_hi, mi * 4096 + rowoff, hi); sts4(sA_lo, mi * 4096 + rowoff, lo);
+                        }
+    #pragma unroll
+                        for (int ni = 0; ni < TC_NCH / 32; ++ni) {
+                            if (ni * 32 < nlen) {
+                                float4 hi, lo;
+                                split_tf32(xb[i2][ni], hi, lo);
+                                sts4(sB_hi, ni * 4096 + rowoff, hi); sts4(sB_lo, ni * 4096 + rowoff, lo);
+                            }
+                        }
+                    }
+                } else {
+                    // ---- dw (K-major fallback): the contraction runs over the ROW index u of both operands, so the producers
+                    //      transpose while storing: lane = u row of this k-block (K index), warps stride over the
+                    //      16-byte column chunks.  For a fixed chunk and component the 32 lanes hit 32 different
+                    //      banks (8 swizzled k-chunks x 4 words), so the 4-byte stores are conflict-free.
+                    constexpr int BCH = TC_NCH / 16;                                      // B column chunks per thread
+                    const int ul = lane, u = k0 + ul;
+                    const int an = (u < rows) ? __ldg(a.t_anchor + u0 + u) : -1;
+                    const uint32_t kc = ul >> 2, ke = (ul & 3) * 4;
+                    float4 xa[8], xb[BCH];
+    #pragma unroll
+                    for (int i = 0; i < 8; ++i) {                                         // A rows: p = m0 + 4c + e
+                        const int p = m0 + 4 * (gw + 4 * i);
+                        xa[i] = (an >= 0 && p < a.Kp) ? ldg4g(a.E + (size_t)an * a.Kp + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+    #pragma unroll
+                    for (int i = 0; i < BCH; ++i) {                                       // B rows: n = n0 + 4c + e
+                        const int c = gw + 4 * i;
+                        xb[i] = (an >= 0 && 4 * c < nlen) ? ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + 4 * c)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+    #pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 hi, lo;
+                        split_tf32(xa[i], hi, lo);
+                        const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
+    #pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t row = 4 * (gw + 4 * i) + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
+                            *reinterpret_cast<float*>(sA_hi + off) = hv[e];
+                            *reinterpret_cast<float*>(sA_lo + off) = lv[e];
+                        }
+                    }
+    #pragma unroll
+                    for (int i = 0; i < BCH; ++i) {
+                        const int c = gw + 4 * i;
+                        if (4 * c < nlen) {
                             float4 hi, lo;
                             split_tf32(xb[i], hi, lo);
-                            const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
-                            sts4(sB_hi, off, hi); sts4(sB_lo, off, lo);
+                            const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
+    #pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint32_t row = 4 * c + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
+                                *reinterpret_cast<float*>(sB_hi + off) = hv[e];
+                                *reinterpret_cast<float*>(sB_lo + off) = lv[e];
+                            }
                         }
                     }
                 }
-            } else if (DW_MN) {
-                // ---- dw, MN-major tiles: rows as they are.  Thread (rsub, j): rows ul = rsub, rsub+16 of the k-block,
-                //      16-byte chunk j of every 32-float atom.
-                float4 xa[2][4], xb[2][TC_NCH / 32];
-#pragma unroll
-                for (int i2 = 0; i2 < 2; ++i2) {
-                    const int u = k0 + rsub + 16 * i2;
-                    const int an = (u < rows) ? (tail ? __ldg(a.u_e1 + u0 + u) : __ldg(a.u_e2 + u0 + u)) : -1;
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) {
-                        const int p = m0 + mi * 32 + j * 4;
-                        xa[i2][mi] = (an >= 0 && p < a.Kp) ? ldg4g(a.E + (size_t)an * a.Kp + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int ni = 0; ni < TC_NCH / 32; ++ni) {
-                        const int n = ni * 32 + j * 4;
-                        xb[i2][ni] = (an >= 0 && n < nlen) ? ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-#pragma unroll
-                for (int i2 = 0; i2 < 2; ++i2) {
-                    const int ul = rsub + 16 * i2;
-                    const uint32_t rowoff = ul * 128 + ((((uint32_t)j >> 1) ^ (ul & 3)) << 5) + (j & 1) * 16;
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) {
-                        float4 hi, lo;
-                        split_tf32(xa[i2][mi], hi, lo);
-                        sts4(sA_hi, mi * 4096 + rowoff, hi); sts4(sA_lo, mi * 4096 + rowoff, lo);
-                    }
-#pragma unroll
-                    for (int ni = 0; ni < TC_NCH / 32; ++ni) {
-                        if (ni * 32 < nlen) {
-                            float4 hi, lo;
-                            split_tf32(xb[i2][ni], hi, lo);
-                            sts4(sB_hi, ni * 4096 + rowoff, hi); sts4(sB_lo, ni * 4096 + rowoff, lo);
-                        }
-                    }
-                }
-            } else {
-                // ---- dw (K-major fallback): the contraction runs over the ROW index u of both operands, so the producers
-                //      transpose while storing: lane = u row of this k-block (K index), warps stride over the
-                //      16-byte column chunks.  For a fixed chunk and component the 32 lanes hit 32 different
-                //      banks (8 swizzled k-chunks x 4 words), so the 4-byte stores are conflict-free.
-                constexpr int BCH = TC_NCH / 16;                                      // B column chunks per thread
-                const int ul = lane, u = k0 + ul;
-                const int an = (u < rows) ? (tail ? __ldg(a.u_e1 + u0 + u) : __ldg(a.u_e2 + u0 + u)) : -1;
-                const uint32_t kc = ul >> 2, ke = (ul & 3) * 4;
-                float4 xa[8], xb[BCH];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {                                         // A rows: p = m0 + 4c + e
-                    const int p = m0 + 4 * (gw + 4 * i);
-                    xa[i] = (an >= 0 && p < a.Kp) ? ldg4g(a.E + (size_t)an * a.Kp + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int i = 0; i < BCH; ++i) {                                       // B rows: n = n0 + 4c + e
-                    const int c = gw + 4 * i;
-                    xb[i] = (an >= 0 && 4 * c < nlen) ? ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + 4 * c)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 hi, lo;
-                    split_tf32(xa[i], hi, lo);
-                    const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t row = 4 * (gw + 4 * i) + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
-                        *reinterpret_cast<float*>(sA_hi + off) = hv[e];
-                        *reinterpret_cast<float*>(sA_lo + off) = lv[e];
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < BCH; ++i) {
-                    const int c = gw + 4 * i;
-                    if (4 * c < nlen) {
-                        float4 hi, lo;
-                        split_tf32(xb[i], hi, lo);
-                        const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const uint32_t row = 4 * c + e, off = row * 128 + ((kc ^ (row & 7)) << 4) + ke;
-                            *reinterpret_cast<float*>(sB_hi + off) = hv[e];
-                            *reinterpret_cast<float*>(sB_lo + off) = lv[e];
-                        }
-                    }
-                }
+                fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
+                mbar_arrive(full_bar(s));
+                stamp();
+                if (!anchors_fetched) { fetch_anchors(w + (int)gridDim.x); anchors_fetched = true; }
             }
-            fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
-            mbar_arrive(full_bar(s));
-            stamp();
+            if (!anchors_fetched) fetch_anchors(w + (int)gridDim.x);
         }
-        // ================================ epilogue (group 0: warps 0-3 own TMEM lanes 32w..32w+31) ================
-        if (group == 0) {
-            if (alive) alive = mbar_wait(acc_bar, 0, a.err);
+    } else if (warp == 4) {
+        // ================================ MMA issuer ================================
+        bool alive = true;
+        int g = 0, tl = 0;
+        for (int w = blockIdx.x; w < nwork && alive; w += gridDim.x, ++tl) {
+            TC_ITEM_GEOMETRY(w)
+            const uint32_t idesc = make_idesc(nlen, DW_MN ? 1 : 0, DW_MN ? 1 : 0);
+            const int b = tl & 1;
+            const uint32_t tacc = tmem_base + (uint32_t)(b * TC_ACC_COLS);
+            alive = mbar_wait(acc_empty(b), (uint32_t)((tl >> 1) & 1) ^ 1u, a.err);   // epilogue has drained this accumulator
             tc_fence_after();
-            stamp();
-            const int row = gw * 32 + lane;              // TMEM lane = accumulator row
-            const uint32_t trow = tmem_base + ((uint32_t)(gw * 32) << 16);
+            for (int kb = 0; kb < nkb && alive; ++kb, ++g) {
+                const int s = g % TC_STAGES;
+                const uint32_t ph = (g / TC_STAGES) & 1;
+                alive = mbar_wait(full_bar(s), ph, a.err);
+                tc_fence_after();
+                stamp();
+                if (lane == 0 && alive) {
+                    const uint32_t sA_hi = smem_u32(smem + s * TC_STAGE_BYTES);
+                    const uint32_t sA_lo = sA_hi + TC_A_BYTES, sB_hi = sA_lo + TC_A_BYTES, sB_lo = sB_hi + TC_B_BYTES;
+                    const int kleft = kext - kb * TC_BK;
+                    const int nks = (kleft >= TC_BK) ? 4 : (kleft + 7) / 8;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        uint64_t dAh, dAl, dBh, dBl;
+                        if (DW_MN) {     // MN-major SWIZZLE_128B_BASE32B: k-step = 8 rows = 1024 B; MN atoms 4096 B apart; 4-row K groups 512 B apart
+                            dAh = make_desc(sA_hi + ks * 1024, 4096, 512, 1); dAl = make_desc(sA_lo + ks * 1024, 4096, 512, 1);
+                            dBh = make_desc(sB_hi + ks * 1024, 4096, 512, 1); dBl = make_desc(sB_lo + ks * 1024, 4096, 512, 1);
+                        } else {         // K-major: a k-step is 32 bytes inside the 128-byte swizzle row; 8-row groups are 1024 B apart
+                            dAh = make_desc(sA_hi + ks * 32, 16, 1024); dAl = make_desc(sA_lo + ks * 32, 16, 1024);
+                            dBh = make_desc(sB_hi + ks * 32, 16, 1024); dBl = make_desc(sB_lo + ks * 32, 16, 1024);
+                        }
+                        const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                        umma_tf32(tacc, dAl, dBh, idesc, first);           // small terms first
+                        umma_tf32(tacc, dAh, dBl, idesc, 1u);
+                        umma_tf32(tacc, dAh, dBh, idesc, 1u);
+                    }
+                    umma_commit(empty_bar(s));                              // stage free once these MMAs have read it
+                    if (kb == nkb - 1) umma_commit(acc_full(b));            // accumulator complete
+                }
+                stamp();
+                __syncwarp();
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ================================ epilogue (warps 9-12; warp w owns TMEM lanes 32*(w%4) .. +31) ================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                       // TMEM lane = accumulator row
+        float* stg = reinterpret_cast<float*>(epi_stage + (warp - 9) * (TC_EPI_BYTES / 4));   // 32 rows x 16 floats
+        bool alive = true;
+        int tl = 0;
+        for (int w = blockIdx.x; w < nwork && alive; w += gridDim.x, ++tl) {
+            TC_ITEM_GEOMETRY(w)
+            const int b = tl & 1;
+            alive = mbar_wait(acc_full(b), (uint32_t)((tl >> 1) & 1), a.err);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + (uint32_t)(b * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16);
             if (MODE == TC_DW) {
                 // partial stored transposed, [n][p]: lanes = consecutive p -> coalesced 128-byte stores
                 const int p = m0 + row;
@@ -414,79 +513,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
                     if (p < a.Kp) {
                         float* dst = a.dWpart + (size_t)item * a.Kp * a.Np + (size_t)(n0 + c0) * a.Kp + p;
 #pragma unroll
-                        for (int q = 0; q < 32; ++q)
-                            if (c0 + q < nlen) dst[(size_t)q * a.Kp] = v[q];
+                        for (int qq = 0; qq < 32; ++qq)
+                            if (c0 + qq < nlen) dst[(size_t)qq * a.Kp] = v[qq];
                     }
                 }
             } else {
-                // all MMAs have completed, so the pipeline stages are free: stage the tile in shared memory
-                // (row pitch nlen+4 floats) and write it out with fully coalesced 16-byte stores
-                const int pitch = nlen + 4;
-                float* stg = reinterpret_cast<float*>(smem);
-                for (int c0 = 0; c0 < nlen && alive; c0 += 32) {
-                    float v[32];
-                    tmem_ld16_issue(trow + c0, v);
-                    if (c0 + 16 < nlen) tmem_ld16_issue(trow + c0 + 16, v + 16);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (c0 + 4 * q < nlen)
-                            *reinterpret_cast<float4*>(stg + (size_t)row * pitch + c0 + 4 * q) =
-                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                }
-                epi_bar_sync();
-                const int c4n = nlen >> 2;                       // <= 40 float4 per row: lanes, then lanes 0..7 again
+                // 16-column slabs through the warp's private staging tile (XOR-swizzled 16-byte chunks, conflict-free
+                // per quarter warp), written out as 64-byte row segments: 8 rows x 2 full sectors per store instruction
                 float* out = (MODE == TC_FWD) ? a.T : a.GA;
                 const int ldo = (MODE == TC_FWD) ? a.Np : a.Kp;
-                for (int rr = gw; rr < rows; rr += 4) {          // one warp per row: contiguous 16-byte stores
-                    float* orow = out + (size_t)(u0 + rr) * ldo + n0;
-                    const float* srow = stg + (size_t)rr * pitch;
-                    if (lane < c4n && n0 + 4 * lane < ldo)
-                        *reinterpret_cast<float4*>(orow + 4 * lane) = *reinterpret_cast<const float4*>(srow + 4 * lane);
-                    if (lane + 32 < c4n && n0 + 4 * (lane + 32) < ldo)
-                        *reinterpret_cast<float4*>(orow + 4 * (lane + 32)) = *reinterpret_cast<const float4*>(srow + 4 * (lane + 32));
-                }
-            }
-            stamp();
-        }
-        tc_fence_before();
-    } else {
-        // ================================ MMA issuer ================================
-        const uint32_t idesc = make_idesc(nlen, DW_MN ? 1 : 0, DW_MN ? 1 : 0);
-        bool alive = true;
-        for (int kb = 0; kb < nkb && alive; ++kb) {
-            const int s = kb % TC_STAGES;
-            const uint32_t ph = (kb / TC_STAGES) & 1;
-            alive = mbar_wait(full_bar(s), ph, a.err);
-            tc_fence_after();
-            stamp();
-            if (lane == 0 && alive) {
-                const uint32_t sA_hi = smem_u32(smem + s * TC_STAGE_BYTES);
-                const uint32_t sA_lo = sA_hi + TC_A_BYTES, sB_hi = sA_lo + TC_A_BYTES, sB_lo = sB_hi + TC_B_BYTES;
-                const int kleft = kext - kb * TC_BK;
-                const int nks = (kleft >= TC_BK) ? 4 : (kleft + 7) / 8;
-                for (int ks = 0; ks < nks; ++ks) {
-                    uint64_t dAh, dAl, dBh, dBl;
-                    if (DW_MN) {     // MN-major SWIZZLE_128B_BASE32B: k-step = 8 rows = 1024 B; MN atoms 4096 B apart; 4-row K groups 512 B apart
-                        dAh = make_desc(sA_hi + ks * 1024, 4096, 512, 1); dAl = make_desc(sA_lo + ks * 1024, 4096, 512, 1);
-                        dBh = make_desc(sB_hi + ks * 1024, 4096, 512, 1); dBl = make_desc(sB_lo + ks * 1024, 4096, 512, 1);
-                    } else {         // K-major: a k-step is 32 bytes inside the 128-byte swizzle row; 8-row groups are 1024 B apart
-                        dAh = make_desc(sA_hi + ks * 32, 16, 1024); dAl = make_desc(sA_lo + ks * 32, 16, 1024);
-                        dBh = make_desc(sB_hi + ks * 32, 16, 1024); dBl = make_desc(sB_lo + ks * 32, 16, 1024);
+                const int rr0 = lane >> 2, cc = lane & 3;
+                for (int c0 = 0; c0 < nlen; c0 += 16) {
+                    float v[16];
+                    tmem_ld16_issue(trow + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        *reinterpret_cast<float4*>(stg + lane * 16 + 4 * (jj ^ ((lane >> 1) & 3))) =
+                            make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = rr0 + 8 * i;
+                        const float4 x = *reinterpret_cast<const float4*>(stg + rr * 16 + 4 * (cc ^ ((rr >> 1) & 3)));
+                        const int col = n0 + c0 + 4 * cc;
+                        if (q * 32 + rr < rows && col < ldo)
+                            *reinterpret_cast<float4*>(out + (size_t)(u0 + q * 32 + rr) * ldo + col) = x;
                     }
-                    const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                    umma_tf32(tmem_base, dAl, dBh, idesc, first);      // small terms first
-                    umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
-                    umma_tf32(tmem_base, dAh, dBh, idesc, 1u);
+                    __syncwarp();
                 }
-                umma_commit(empty_bar(s));                              // stage free once these MMAs have read it
-                if (kb == nkb - 1) umma_commit(acc_bar);                // accumulator complete
             }
+            tc_fence_before();
+            mbar_arrive(acc_empty(b));                       // 128 arrivals: the accumulator may be overwritten
             stamp();
-            __syncwarp();
         }
-        tc_fence_before();
     }
+#undef TC_ITEM_GEOMETRY
+    tc_fence_before();
     __syncthreads();
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, TC_TMEM_COLS); }
 }
@@ -516,7 +579,9 @@ __device__ __forceinline__ void split1(float v, float& h, float& l) {
 }
 __global__ void __launch_bounds__(256) k_tc_w_prep(const float* __restrict__ theta, const uint8_t* __restrict__ side,
                                                    float* WT, float* W, float* WT_hi, float* WT_lo, float* W_hi, float* W_lo,
-                                                   NtnDims dm, int KpP, int KpN, int NpP) {
+                                                   NtnDims dm, int KpP, int KpN, int NpP, const int* __restrict__ u_rel,
+                                                   const int* __restrict__ u_e1, const int* __restrict__ u_e2, int Nu,
+                                                   int* __restrict__ t_anchor) {
     const int64_t nA = (int64_t)dm.R * dm.Np * KpP, nB = (int64_t)dm.R * KpN * NpP;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nA) {
@@ -534,6 +599,11 @@ __global__ void __launch_bounds__(256) k_tc_w_prep(const float* __restrict__ the
         const float v = waug_at(theta, dm, r, side[r] != 0, p, n);
         W[i] = v;
         if (W_hi) { float h, l; split1(v, h, l); W_hi[i] = h; W_lo[i] = l; }
+    } else if (i < nA + nB + Nu) {
+        // anchor entity of every unique triple under this evaluation's corrupt sides (NTN.java:146-156): the entity
+        // that is NOT replaced -- e1 when the tail is corrupted, e2 when the head is
+        const int u = (int)(i - nA - nB);
+        t_anchor[u] = side[u_rel[u]] != 0 ? u_e1[u] : u_e2[u];
     }
 }
 
@@ -577,7 +647,7 @@ static TcArgs tc_args(ntn_handle* h, bool chunks) {
     const DeviceBatch& b = h->b;
     TcArgs a{};
     a.t_rel = chunks ? b.ch_rel : b.t_rel; a.t_u0 = chunks ? b.ch_u0 : b.t_u0; a.t_n = chunks ? b.ch_n : b.t_n;
-    a.u_e1 = b.u_e1; a.u_e2 = b.u_e2; a.side = h->side; a.E = h->E; a.M = b.M;
+    a.u_e1 = b.u_e1; a.u_e2 = b.u_e2; a.t_anchor = st->t_anchor; a.side = h->side; a.E = h->E; a.M = b.M;
     a.WT = st->WT; a.W = st->W;
     a.T = b.T; a.GA = b.GA; a.dWpart = b.dWpart;
     a.Kp = h->dm.Kp; a.Np = h->dm.Np; a.KpP = st->KpP; a.KpN = st->KpN; a.NpP = st->NpP;
@@ -631,13 +701,24 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
             return NTN_ECUDA;
         }
     }
+    {
+        // per-evaluation anchor table, sized for this batch job
+        TcState* st = (TcState*)h->tc;
+        const size_t need = (size_t)std::max(h->b.Nu, 1);
+        if (st->anchor_cap < need) {
+            cudaFree(st->t_anchor); st->t_anchor = nullptr; st->anchor_cap = 0;
+            cudaError_t e = cudaMalloc((void**)&st->t_anchor, need * sizeof(int));
+            if (e != cudaSuccess) { h->err = std::string("tcgen05 anchor table: ") + cudaGetErrorString(e); return NTN_ECUDA; }
+            st->anchor_cap = need;
+        }
+    }
     return NTN_OK;
 }
 
 void ntn_tc_release(ntn_handle* h) {
     TcState* st = (TcState*)h->tc;
     if (!st) return;
-    cudaFree(st->WT); cudaFree(st->W); cudaFree(st->err); cudaFree(st->dbg);
+    cudaFree(st->WT); cudaFree(st->W); cudaFree(st->err); cudaFree(st->dbg); cudaFree(st->t_anchor);
     cudaFree(st->WT_hi); cudaFree(st->WT_lo); cudaFree(st->W_hi); cudaFree(st->W_lo);
     delete st;
     h->tc = nullptr;
@@ -646,17 +727,25 @@ void ntn_tc_release(ntn_handle* h) {
 int ntn_tc_w_prep(ntn_handle* h, const float* theta, cudaStream_t stq) {
     TcState* st = (TcState*)h->tc;
     const NtnDims& dm = h->dm;
-    int64_t n = (int64_t)dm.R * dm.Np * st->KpP + (int64_t)dm.R * st->KpN * st->NpP;
+    int64_t n = (int64_t)dm.R * dm.Np * st->KpP + (int64_t)dm.R * st->KpN * st->NpP + h->b.Nu;
     k_tc_w_prep<<<cdivi(n, 256), 256, 0, stq>>>(theta, h->side, st->WT, st->W, st->WT_hi, st->WT_lo, st->W_hi, st->W_lo, dm,
-                                                      st->KpP, st->KpN, st->NpP);
+                                                      st->KpP, st->KpN, st->NpP, h->b.u_rel, h->b.u_e1, h->b.u_e2, h->b.Nu, st->t_anchor);
     h->launches++;
     return NTN_OK;
+}
+
+// persistent grid: one CTA per SM walks the work items round-robin (NTN_TC_PERSIST=0: one CTA per item)
+static dim3 tc_grid(ntn_handle* h, TcArgs& a, int nitems, int ny, int nz) {
+    static const bool persist = [] { const char* e = getenv("NTN_TC_PERSIST"); return !(e && e[0] == '0'); }();
+    a.nitems = nitems; a.ny = ny; a.nz = nz;
+    const int64_t nwork = (int64_t)nitems * ny * nz;
+    return dim3((unsigned)std::max<int64_t>(1, persist ? std::min<int64_t>(nwork, h->sm_count) : nwork));
 }
 
 int ntn_tc_gemm_fwd(ntn_handle* h) {
     TcArgs a = tc_args(h, false);
     TcState* st = (TcState*)h->tc;
-    dim3 g(h->b.ntiles, cdivi(h->dm.Np, TC_NCH));
+    dim3 g = tc_grid(h, a, h->b.ntiles, cdivi(h->dm.Np, TC_NCH), 1);
     if (st->use_tma) {
         a.b_rows_per_rel = h->dm.Np; a.b_box_rows = st->box_fwd;
         k_tc_gemm<TC_FWD, true><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mWT_hi, st->mWT_lo);
@@ -669,7 +758,7 @@ int ntn_tc_gemm_fwd(ntn_handle* h) {
 
 int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t stq) {
     TcArgs a = tc_args(h, true);
-    dim3 g(h->b.nchunks, cdivi(h->dm.Np, TC_NCH), cdivi(h->dm.Kp, 128));
+    dim3 g = tc_grid(h, a, h->b.nchunks, cdivi(h->dm.Np, TC_NCH), cdivi(h->dm.Kp, 128));
     TcState* st = (TcState*)h->tc;
     if (st->dw_mn) k_tc_gemm<TC_DW, false, true><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo);
     else k_tc_gemm<TC_DW, false><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo);
@@ -680,7 +769,7 @@ int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t stq) {
 int ntn_tc_gemm_ge(ntn_handle* h) {
     TcArgs a = tc_args(h, false);
     TcState* st = (TcState*)h->tc;
-    dim3 g(h->b.ntiles, cdivi(st->KpN, TC_NCH));
+    dim3 g = tc_grid(h, a, h->b.ntiles, cdivi(st->KpN, TC_NCH), 1);
     if (st->use_tma) {
         a.b_rows_per_rel = st->KpN; a.b_box_rows = st->box_ge;
         k_tc_gemm<TC_GE, true><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mW_hi, st->mW_lo);
