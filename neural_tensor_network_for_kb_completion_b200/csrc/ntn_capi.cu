@@ -809,12 +809,24 @@ template <typename D> static cudaError_t download_pipelined(ntn_handle* h, const
         if (e != cudaSuccess) return e;
         cudaEventRecord(h->xfer_ev[i], h->stream);
     }
+    static const bool timing = getenv("NTN_TIMING") != nullptr;
+    double t_wait = 0, t_conv = 0;
     for (int i = 0; i < nchunks; ++i) {
         int64_t o = (int64_t)i * NTN_XFER_CHUNK, c = std::min<int64_t>(NTN_XFER_CHUNK, n - o);
-        cudaError_t e = cudaEventSynchronize(h->xfer_ev[i]);
+        const auto a0 = std::chrono::steady_clock::now();
+        // poll instead of a blocking wait: a chunk is ~70 us of DMA, the wake-up of a blocked thread is of that order
+        cudaError_t e;
+        while ((e = cudaEventQuery(h->xfer_ev[i])) == cudaErrorNotReady) {}
         if (e != cudaSuccess) return e;
+        const auto a1 = std::chrono::steady_clock::now();
         convert_range(h->h_stage + o, dst + o, c);
+        if (timing) {
+            const auto a2 = std::chrono::steady_clock::now();
+            t_wait += std::chrono::duration<double, std::milli>(a1 - a0).count();
+            t_conv += std::chrono::duration<double, std::milli>(a2 - a1).count();
+        }
     }
+    if (timing) fprintf(stderr, "[download] %d chunks: waiting for DMA %.3f ms, converting %.3f ms\n", nchunks, t_wait, t_conv);
     return cudaSuccess;
 }
 
@@ -837,15 +849,28 @@ static int eval_host(ntn_handle* h, const TH* theta, const uint8_t* corrupt_side
     int rc = ensure_host_path(h);
     if (rc) return rc;
     const NtnDims& dm = h->dm;
+    static const bool timing = getenv("NTN_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
     CK(cudaStreamSynchronize(h->stream));
+    const auto t0 = now();
     CK(upload_pipelined(h, theta, h->d_ref_theta, dm.P));
+    const auto t1 = now();
     ntn_launch_to_internal(h, h->d_ref_theta, h->d_int_theta);
     rc = eval_internal(h, h->d_int_theta, corrupt_side, h->d_int_grad);
     if (rc) return rc;
     int launches = h->launches + 2;
     ntn_launch_from_internal(h, h->d_int_grad, h->d_ref_grad);
     h->launches = launches + 2;
+    if (timing) cudaStreamSynchronize(h->stream);
+    const auto t2 = now();
     CK(download_pipelined(h, h->d_ref_grad, grad, dm.P));
+    const auto t3 = now();
+    if (timing)
+        fprintf(stderr, "[ntn_eval] convert+enqueue upload %.3f ms, H2D tail + evaluation %.3f ms, D2H + convert %.3f ms\n",
+                ms(t0, t1), ms(t1, t2), ms(t2, t3));
     return ntn_last_cost(h, cost, n_active);
 }
 
