@@ -213,6 +213,8 @@ def main():
     ap.add_argument("--wv-source", default="theta", choices=["theta", "frozen"])
     ap.add_argument("--gemm-path", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline", action="store_true",
+                    help="time the CPU port also on c4/c5 (one c4 evaluation is ~1 min of CPU; c5 is tens of minutes)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     args = ap.parse_args()
@@ -418,7 +420,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 only): one full evaluation by the oracle port ---------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and (args.config in ("c1", "c3") or args.cpu_baseline):
         from oracle import ntn_ref                                  # checker / baseline only
         p = ntn_ref.NTNProblem(d=D, k=K_SLICES, R=kb.R, Ne=kb.Ne, Nw=kb.Nw, lam=LAMBDA, batch_size=BATCH,
                                fwd_off=maps[0], fwd_idx=maps[1], bwd_off=maps[2], bwd_idx=maps[3], len_bwd=maps[4])
