@@ -244,7 +244,9 @@ def main():
     else:
         torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.Stream(device=dev)          # everything (kernels, NCCL, timing events) on this stream
+    prio = -1 if os.environ.get("NTN_STREAM_PRIORITY", "1") != "0" else 0
+    stream = torch.cuda.Stream(device=dev, priority=prio)   # everything (kernels, NCCL, timing events) on this stream; the
+    #                                                         library's forked branches run on lowest-priority streams
     torch.cuda.set_stream(stream)
 
     kb = build_problem(world)

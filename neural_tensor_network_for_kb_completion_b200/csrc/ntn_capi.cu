@@ -127,9 +127,15 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
         h->err = "this library is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
         return bail(NTN_ECUDA);
     }
-    CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+    // the main chain (forward -> score -> entity gradient -> pulls) is the critical path of an evaluation; the forked
+    // branches (weight prep / dW contraction / finalize, hub words) only have to finish before the final reduce.  The
+    // chain's stream gets the highest priority and the branches the lowest, so that free SM slots go to the chain first.
+    int prio_lo = 0, prio_hi = 0;
+    CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));      // numerically: hi <= lo
+    static const bool use_prio = [] { const char* e = getenv("NTN_STREAM_PRIORITY"); return !(e && e[0] == '0'); }();
+    CKC(cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
+    CKC(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo));
+    CKC(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prio_lo));
     CKC(cudaEventCreateWithFlags(&h->ev_f0, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_j0, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_f1, cudaEventDisableTiming));
