@@ -559,8 +559,9 @@ __device__ __forceinline__ float4 pull_range(const PullArgs& a, int j0, int j1, 
             for (int i = 0; i < NB; ++i) {
                 const bool ok = jb + i < j1;
                 const int4 rec = ok ? __ldg(a.inc + jb + i) : make_int4(0, 0, 2, 0);
-                const bool tail = a.side[rec.w] != 0;
-                const bool anchor = (rec.z == 0 && tail) || (rec.z == 1 && !tail);
+                // a corrupt incident (role 2, >90 % of them) is never the anchor: the side flag is only looked up for
+                // the e1 / e2 roles, so the common chain is record -> rows, not record -> flag -> rows
+                const bool anchor = rec.z != 2 && ((a.side[rec.w] != 0) == (rec.z == 0));
                 rows[i] = ok ? ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : a.GV + (size_t)rec.y * a.dq + c * 4) : zero4();
             }
 #pragma unroll
@@ -576,8 +577,7 @@ __device__ __forceinline__ float4 pull_range(const PullArgs& a, int j0, int j1, 
             for (int i = 0; i < NB; ++i) {
                 const bool ok = jb + i < j1;
                 const int4 rec = ok ? __ldg(a.inc + jb + i) : make_int4(0, 0, 2, 0);
-                const bool tail = a.side[rec.w] != 0;
-                const bool anchor = ok && ((rec.z == 0 && tail) || (rec.z == 1 && !tail));
+                const bool anchor = ok && rec.z != 2 && ((a.side[rec.w] != 0) == (rec.z == 0));
                 // coefficient and row loads are issued together: gating the rows on "any coefficient non-zero"
                 // (inactive column, NTN.java:229-239) would add one more dependent round trip to every incident
 #pragma unroll
