@@ -96,3 +96,34 @@ def test_host_java_random_is_bit_exact_with_oracle():
     assert a.nextInts(2000, 75043).tolist() == [b.next_int(75043) for _ in range(2000)]
     assert [a.nextDouble() for _ in range(50)] == [b.next_double() for _ in range(50)]
     assert a.nextInts(100, 1024).tolist() == [b.next_int(1024) for _ in range(100)]
+
+
+@pytest.mark.parametrize("sampler", ["reference", "shuffle", "device", "device-filter"])
+def test_run_ntn_binary_with_every_sampler(tmp_path, sampler):
+    """The compiled host (csrc/host/run_ntn.cpp = Run_NTN.main, Run_NTN.java:38-150) end to end on Socher-format
+    files, once per sampler variant: the reference's seeded java.util.Random job, the re-enabled shuffle, and the
+    on-device counter-based sampler without / with true-triple filtering."""
+    import subprocess
+    import neural_tensor_network_for_kb_completion_b200 as pkg
+    exe = os.path.join(os.path.dirname(pkg.__file__), "run_ntn")
+    if not os.path.exists(exe):
+        pytest.skip("run_ntn binary not built")
+    kb = synth.make_structured_kb(Ne=200, R=3, T=500, d=100, clusters=8, n_dev=60, n_test=60, seed=4)
+    d = str(tmp_path)
+    open(os.path.join(d, "entities.txt"), "w").write("\n".join(kb.entity_names) + "\n")
+    open(os.path.join(d, "relations.txt"), "w").write("\n".join(kb.relations) + "\n")
+    name = lambda t: f"{kb.entity_names[t[0]]}\t{kb.relations[t[1]]}\t{kb.entity_names[t[2]]}"
+    open(os.path.join(d, "train.txt"), "w").write("\n".join(name(t) for t in kb.train) + "\n")
+    for fn, arr in (("dev.txt", kb.dev), ("test.txt", kb.test)):
+        open(os.path.join(d, fn), "w").write("\n".join(name(t) + f"\t{t[3]}" for t in arr) + "\n")
+    with open(os.path.join(d, "wordvectors.txt"), "w") as f:
+        for i, w in enumerate(kb.vocab_words):
+            f.write(w + " " + " ".join(f"{x:.8g}" for x in kb.wv[:, i]) + "\n")
+    r = subprocess.run([exe, d, d, d, "2", sampler], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Accuracy of predictions:" in r.stdout and "Model saved!" in r.stdout
+    acc = float(r.stdout.split("Accuracy of predictions:")[1].split()[0])
+    assert 0.0 <= acc <= 1.0
+    costs = [float(l.split("|")[1]) for l in r.stdout.splitlines() if l.startswith("res:")]
+    assert len(costs) == 2 and all(np.isfinite(costs))
+    assert os.path.exists(os.path.join(d, "theta_opt_iteration_0.txt"))
