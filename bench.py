@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "25"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.rows.append(l) for l in self.p.stdout], daemon=True)
             self.t.start()
@@ -226,7 +226,7 @@ def main():
         args.steps = 3 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
         return run_reference(args)
-    args.steps = 200 if args.steps is None else args.steps
+    args.steps = 1000 if args.steps is None else args.steps        # ~0.25 s timed region at the headline config: enough clock samples
     args.warmup = max(3, 10 if args.warmup is None else args.warmup)
 
     import torch
