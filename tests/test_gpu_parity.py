@@ -483,3 +483,71 @@ def test_training_loop_with_device_sampler():
     for a, b in zip(cols, want):
         np.testing.assert_array_equal(a, b)
     t.close()
+
+
+def test_full_size_freebase_shape_properties():
+    """BASELINE.json configs[2] (the headline: Freebase shape, 75,043 entities, 13 relations, d=100, k=3, 20,000 triples
+    x 10 corrupt) is too slow for the float64 oracle in a test, so it is checked through size-independent properties:
+      1. bit-reproducibility (no float atomics anywhere);
+      2. linearity over shards: 4 handles with reg_scale = 1/4 on disjoint shards sum to the full result
+         (the data-parallel decomposition, SURVEY §8e);
+      3. the gradient is the derivative of the cost: central difference of the COST along a random direction and along
+         the gradient direction against g.v (FP32 cost, so a loose tolerance; hinge kinks only move it slightly);
+      4. an empty-relation / regulariser identity: d cost / d theta restricted to words no entity uses equals lambda*theta."""
+    from neural_tensor_network_for_kb_completion_b200 import synth
+    from neural_tensor_network_for_kb_completion_b200.data_factory import DataFactory
+    from neural_tensor_network_for_kb_completion_b200.distributed import shard_columns
+    kb = synth.make_shaped("freebase", d=100, Nw=67447, T=20000, seed=0)
+    tbj = DataFactory.from_kb(kb, 20000, 10, seed=42)
+    maps = tbj.entityWordMaps()
+    batch = tbj.generateNewTrainingBatchJob()
+    lam, B = 1e-4, 20000
+
+    def handle(reg_scale=1.0):
+        h = _capi.Handle(100, 3, kb.R, kb.Ne, kb.Nw, B, lam, wv_source="theta", reg_scale=reg_scale)
+        h.set_entity_words(*maps)
+        return h
+    h = handle()
+    h.set_batch(*batch)
+    assert h.gemm_path == "tcgen05"
+    rng = np.random.default_rng(5)
+    r = 1.0 / np.sqrt(200.0)
+    theta = np.concatenate([rng.random(kb.R * 3 * 100 * 100) * r, np.full(kb.R * 600, 0.4), np.full(kb.R * 3, 0.01),
+                            np.full(kb.R * 3, 0.8), kb.wv.astype(np.float64).ravel()])
+    theta = f32(theta + rng.standard_normal(theta.size) * 0.05)
+    side = data_ref.draw_corrupt_sides(batch[1], kb.R, JavaRandom(7))
+    c, g, n = h.eval(theta, side)
+    assert 0 < n < 200000 and np.isfinite(c) and np.all(np.isfinite(g))
+    # 1. reproducible
+    c2, g2, n2 = h.eval(theta, side)
+    assert c == c2 and n == n2 and np.array_equal(g, g2)
+    # 2. shard linearity
+    G = 4
+    acc_c, acc_g, acc_n = 0.0, np.zeros_like(g), 0
+    for rank in range(G):
+        hr = handle(1.0 / G)
+        hr.set_batch(*shard_columns(*batch, rank, G))
+        cr, gr, nr = hr.eval(theta, side)
+        acc_c += cr; acc_g += gr; acc_n += nr
+        hr.close()
+    assert acc_n == n and acc_c == pytest.approx(c, rel=2e-6)
+    assert np.allclose(acc_g, g, rtol=1e-4, atol=2e-7)
+    # 3. directional derivatives
+    for v in (rng.standard_normal(theta.size), g.copy()):
+        v /= np.linalg.norm(v)
+        eps = 2e-3
+        cp = h.eval(f32(theta + eps * v), side)[0]
+        cm = h.eval(f32(theta - eps * v), side)[0]
+        th_p, th_m = f32(theta + eps * v), f32(theta - eps * v)
+        fd = (cp - cm) / float(np.dot(th_p - th_m, v))
+        gv = float(np.dot(g, v))
+        assert abs(fd - gv) <= 2e-2 * max(abs(gv), 0.05), (fd, gv)
+    # 4. unused words see the regulariser only
+    used = np.zeros(kb.Nw, bool)
+    used[maps[3]] = True                                           # backward word lists (NTN.java:414-426)
+    unused = np.nonzero(~used)[0][:200]
+    oWV = theta.size - 100 * kb.Nw
+    for w in unused[:50]:
+        idx = oWV + np.arange(100) * kb.Nw + w                     # word block is d x Nw row-major (NTN.java:450-481)
+        assert np.allclose(g[idx], lam * theta[idx], rtol=1e-5, atol=1e-12)
+    h.close()
