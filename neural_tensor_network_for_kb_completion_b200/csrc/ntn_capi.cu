@@ -117,6 +117,10 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
     h->dm = make_dims(*cfg);
     h->device = cfg->device;
     h->use_graph = getenv("NTN_NO_GRAPH") == nullptr;
+    if (getenv("NTN_GRAPH_TIMELINE")) {
+        if (cudaMalloc((void**)&h->d_stamps, 2 * NTN_NUM_PHASES * sizeof(unsigned long long)) != cudaSuccess) h->d_stamps = nullptr;
+        else cudaMemset(h->d_stamps, 0, 2 * NTN_NUM_PHASES * sizeof(unsigned long long));
+    }
     auto bail = [&](int rc) { g_create_err = h->err; ntn_destroy(h); return rc; };
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(NTN_ECUDA); } } while (0)
     CKC(cudaSetDevice(h->device));
@@ -187,6 +191,7 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     dev_free(h->reg_part); dev_free(h->d_out); dev_free(h->d_ref_theta); dev_free(h->d_ref_grad);
     dev_free(h->d_int_theta); dev_free(h->d_int_grad);
     if (h->lbfgs_ws) cudaFree(h->lbfgs_ws);
+    if (h->d_stamps) cudaFree(h->d_stamps);
     if (h->bi_ws) cudaFree(h->bi_ws);
     if (h->h_meta) cudaFreeHost(h->h_meta);
     if (h->h_cols) cudaFreeHost(h->h_cols);
@@ -607,9 +612,24 @@ extern "C" int ntn_set_batch_dev(ntn_handle* h, int64_t n, const int32_t* d_e1, 
 
 // Enqueue the kernels of one evaluation on h->stream with its forked branches (also what gets captured
 // into the CUDA graph).  prof: bracket every phase with its own event pair.
+// NTN_GRAPH_TIMELINE=1: one-thread kernels that store %globaltimer before and after every kernel group, also inside the
+// captured graph -- the only way to see how the forked branches really interleave under graph replay (the event
+// brackets of the profiling mode launch the kernels outside the graph).  Fetched with ntn_debug_fetch("graph_timeline").
+__global__ void k_stamp(unsigned long long* dst) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *dst = t;
+}
+
 static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_grad, const float* wvt, bool prof, int slot) {
-    auto begin = [&](int p, cudaStream_t st) { if (prof) cudaEventRecord(h->ev[slot][p][0], st); };
-    auto end = [&](int p, cudaStream_t st) { if (prof) cudaEventRecord(h->ev[slot][p][1], st); };
+    auto begin = [&](int p, cudaStream_t st) {
+        if (prof) cudaEventRecord(h->ev[slot][p][0], st);
+        if (h->d_stamps) k_stamp<<<1, 1, 0, st>>>(h->d_stamps + 2 * p);
+    };
+    auto end = [&](int p, cudaStream_t st) {
+        if (prof) cudaEventRecord(h->ev[slot][p][1], st);
+        if (h->d_stamps) k_stamp<<<1, 1, 0, st>>>(h->d_stamps + 2 * p + 1);
+    };
     enum { P_EB, P_WP, P_FWD, P_SC, P_DW, P_GE, P_EP, P_WPULL, P_FIN };
     cudaStream_t s0 = h->stream, s1 = h->stream3;
     const bool tc = h->gemm_path_active == NTN_GEMM_TCGEN05 && h->b.ntiles > 0;
@@ -930,6 +950,18 @@ extern "C" int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, 
     else if (s == "E") { src = h->E; n = (int64_t)dm.Ne * dm.Kp; }
     else if (s == "gE") { src = h->gE; n = (int64_t)dm.Ne * dm.dq; }
     else if (s == "tc_timeline") return ntn_tc_fetch_timeline(h, out, cap);
+    else if (s == "graph_timeline") {
+        // begin/end of every kernel group of the LAST evaluation, microseconds relative to the earliest stamp
+        if (!h->d_stamps) return 0;
+        const int m = 2 * NTN_NUM_PHASES;
+        if (out && cap >= m) {
+            unsigned long long t[2 * NTN_NUM_PHASES], t0 = ~0ull;
+            cudaMemcpy(t, h->d_stamps, sizeof(t), cudaMemcpyDeviceToHost);
+            for (int i = 0; i < m; ++i) if (t[i] && t[i] < t0) t0 = t[i];
+            for (int i = 0; i < m; ++i) out[i] = t[i] ? (float)((double)(t[i] - t0) * 1e-3) : -1.f;
+        }
+        return m;
+    }
     else if (s.rfind("i:", 0) == 0) {
         // integer batch tables, copied bit for bit (the caller views the buffer as int32)
         const int* isrc = nullptr;

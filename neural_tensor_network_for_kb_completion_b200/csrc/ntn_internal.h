@@ -129,6 +129,7 @@ struct ntn_handle {
     bool ev_pending[NTN_RING] = {};
     double phase_acc[NTN_NUM_PHASES] = {};
     int phase_n = 0;
+    unsigned long long *d_stamps = nullptr;   // NTN_GRAPH_TIMELINE: %globaltimer at begin/end of every kernel group
     void *tc = nullptr;           // tcgen05 path state (gemm_tcgen05.cu)
     void *bi_ws = nullptr;        // batch-index workspace (batch_index.cu), grow-only
     size_t bi_ws_bytes = 0;
