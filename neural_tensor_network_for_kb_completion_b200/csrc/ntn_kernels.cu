@@ -402,6 +402,9 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
                 tp[s] = act_diff<ACT>(zp[s]) * U[s];                  // :280
             }
         }
+        // the next triple's corrupt ids: its range (requested at the top of this iteration) has arrived by now, and the
+        // ids have the whole corrupt-column loop below to land
+        if (i + 8 < rows) nx_e3 = (nx_c0 + lane < nx_c1) ? __ldg(a.c_e3 + nx_c0 + lane) : 0;
         float my_zp = 0.f;
 #pragma unroll
         for (int s = 0; s < KS; ++s) my_zp += zp[s] * (my_s == s);
@@ -474,7 +477,6 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
                 }
             }
         }
-        if (i + 8 < rows) nx_e3 = (nx_c0 + lane < nx_c1) ? __ldg(a.c_e3 + nx_c0 + lane) : 0;
         float* Mrow = a.M + (size_t)u * a.Np;
         float4 gvo[CH];
 #pragma unroll
