@@ -811,10 +811,23 @@ extern "C" int ntn_host_convert_f32_f64(const float* src, double* dst, int64_t n
     return NTN_OK;
 }
 
+// chunk boundaries of a pipelined transfer: the first chunks are small (the pipeline fills quickly: what is exposed is
+// one conversion before the first copy and one copy before the first conversion), then they double up to NTN_XFER_CHUNK
+static std::vector<int64_t> xfer_chunks(int64_t n) {
+    std::vector<int64_t> off{0};
+    int64_t c = std::min<int64_t>(NTN_XFER_CHUNK, (int64_t)1 << 18);
+    while (off.back() < n) {
+        off.push_back(std::min(n, off.back() + c));
+        c = std::min<int64_t>(NTN_XFER_CHUNK, c * 2);
+    }
+    return off;
+}
+
 // theta (host, S) -> pinned float staging -> device, chunk-pipelined
 template <typename S> static cudaError_t upload_pipelined(ntn_handle* h, const S* src, float* d_dst, int64_t n) {
-    for (int64_t o = 0; o < n; o += NTN_XFER_CHUNK) {
-        int64_t c = std::min<int64_t>(NTN_XFER_CHUNK, n - o);
+    const std::vector<int64_t> off = xfer_chunks(n);
+    for (size_t i = 0; i + 1 < off.size(); ++i) {
+        const int64_t o = off[i], c = off[i + 1] - o;
         convert_range(src + o, h->h_stage + o, c);
         cudaError_t e = cudaMemcpyAsync(d_dst + o, h->h_stage + o, (size_t)c * sizeof(float), cudaMemcpyHostToDevice, h->stream);
         if (e != cudaSuccess) return e;
@@ -823,14 +836,15 @@ template <typename S> static cudaError_t upload_pipelined(ntn_handle* h, const S
 }
 // device -> pinned float staging -> host (D), chunk-pipelined on the handle's stream
 template <typename D> static cudaError_t download_pipelined(ntn_handle* h, const float* d_src, D* dst, int64_t n) {
-    const int nchunks = (int)((n + NTN_XFER_CHUNK - 1) / NTN_XFER_CHUNK);
+    const std::vector<int64_t> off = xfer_chunks(n);
+    const int nchunks = (int)off.size() - 1;
     if ((int)h->xfer_ev.size() < nchunks) {
         size_t old = h->xfer_ev.size();
         h->xfer_ev.resize(nchunks);
         for (size_t i = old; i < h->xfer_ev.size(); ++i) cudaEventCreateWithFlags(&h->xfer_ev[i], cudaEventDisableTiming);
     }
     for (int i = 0; i < nchunks; ++i) {
-        int64_t o = (int64_t)i * NTN_XFER_CHUNK, c = std::min<int64_t>(NTN_XFER_CHUNK, n - o);
+        const int64_t o = off[i], c = off[i + 1] - o;
         cudaError_t e = cudaMemcpyAsync(h->h_stage + o, d_src + o, (size_t)c * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
         if (e != cudaSuccess) return e;
         cudaEventRecord(h->xfer_ev[i], h->stream);
@@ -838,7 +852,7 @@ template <typename D> static cudaError_t download_pipelined(ntn_handle* h, const
     static const bool timing = getenv("NTN_TIMING") != nullptr;
     double t_wait = 0, t_conv = 0;
     for (int i = 0; i < nchunks; ++i) {
-        int64_t o = (int64_t)i * NTN_XFER_CHUNK, c = std::min<int64_t>(NTN_XFER_CHUNK, n - o);
+        const int64_t o = off[i], c = off[i + 1] - o;
         const auto a0 = std::chrono::steady_clock::now();
         // poll instead of a blocking wait: a chunk is ~70 us of DMA, the wake-up of a blocked thread is of that order
         cudaError_t e;
