@@ -548,54 +548,57 @@ struct PullArgs {
     int Ne, dq, Kp, Np, n_segs;
 };
 
+// One batch of N incidents, all valid: records first, then every row / coefficient load of the batch (latency overlaps),
+// then the FMAs in incident order (deterministic).
+template <int KS, bool GVR, int N>
+__device__ __forceinline__ void pull_batch(const PullArgs& a, int jb, int c, float4& acc) {
+    if (GVR) {
+        float4 rows[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int4 rec = __ldg(a.inc + jb + i);
+            // a corrupt incident (role 2, >90 % of them) is never the anchor: the side flag is only looked up for
+            // the e1 / e2 roles, so the common chain is record -> rows, not record -> flag -> rows
+            const bool anchor = rec.z != 2 && ((a.side[rec.w] != 0) == (rec.z == 0));
+            rows[i] = ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : a.GV + (size_t)rec.y * a.dq + c * 4);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { acc.x += rows[i].x; acc.y += rows[i].y; acc.z += rows[i].z; acc.w += rows[i].w; }
+    } else {
+        float co[N][KS]; float4 rows[N][KS];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int4 rec = __ldg(a.inc + jb + i);
+            const bool anchor = rec.z != 2 && ((a.side[rec.w] != 0) == (rec.z == 0));
+            // coefficient and row loads are issued together: gating the rows on "any coefficient non-zero"
+            // (inactive column, NTN.java:229-239) would add one more dependent round trip to every incident
+            const float* Trow = a.T + (size_t)rec.x * a.Np + c * 4;
+            const float* crow = a.coef + (size_t)rec.y * KS;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) co[i][s] = anchor ? 0.f : __ldg(crow + s);
+            rows[i][0] = ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : Trow);
+#pragma unroll
+            for (int s = 1; s < KS; ++s) rows[i][s] = anchor ? zero4() : ldg4(Trow + s * a.dq);
+            if (anchor) co[i][0] = 1.f;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int s = 0; s < KS; ++s) fma4(acc, co[i][s], rows[i][s]);
+    }
+}
+
 // GVR = true : every non-anchor incident reads ONE materialised row (large batches: T' does not fit in L2)
 // GVR = false: it reads its coefficients and the k T' rows (small batches: T' is L2-resident, k_score stays lean)
+// Full batches run without per-incident predicates (the kernel is issue-bound: 62 % issue-active, a fifth of it address
+// arithmetic and zero-filling of the predicated tail); the remainder goes one incident at a time.
 template <int KS, bool GVR>
 __device__ __forceinline__ float4 pull_range(const PullArgs& a, int j0, int j1, int c) {
+    constexpr int NB = GVR ? 4 : ((KS <= 4) ? 2 : 1);               // incidents in flight (ILP)
     float4 acc = zero4();
-    if (GVR) {
-        constexpr int NB = 4;                                        // incidents in flight (ILP)
-        for (int jb = j0; jb < j1; jb += NB) {
-            float4 rows[NB];
-#pragma unroll
-            for (int i = 0; i < NB; ++i) {
-                const bool ok = jb + i < j1;
-                const int4 rec = ok ? __ldg(a.inc + jb + i) : make_int4(0, 0, 2, 0);
-                // a corrupt incident (role 2, >90 % of them) is never the anchor: the side flag is only looked up for
-                // the e1 / e2 roles, so the common chain is record -> rows, not record -> flag -> rows
-                const bool anchor = rec.z != 2 && ((a.side[rec.w] != 0) == (rec.z == 0));
-                rows[i] = ok ? ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : a.GV + (size_t)rec.y * a.dq + c * 4) : zero4();
-            }
-#pragma unroll
-            for (int i = 0; i < NB; ++i) {                           // incident order: deterministic
-                acc.x += rows[i].x; acc.y += rows[i].y; acc.z += rows[i].z; acc.w += rows[i].w;
-            }
-        }
-    } else {
-        constexpr int NB = (KS <= 4) ? 2 : 1;
-        for (int jb = j0; jb < j1; jb += NB) {
-            float co[NB][KS]; float4 rows[NB][KS];
-#pragma unroll
-            for (int i = 0; i < NB; ++i) {
-                const bool ok = jb + i < j1;
-                const int4 rec = ok ? __ldg(a.inc + jb + i) : make_int4(0, 0, 2, 0);
-                const bool anchor = ok && rec.z != 2 && ((a.side[rec.w] != 0) == (rec.z == 0));
-                // coefficient and row loads are issued together: gating the rows on "any coefficient non-zero"
-                // (inactive column, NTN.java:229-239) would add one more dependent round trip to every incident
-#pragma unroll
-                for (int s = 0; s < KS; ++s) co[i][s] = (ok && !anchor) ? __ldg(a.coef + (size_t)rec.y * KS + s) : 0.f;
-                const float* Trow = a.T + (size_t)rec.x * a.Np + c * 4;
-                rows[i][0] = ok ? ldg4(anchor ? a.GA + (size_t)rec.x * a.Kp + c * 4 : Trow) : zero4();
-#pragma unroll
-                for (int s = 1; s < KS; ++s) rows[i][s] = (ok && !anchor) ? ldg4(Trow + s * a.dq) : zero4();
-                if (anchor) co[i][0] = 1.f;
-            }
-#pragma unroll
-            for (int i = 0; i < NB; ++i)                             // incident order: deterministic
-#pragma unroll
-                for (int s = 0; s < KS; ++s) fma4(acc, co[i][s], rows[i][s]);
-        }
-    }
+    int jb = j0;
+    for (; jb + NB <= j1; jb += NB) pull_batch<KS, GVR, NB>(a, jb, c, acc);
+    for (; jb < j1; ++jb) pull_batch<KS, GVR, 1>(a, jb, c, acc);
     return acc;
 }
 
