@@ -658,24 +658,28 @@ struct WordArgs {
     float inv_B, lam;
 };
 
+// one batch of N entities of a word's list, all valid: loads first, then the adds in entity order (NTN.java:414-426)
+template <int N>
+__device__ __forceinline__ void word_batch(const WordArgs& a, int jb, int c, float4& acc) {
+    float4 v[N]; float inv[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int n = __ldg(a.w_ent + jb + i);
+        inv[i] = 1.0f / __ldg(a.len_bwd + n);                        // :420 (one division per entity, not per component)
+        v[i] = ldg4(a.gE + (size_t)n * a.dq + c * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        acc.x = fmaf(v[i].x, inv[i], acc.x); acc.y = fmaf(v[i].y, inv[i], acc.y);
+        acc.z = fmaf(v[i].z, inv[i], acc.z); acc.w = fmaf(v[i].w, inv[i], acc.w);
+    }
+}
 template <int NB>                                                    // entities in flight (ILP)
 __device__ __forceinline__ float4 word_range(const WordArgs& a, int j0, int j1, int c) {
     float4 acc = zero4();
-    for (int jb = j0; jb < j1; jb += NB) {
-        float4 v[NB]; float len[NB];
-#pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            const bool ok = jb + i < j1;
-            const int n = ok ? __ldg(a.w_ent + jb + i) : 0;
-            len[i] = ok ? __ldg(a.len_bwd + n) : 1.f;
-            v[i] = ok ? ldg4(a.gE + (size_t)n * a.dq + c * 4) : zero4();
-        }
-#pragma unroll
-        for (int i = 0; i < NB; ++i) {                                // entity order, like NTN.java:414-426
-            acc.x += v[i].x / len[i]; acc.y += v[i].y / len[i];       // :420
-            acc.z += v[i].z / len[i]; acc.w += v[i].w / len[i];
-        }
-    }
+    int jb = j0;
+    for (; jb + NB <= j1; jb += NB) word_batch<NB>(a, jb, c, acc);   // full batches: no per-entity predicates
+    for (; jb < j1; ++jb) word_batch<1>(a, jb, c, acc);
     return acc;
 }
 
@@ -745,7 +749,7 @@ __global__ void __launch_bounds__(1024) k_word_finish_hub(WordArgs a) {
 }
 
 // one thread per (word, float4 chunk); hub words are finished by k_word_finish_hub
-__global__ void __launch_bounds__(256, 6) k_word_pull(WordArgs a) {
+__global__ void __launch_bounds__(256, 5) k_word_pull(WordArgs a) {
     __shared__ double s_reg[8];
     const int cpr = a.dq >> 2;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -760,7 +764,8 @@ __global__ void __launch_bounds__(256, 6) k_word_pull(WordArgs a) {
             if (rec.y - rec.x == 1) {                                // the common case: exactly one entity
                 const float len = __ldg(a.len_bwd + rec.z);
                 float4 v = ldg4(a.gE + (size_t)rec.z * a.dq + c * 4);
-                acc = make_float4(v.x / len, v.y / len, v.z / len, v.w / len);
+                const float inv = 1.0f / len;                        // len is 1..4 in practice; one division, not four
+                acc = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
             } else if (rec.y > rec.x) {
                 acc = word_range<4>(a, rec.x, rec.y, c);                // main kernel: keep registers (occupancy) low
             }
