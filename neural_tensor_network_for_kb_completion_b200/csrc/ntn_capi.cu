@@ -280,6 +280,8 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
     const NtnDims& dm = h->dm;
     if (!bwd_off || !bwd_idx) { bwd_off = fwd_off; bwd_idx = fwd_idx; }
     if (fwd_off[0] != 0 || bwd_off[0] != 0) FAIL(NTN_EINVAL, "CSR offsets must start at 0");
+    if ((int64_t)dm.Ne * (dm.Kp / 4) >= ((int64_t)1 << 32) || (int64_t)dm.Nw * (dm.dq / 4) >= ((int64_t)1 << 32))
+        FAIL(NTN_EUNSUP, "entity or word table too large for the flat 32-bit thread index of the gather kernels");
     for (int n = 0; n < dm.Ne; ++n) {
         if (fwd_off[n + 1] <= fwd_off[n]) FAIL(NTN_EINVAL, "entity " + std::to_string(n) + " has no forward word");
         if (bwd_off[n + 1] < bwd_off[n]) FAIL(NTN_EINVAL, "backward CSR offsets not monotone");
@@ -304,7 +306,7 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
             for (int j = bwd_off[n]; j < bwd_off[n + 1]; ++j) went[cur[bwd_idx[j]]++] = n;
     }
     std::vector<float> lb(dm.Ne);
-    for (int n = 0; n < dm.Ne; ++n) lb[n] = (float)len_bwd[n];
+    for (int n = 0; n < dm.Ne; ++n) lb[n] = (float)(1.0 / (double)len_bwd[n]);   // the kernels multiply by 1/len (NTN.java:420 divides)
     std::vector<int> sr, sb, se, first, count;
     build_hub_segments(woff, dm.Nw, sr, sb, se, first, count, NTN_WORD_HUB_SEG, NTN_HUB_SEG);
     w.n_hub_segs = (int)sr.size();

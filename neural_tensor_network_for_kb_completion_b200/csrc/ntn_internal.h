@@ -81,7 +81,7 @@ struct DeviceWords {
     int4 *fwd_rec = nullptr;                       // per entity {first index, word count, word 0, word 1}
     int *w_off = nullptr, *w_ent = nullptr;        // word -> entities of the backward lists (inverse CSR)
     int4 *w_rec = nullptr;                         // per word {j0, j1, first entity, hub segment count}
-    float *len_bwd = nullptr;                      // Ne, as float
+    float *len_bwd = nullptr;                      // Ne: 1 / entityLength(n) as float (the kernels multiply)
     int n_hub_segs = 0, n_hub_words = 0;
     int *hub_words = nullptr;                      // ids of the hub words
     int *wh_word = nullptr, *wh_begin = nullptr, *wh_end = nullptr;

@@ -35,6 +35,27 @@ __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+// Division of the flat thread index by the run-time row width (threads per row), Granlund-Montgomery style: the
+// generic 64-bit division costs ~25 instructions in every thread of the gather kernels, which are issue-bound.
+// Exact for every 32-bit n; the host checks that the grid fits 32 bits.
+struct FastDiv {
+    unsigned d, m, s;                                              // divisor, magic, shift (= ceil(log2 d) - 1, or 0)
+};
+static FastDiv make_fastdiv(unsigned d) {
+    FastDiv f{d, 0u, 0u};
+    if (d <= 1) return f;                                          // handled in fd_div
+    unsigned l = 0; while ((1ull << l) < d) ++l;
+    f.m = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s = l - 1;
+    return f;
+}
+__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
+    if (f.d <= 1) return n;
+    const unsigned t = __umulhi(f.m, n);
+    return (t + ((n - t) >> 1)) >> f.s;
+}
+__device__ __forceinline__ unsigned flat_index() { return blockIdx.x * blockDim.x + threadIdx.x; }
+
 template <int ACT> __device__ __forceinline__ float act_fn(float x) {
     if (ACT == NTN_ACT_TANH) return tanhf(x);               // NTN.java:200-201
     return 1.0f / (1.0f + expf(-x));
@@ -51,12 +72,11 @@ template <int ACT> __device__ __forceinline__ float act_diff(float z) {   // NTN
 // ==========================================================================================
 __global__ void __launch_bounds__(256) k_entity_build(const float* __restrict__ wvt, const int4* __restrict__ rec,
                                                       const int* __restrict__ idx, float* __restrict__ E,
-                                                      int Ne, int d, int dq, int Kp) {
+                                                      int Ne, int d, int dq, int Kp, FastDiv fd) {
     // flat mapping: one thread per (entity, float4 chunk of the Kp-wide row).  rec = {first index into idx, word
     // count, word 0, word 1}: entities of one or two words (92 %) need no second dependent index load.
-    const int cpr = Kp >> 2;
-    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = (int)(gid / cpr), c = (int)(gid - (int64_t)n * cpr);
+    const unsigned gid = flat_index();
+    const int n = (int)fd_div(gid, fd), c = (int)(gid - (unsigned)n * fd.d);       // fd.d = Kp / 4 chunks per row
     if (n >= Ne) return;
     const int4 r = __ldg(rec + n);
     const int cnt = r.y;
@@ -546,6 +566,7 @@ struct PullArgs {
     const int *eh_first, *eh_count, *eh_begin, *eh_end;
     float* eh_part;
     int Ne, dq, Kp, Np, n_segs;
+    FastDiv fd;                          // threads per row = dq / 4
 };
 
 // One batch of N incidents, all valid: records first, then every row / coefficient load of the batch (latency overlaps),
@@ -604,9 +625,8 @@ __device__ __forceinline__ float4 pull_range(const PullArgs& a, int j0, int j1, 
 
 template <int KS, bool GVR>
 __global__ void __launch_bounds__(256) k_entity_pull_hub(PullArgs a) {
-    const int cpr = a.dq >> 2;
-    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int seg = (int)(gid / cpr), c = (int)(gid - (int64_t)seg * cpr);
+    const unsigned gid = flat_index();
+    const int seg = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)seg * a.fd.d);
     if (seg >= a.n_segs) return;
     float4 acc = pull_range<KS, GVR>(a, a.eh_begin[seg], a.eh_end[seg], c);
     *reinterpret_cast<float4*>(a.eh_part + (size_t)seg * a.dq + c * 4) = acc;
@@ -614,9 +634,8 @@ __global__ void __launch_bounds__(256) k_entity_pull_hub(PullArgs a) {
 
 template <int KS, bool GVR>
 __global__ void __launch_bounds__(256, (KS <= 4) ? 6 : 2) k_entity_pull(PullArgs a) {
-    const int cpr = a.dq >> 2;
-    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = (int)(gid / cpr), c = (int)(gid - (int64_t)n * cpr);
+    const unsigned gid = flat_index();
+    const int n = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)n * a.fd.d);
     if (n >= a.Ne) return;
     float4 acc;
     int nseg = a.eh_count ? a.eh_count[n] : 0;
@@ -646,7 +665,7 @@ __global__ void __launch_bounds__(256, (KS <= 4) ? 6 : 2) k_entity_pull(PullArgs
 //     pre-reduced by k_word_pull_hub and are finished by one block each in k_word_finish_hub.
 // ==========================================================================================
 struct WordArgs {
-    const float *gE, *len_bwd, *theta;
+    const float *gE, *inv_len, *theta;   // inv_len[n] = 1 / entityLength(n), rounded once on the host (NTN.java:420)
     float* grad;
     const int *w_off, *w_ent;
     const int4* w_rec;                   // {j0, j1, first entity (or -1), hub segment count}: one load instead of a chain
@@ -656,6 +675,7 @@ struct WordArgs {
     int Nw, dq, n_segs, n_hub_words, n_word_blocks;
     int64_t oWV;
     float inv_B, lam;
+    FastDiv fd;                          // threads per row = dq / 4
 };
 
 // one batch of N entities of a word's list, all valid: loads first, then the adds in entity order (NTN.java:414-426)
@@ -665,7 +685,7 @@ __device__ __forceinline__ void word_batch(const WordArgs& a, int jb, int c, flo
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const int n = __ldg(a.w_ent + jb + i);
-        inv[i] = 1.0f / __ldg(a.len_bwd + n);                        // :420 (one division per entity, not per component)
+        inv[i] = __ldg(a.inv_len + n);                               // :420
         v[i] = ldg4(a.gE + (size_t)n * a.dq + c * 4);
     }
 #pragma unroll
@@ -692,9 +712,8 @@ __device__ __forceinline__ float word_store(const WordArgs& a, size_t o, const f
 
 // one thread per (hub segment, float4 chunk)
 __global__ void __launch_bounds__(256) k_word_pull_hub(WordArgs a) {
-    const int cpr = a.dq >> 2;
-    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int seg = (int)(gid / cpr), c = (int)(gid - (int64_t)seg * cpr);
+    const unsigned gid = flat_index();
+    const int seg = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)seg * a.fd.d);
     if (seg >= a.n_segs) return;
     float4 acc = word_range<8>(a, a.wh_begin[seg], a.wh_end[seg], c);   // short latency-bound branch: 8 rows in flight
     *reinterpret_cast<float4*>(a.wh_part + (size_t)seg * a.dq + c * 4) = acc;
@@ -751,9 +770,8 @@ __global__ void __launch_bounds__(1024) k_word_finish_hub(WordArgs a) {
 // one thread per (word, float4 chunk); hub words are finished by k_word_finish_hub
 __global__ void __launch_bounds__(256, 5) k_word_pull(WordArgs a) {
     __shared__ double s_reg[8];
-    const int cpr = a.dq >> 2;
-    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int w = (int)(gid / cpr), c = (int)(gid - (int64_t)w * cpr);
+    const unsigned gid = flat_index();
+    const int w = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)w * a.fd.d);
     float reg = 0.f;
     if (w < a.Nw) {
         const int4 rec = __ldg(a.w_rec + w);
@@ -762,9 +780,8 @@ __global__ void __launch_bounds__(256, 5) k_word_pull(WordArgs a) {
             float4 th = ldg4(a.theta + o);
             float4 acc = zero4();
             if (rec.y - rec.x == 1) {                                // the common case: exactly one entity
-                const float len = __ldg(a.len_bwd + rec.z);
+                const float inv = __ldg(a.inv_len + rec.z);
                 float4 v = ldg4(a.gE + (size_t)rec.z * a.dq + c * 4);
-                const float inv = 1.0f / len;                        // len is 1..4 in practice; one division, not four
                 acc = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
             } else if (rec.y > rec.x) {
                 acc = word_range<4>(a, rec.x, rec.y, c);                // main kernel: keep registers (occupancy) low
@@ -977,7 +994,7 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 void ntn_launch_entity_build(ntn_handle* h, const float* wvt) {
     const NtnDims& dm = h->dm;
     k_entity_build<<<cdiv((int64_t)dm.Ne * (dm.Kp / 4), 256), 256, 0, h->stream>>>(wvt, h->w.fwd_rec, h->w.fwd_idx, h->E,
-                                                                                   dm.Ne, dm.d, dm.dq, dm.Kp);
+                                                                                   dm.Ne, dm.d, dm.dq, dm.Kp, make_fastdiv((unsigned)(dm.Kp / 4)));
     h->launches++;
 }
 
@@ -1056,7 +1073,7 @@ void ntn_launch_entity_pull(ntn_handle* h) {
     const DeviceBatch& b = h->b;
     PullArgs a{b.T, b.acoef, b.GV, b.GA, b.inc, b.inc_off, h->side, h->gE,
                b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
-               b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.n_ent_hub_segs};
+               b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.n_ent_hub_segs, make_fastdiv((unsigned)(dm.dq / 4))};
     const int cpr = dm.dq / 4;
     DISPATCH_KS(dm.k, {
         if (b.n_ent_hub_segs) {
@@ -1075,9 +1092,9 @@ static int word_pull_blocks(const NtnDims& dm) { return cdiv((int64_t)dm.Nw * (d
 void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad) {
     const NtnDims& dm = h->dm;
     const DeviceWords& w = h->w;
-    WordArgs a{h->gE, w.len_bwd, theta, grad, w.w_off, w.w_ent, w.w_rec, w.wh_first, w.wh_count, w.wh_begin, w.wh_end,
+    WordArgs a{h->gE, w.len_bwd /* reciprocals */, theta, grad, w.w_off, w.w_ent, w.w_rec, w.wh_first, w.wh_count, w.wh_begin, w.wh_end,
                w.hub_words, w.wh_part, h->reg_part, dm.Nw, dm.dq, w.n_hub_segs, w.n_hub_words, word_pull_blocks(dm),
-               dm.oWVint, 1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale};
+               dm.oWVint, 1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale, make_fastdiv((unsigned)(dm.dq / 4))};
     const int cpr = dm.dq / 4;
     int ch = cdiv(cpr, 32);
     if (w.n_hub_segs) {
