@@ -451,14 +451,17 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
             }
             float v[32];
 #pragma unroll
-            for (int q = 0; q < 32; ++q) v[q] = 0.f;
+            for (int q = V; q < 32; ++q) v[q] = 0.f;                      // slots beyond the batch's COLB x KS values
 #pragma unroll
             for (int j = 0; j < COLB; ++j)
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     if (masked) { ev[j][c].x *= cm[c].x; ev[j][c].y *= cm[c].y; ev[j][c].z *= cm[c].z; ev[j][c].w *= cm[c].w; }
 #pragma unroll
-                    for (int s = 0; s < KS; ++s) v[j * KS + s] += dot4(t[s][c], ev[j][c]);
+                    for (int s = 0; s < KS; ++s) {                        // first chunk assigns: no zero-fill + add
+                        if (c == 0) v[j * KS + s] = dot4(t[s][c], ev[j][c]);
+                        else v[j * KS + s] += dot4(t[s][c], ev[j][c]);
+                    }
                 }
             warp_transpose_reduce32(v, lane);                          // lane l: pre-activation (my_j, my_s)
             const bool mine_valid = lane < V && my_j < nb;
