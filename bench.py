@@ -68,14 +68,20 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def mark(self):
+        """Called when the timed region starts: only samples taken from here on are reported (the sampler itself is
+        started before the warm-up so that nvidia-smi's start-up does not eat a short timed region)."""
+        self.first = len(self.rows)
+
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for l in self.rows:
+        rows = self.rows[getattr(self, "first", 0):] or self.rows[-3:]
+        for l in rows:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
@@ -314,13 +320,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i, sync=True)
-    launches_per_eval = h0.launches
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        step(i, sync=True)
+    launches_per_eval = h0.launches
     barrier()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for i in range(args.steps):
