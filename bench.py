@@ -232,7 +232,7 @@ def main():
         args.steps = 3 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
         return run_reference(args)
-    args.steps = 1000 if args.steps is None else args.steps        # ~0.25 s timed region at the headline config: enough clock samples
+    args.steps = 4000 if args.steps is None else args.steps        # ~0.9 s timed region at the headline config: nvidia-smi answers every 0.1-0.2 s
     args.warmup = max(3, 10 if args.warmup is None else args.warmup)
 
     import torch
