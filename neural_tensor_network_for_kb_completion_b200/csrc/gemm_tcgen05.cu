@@ -589,16 +589,16 @@ __global__ void __launch_bounds__(256) k_tc_w_prep(const float* __restrict__ the
         int rem = (int)(i - (int64_t)r * dm.Np * KpP);
         int n = rem / KpP, p = rem - n * KpP;
         const float v = waug_at(theta, dm, r, side[r] != 0, p, n);
-        WT[i] = v;
-        if (WT_hi) { float h, l; split1(v, h, l); WT_hi[i] = h; WT_lo[i] = l; }
+        if (WT_hi) { float h, l; split1(v, h, l); WT_hi[i] = h; WT_lo[i] = l; }   // TMA path: only the pre-split copies are read
+        else WT[i] = v;
     } else if (i < nA + nB) {
         i -= nA;
         int r = (int)(i / ((int64_t)KpN * NpP));
         int rem = (int)(i - (int64_t)r * KpN * NpP);
         int p = rem / NpP, n = rem - p * NpP;
         const float v = waug_at(theta, dm, r, side[r] != 0, p, n);
-        W[i] = v;
         if (W_hi) { float h, l; split1(v, h, l); W_hi[i] = h; W_lo[i] = l; }
+        else W[i] = v;
     } else if (i < nA + nB + Nu) {
         // anchor entity of every unique triple under this evaluation's corrupt sides (NTN.java:146-156): the entity
         // that is NOT replaced -- e1 when the tail is corrupted, e2 when the head is
