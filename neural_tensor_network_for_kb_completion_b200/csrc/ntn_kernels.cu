@@ -49,10 +49,21 @@ static FastDiv make_fastdiv(unsigned d) {
     f.s = l - 1;
     return f;
 }
-__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
+__host__ __device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
     if (f.d <= 1) return n;
+#ifdef __CUDA_ARCH__
     const unsigned t = __umulhi(f.m, n);
+#else
+    const unsigned t = (unsigned)(((unsigned long long)f.m * n) >> 32);
+#endif
     return (t + ((n - t) >> 1)) >> f.s;
+}
+// test hook (CPU): q[i] = n[i] / d through the same magic numbers the kernels use
+extern "C" int ntn_host_fastdiv(uint32_t d, int64_t count, const uint32_t* n, uint32_t* q) {
+    if (d == 0 || count < 0 || (count > 0 && (!n || !q))) return NTN_EINVAL;
+    const FastDiv f = make_fastdiv(d);
+    for (int64_t i = 0; i < count; ++i) q[i] = fd_div(n[i], f);
+    return NTN_OK;
 }
 __device__ __forceinline__ unsigned flat_index() { return blockIdx.x * blockDim.x + threadIdx.x; }
 

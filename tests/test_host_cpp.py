@@ -121,3 +121,17 @@ def test_device_sampler_restatement_is_uniform_and_counter_based():
     assert not np.array_equal(a, data_ref.device_corrupt_sample(42, 4, j, 1000))
     assert not np.array_equal(a, data_ref.device_corrupt_sample(43, 3, j, 1000))
     assert not np.array_equal(a, data_ref.device_corrupt_sample(42, 3, j, 1000, attempt=1))
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 7, 13, 25, 26, 33, 64, 65, 100, 257, 4096, 65537, 2**31 - 1, 2**31, 2**32 - 1])
+def test_invariant_division_of_the_flat_thread_index(d):
+    """The gather kernels divide their flat 32-bit thread index by the run-time row width with precomputed magic
+    numbers (ntn_kernels.cu: FastDiv); the quotient must be exact for every 32-bit dividend."""
+    lib = _capi.load()
+    rng = np.random.default_rng(d % 1000)
+    edge = np.array([0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2**31 - 1, 2**31, 2**32 - 1], dtype=np.int64) % (2**32)
+    n = np.concatenate([edge, rng.integers(0, 2**32, size=20000, dtype=np.int64),
+                        (rng.integers(0, 2**32 // d + 1, size=2000, dtype=np.int64) * d) % (2**32)]).astype(np.uint32)
+    q = np.empty_like(n)
+    assert lib.ntn_host_fastdiv(d, len(n), n.ctypes.data, q.ctypes.data) == 0
+    np.testing.assert_array_equal(q, (n.astype(np.uint64) // np.uint64(d)).astype(np.uint32))
