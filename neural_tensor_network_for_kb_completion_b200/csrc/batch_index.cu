@@ -127,6 +127,14 @@ __global__ void k_bi_hub_fill(const int* __restrict__ inc_off, const int* __rest
     }
 }
 
+// visiting order of the entity pull: entities by descending incident count (clamped), stable -> key = clamp - min(deg, clamp)
+__global__ void k_bi_order_keys(const int* __restrict__ inc_off, int Ne, uint32_t* __restrict__ key, int* __restrict__ val) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Ne) return;
+    key[e] = (uint32_t)(NTN_ORDER_CLAMP - min(inc_off[e + 1] - inc_off[e], NTN_ORDER_CLAMP));
+    val[e] = e;
+}
+
 // ---- on-device batch-job generator ---------------------------------------------------------------
 // Counter-based corrupt sampler: e3 of column j of batch job `job` is a pure function of (seed, job, j, attempt), so a
 // batch job can be regenerated anywhere (tests restate it in NumPy, oracle/data_ref.py: device_corrupt_sample).
@@ -209,12 +217,16 @@ int ntn_index_batch_dev(ntn_handle* h, int64_t n, const int* d_e1, const int* d_
                                     (int)n3, 0, eb, st);
     cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, (int*)nullptr, (int*)nullptr, (int)n, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan_e, (int*)nullptr, (int*)nullptr, dm.Ne, st);
-    const size_t tmp_bytes = std::max(std::max(tmp_sort64, tmp_sort32), std::max(tmp_scan, tmp_scan_e));
+    size_t tmp_sort_o = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort_o, (uint32_t*)nullptr, (uint32_t*)nullptr, (int*)nullptr, (int*)nullptr,
+                                    dm.Ne, 0, 10, st);
+    const size_t tmp_bytes = std::max(std::max(std::max(tmp_sort64, tmp_sort32), std::max(tmp_scan, tmp_scan_e)), tmp_sort_o);
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_key = 0, o_key2 = o_key + al((size_t)n * 8), o_val = o_key2 + al((size_t)n * 8),
                  o_val2 = o_val + al((size_t)n * 4), o_scan = o_val2 + al((size_t)n * 4), o_colu = o_scan + al((size_t)n * 4),
                  o_ik = o_colu + al((size_t)n * 4), o_ik2 = o_ik + al(n3 * 4), o_iv = o_ik2 + al(n3 * 4), o_iv2 = o_iv + al(n3 * 4),
-                 o_meta = o_iv2 + al(n3 * 4), o_tmp = o_meta + al((size_t)n_meta * 4), total = o_tmp + al(tmp_bytes);
+                 o_meta = o_iv2 + al(n3 * 4), o_ok = o_meta + al((size_t)n_meta * 4), o_ok2 = o_ok + al((size_t)dm.Ne * 4),
+                 o_ov = o_ok2 + al((size_t)dm.Ne * 4), o_tmp = o_ov + al((size_t)dm.Ne * 4), total = o_tmp + al(tmp_bytes);
     if (h->bi_ws_bytes < total) {
         if (h->bi_ws) cudaFree(h->bi_ws);
         h->bi_ws = nullptr; h->bi_ws_bytes = 0;
@@ -233,7 +245,8 @@ int ntn_index_batch_dev(ntn_handle* h, int64_t n, const int* d_e1, const int* d_
     int rc;
     if ((rc = grow(h, &b.u_e1, (size_t)n)) || (rc = grow(h, &b.u_e2, (size_t)n)) || (rc = grow(h, &b.u_rel, (size_t)n)) ||
         (rc = grow(h, &b.c_off, (size_t)n + 1)) || (rc = grow(h, &b.c_e3, (size_t)n)) || (rc = grow(h, &b.inc_off, (size_t)dm.Ne + 1)) ||
-        (rc = grow(h, &b.inc, n3)) || (rc = grow(h, &b.eh_first, (size_t)dm.Ne)) || (rc = grow(h, &b.eh_count, (size_t)dm.Ne)))
+        (rc = grow(h, &b.inc, n3)) || (rc = grow(h, &b.eh_first, (size_t)dm.Ne)) || (rc = grow(h, &b.eh_count, (size_t)dm.Ne)) ||
+        (rc = grow(h, &b.ent_order, (size_t)dm.Ne)))
         return rc;
 
     const int T = 256;
@@ -265,6 +278,13 @@ int ntn_index_batch_dev(ntn_handle* h, int64_t n, const int* d_e1, const int* d_
         BCK(cub::DeviceRadixSort::SortPairs(tmp, tb, ik, ik2, iv, iv2, (int)n_inc, 0, eb, st));
     }
     k_bi_inc_records<<<cdiv64(n_inc + 1, T), T, 0, st>>>(ik2, iv2, b.u_rel, col_u, Nu, n_inc, dm.Ne, b.inc, b.inc_off);
+    {
+        uint32_t *ok = (uint32_t*)(ws + o_ok), *ok2 = (uint32_t*)(ws + o_ok2);
+        int* ov = (int*)(ws + o_ov);
+        k_bi_order_keys<<<cdiv64(dm.Ne, T), T, 0, st>>>(b.inc_off, dm.Ne, ok, ov);
+        tb = tmp_bytes;
+        BCK(cub::DeviceRadixSort::SortPairs(tmp, tb, ok, ok2, ov, b.ent_order, dm.Ne, 0, 10, st));
+    }
     k_bi_hub_count<<<cdiv64(dm.Ne, T), T, 0, st>>>(b.inc_off, dm.Ne, NTN_HUB_SEG, NTN_HUB_SEG, b.eh_count);
     tb = tmp_bytes;
     BCK(cub::DeviceScan::ExclusiveSum(tmp, tb, b.eh_count, b.eh_first, dm.Ne, st));

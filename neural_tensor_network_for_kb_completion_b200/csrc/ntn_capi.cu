@@ -171,7 +171,7 @@ static void free_batch(DeviceBatch& b) {
     dev_free(b.t_rel); dev_free(b.t_u0); dev_free(b.t_n); dev_free(b.ch_rel); dev_free(b.ch_u0); dev_free(b.ch_n);
     dev_free(b.relch_off); dev_free(b.reltile_off); dev_free(b.inc_off); dev_free(b.inc);
     dev_free(b.eh_ent); dev_free(b.eh_begin); dev_free(b.eh_end); dev_free(b.eh_first); dev_free(b.eh_count);
-    dev_free(b.T); dev_free(b.M); dev_free(b.GA); dev_free(b.GV); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.dWpart);
+    dev_free(b.T); dev_free(b.M); dev_free(b.GA); dev_free(b.GV); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.crec); dev_free(b.ent_order); dev_free(b.dWpart);
     dev_free(b.tp_cost); dev_free(b.tp_nact); dev_free(b.tp_dU); dev_free(b.eh_part);
     b = DeviceBatch();
 }
@@ -366,13 +366,18 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
     // split-K chunk of the dW contraction: about two chunks per SM (every chunk costs a Kp x Np partial that the
     // finalize kernel sums serially), never below NTN_CHUNK_ROWS, a multiple of the 32-row k-block
     const int chunk_rows = std::max(NTN_CHUNK_ROWS, (int)round_up((Nu + 2 * h->sm_count - 1) / (2 * h->sm_count), 32));
-    // score tile height: a block is 8 warps and runs 2 per SM; every warp takes rows/8 triples in turn.  At the
-    // reference's batch size the kernel is only a few waves long, so the height is picked to minimise
-    // (waves x triples per warp) with half a triple of fixed cost per block -- measured at 20,000 triples on 13 relations:
-    // 8 rows 60.6 us, 16: 55.0, 24: 49.4, 32: 56.6, 40: 51.1, 48: 58.5.  Long grids keep 32 (64 measured 6 % slower at
-    // 316k triples).  NTN_SCORE_ROWS overrides.
+    // entity-gradient pull variant: while T' (Nu x Np floats) stays L2-resident every incident re-reads its k T' rows
+    // (k_score2 + k_entity_pull2, the default); beyond that k_score materialises one contribution row per incident
+    // (measured in round 1: C3 0.256 vs 0.278 ms with rows, C4 2.89 vs 2.42 ms).  NTN_GV=0/1 overrides.
+    bool use_gv = (size_t)Nu * dm.Np * sizeof(float) > ((size_t)48 << 20);
+    if (const char* e = getenv("NTN_GV")) use_gv = e[0] == '1';
     int score_rows = NTN_SCORE_ROWS;
-    {
+    if (!use_gv) {
+        score_rows = ntn_score2_rows(dm.k);          // one block of k_score2: 4 warps x (32 / k) unique triples
+    } else {
+        // k_score (GV variant) tile height: a block is 8 warps and runs 2 per SM; every warp takes rows/8 triples in turn.
+        // Short grids pick the height that minimises (waves x triples per warp) with half a triple of fixed cost per
+        // block; long grids keep 32 (64 measured 6 % slower at 316k triples).  NTN_SCORE_ROWS overrides.
         const int slots = 2 * h->sm_count;
         auto tiles_at = [&](int rows) { int64_t t = 0; for (int r = 0; r < dm.R; ++r) t += (rel_count[r] + rows - 1) / rows; return t; };
         if (tiles_at(NTN_SCORE_ROWS) <= 4 * (int64_t)slots) {
@@ -398,11 +403,6 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
         reltile_off[r + 1] = (int)t_rel.size();
         relch_off[r + 1] = (int)ch_rel.size();
     }
-    // entity-gradient pull variant: while T' (Nu x Np floats) stays L2-resident every incident re-reads its k T' rows;
-    // beyond that k_score materialises one contribution row per incident (measured: C3 0.256 vs 0.278 ms with rows,
-    // C4 2.89 vs 2.42 ms).  NTN_GV=0/1 overrides.
-    bool use_gv = (size_t)Nu * dm.Np * sizeof(float) > ((size_t)48 << 20);
-    if (const char* e = getenv("NTN_GV")) use_gv = e[0] == '1';
     DeviceBatch& b = h->b;
     b.N = n; b.Nu = Nu; b.ntiles = (int)t_rel.size(); b.nchunks = (int)ch_rel.size(); b.n_inc = 2 * Nu + (int)n;
     b.nstiles = (int)st_rel.size();
@@ -415,13 +415,15 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
         (rc = dev_upload(h, &b.ch_rel, ch_rel)) || (rc = dev_upload(h, &b.ch_u0, ch_u0)) || (rc = dev_upload(h, &b.ch_n, ch_n)) ||
         (rc = dev_upload(h, &b.relch_off, relch_off)) || (rc = dev_upload(h, &b.reltile_off, reltile_off)) ||
         (rc = dev_alloc(h, &b.T, (size_t)Nu * dm.Np)) || (rc = dev_alloc(h, &b.M, (size_t)Nu * dm.Np)) ||
-        (rc = dev_alloc(h, &b.GA, (size_t)Nu * dm.Kp)) || (rc = dev_alloc(h, &b.GV, use_gv ? ((size_t)Nu + (size_t)n) * dm.dq : 1)) || (rc = dev_alloc(h, &b.acoef, ((size_t)Nu + (size_t)n) * dm.k)) ||
+        (rc = dev_alloc(h, &b.GA, (size_t)Nu * dm.Kp)) || (rc = dev_alloc(h, &b.GV, use_gv ? ((size_t)Nu + (size_t)n) * dm.dq : 1)) || (rc = dev_alloc(h, &b.acoef, use_gv ? ((size_t)Nu + (size_t)n) * dm.k : 1)) ||
+        (rc = dev_alloc(h, &b.crec, use_gv ? 1 : ((size_t)Nu + (size_t)n) * (size_t)round_up(dm.k + 1, 4))) ||
         (rc = dev_alloc(h, &b.dWpart, (size_t)b.nchunks * dm.Kp * dm.Np)) ||
         (rc = dev_alloc(h, &b.tp_cost, (size_t)b.nstiles)) || (rc = dev_alloc(h, &b.tp_nact, (size_t)b.nstiles)) ||
         (rc = dev_alloc(h, &b.tp_dU, (size_t)b.nstiles * dm.k)) ||
         (rc = dev_alloc(h, &b.eh_part, (size_t)b.n_ent_hub_segs * dm.dq)))
         return rc;
-    b.ccoef = b.acoef + (size_t)Nu * dm.k;
+    b.ccoef = b.acoef + (use_gv ? (size_t)Nu * dm.k : 0);
+    b.RS = (int)round_up(dm.k + 1, 4);
     CK(cudaStreamSynchronize(h->stream));            // the small tables above come from host vectors that die here
     // contraction path for this batch
     h->gemm_path_active = NTN_GEMM_SIMT;
@@ -495,9 +497,15 @@ static int set_batch_host_tables(ntn_handle* h, int64_t n, const int32_t* e1, co
     }
     std::vector<int> sr, sb, se, first, count;
     build_hub_segments(inc_off, dm.Ne, sr, sb, se, first, count);
+    // visiting order of the entity pull: descending incident count (clamped like the device builder), stable
+    std::vector<int> ent_order(dm.Ne);
+    std::iota(ent_order.begin(), ent_order.end(), 0);
+    std::stable_sort(ent_order.begin(), ent_order.end(), [&](int x, int y) {
+        return std::min(inc_off[x + 1] - inc_off[x], NTN_ORDER_CLAMP) > std::min(inc_off[y + 1] - inc_off[y], NTN_ORDER_CLAMP);
+    });
     DeviceBatch& b = h->b;
     int rc;
-    if ((rc = dev_upload(h, &b.u_e1, u_e1)) || (rc = dev_upload(h, &b.u_e2, u_e2)) || (rc = dev_upload(h, &b.u_rel, u_rel)) ||
+    if ((rc = dev_upload(h, &b.ent_order, ent_order)) || (rc = dev_upload(h, &b.u_e1, u_e1)) || (rc = dev_upload(h, &b.u_e2, u_e2)) || (rc = dev_upload(h, &b.u_rel, u_rel)) ||
         (rc = dev_upload(h, &b.c_off, c_off)) || (rc = dev_upload(h, &b.c_e3, c_e3)) ||
         (rc = dev_upload(h, &b.inc_off, inc_off)) || (rc = dev_upload(h, &b.inc, inc)) ||
         (rc = dev_upload(h, &b.eh_ent, sr)) || (rc = dev_upload(h, &b.eh_begin, sb)) || (rc = dev_upload(h, &b.eh_end, se)) ||
@@ -993,6 +1001,7 @@ extern "C" int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, 
         else if (t == "eh_count") { isrc = b.eh_count; n = dm.Ne; }
         else if (t == "eh_begin") { isrc = b.eh_begin; n = b.n_ent_hub_segs; }
         else if (t == "eh_end") { isrc = b.eh_end; n = b.n_ent_hub_segs; }
+        else if (t == "ent_order") { isrc = b.ent_order; n = dm.Ne; }
         else return -1;
         if (out && cap >= n && n > 0) cudaMemcpy(out, isrc, n * sizeof(int), cudaMemcpyDeviceToHost);
         return n;

@@ -34,6 +34,7 @@ struct NtnDims {
 #define NTN_SCORE_ROWS  32       // default unique triples per score tile (8 warps x 4); finish_batch picks per batch job
 #define NTN_HUB_SEG     32       // incident-list segment length for hub entities
 #define NTN_WORD_HUB_SEG 16      // ... and for hub words (their branch is a short, latency-bound tail: more, shorter segments)
+#define NTN_ORDER_CLAMP 1023    // incident counts are clamped here when the pull's visiting order is sorted
 #define NTN_RING        8        // in-flight evaluations the host may enqueue without synchronising
 
 struct DeviceBatch {
@@ -65,7 +66,10 @@ struct DeviceBatch {
     float *M = nullptr;          // Nu x Np   backward coefficients folded with the gathered rows
     float *GA = nullptr;         // Nu x Kp   anchor-entity gradient rows
     float *GV = nullptr;         // (Nu + N) x dq   per-incident contribution rows (non-anchor roles), written by k_score
-    float *acoef = nullptr;      // (Nu + N) x k : a_{u,s} rows, then c_{col,s} rows (one allocation)
+    float *crec = nullptr;       // (Nu + N) x RS packed coefficient records (k_score2 -> k_entity_pull2), RS = ceil4(k + 1)
+    int RS = 4;
+    int *ent_order = nullptr;    // Ne: entities in descending order of their incident count (stable): the pull's visiting order
+    float *acoef = nullptr;      // (Nu + N) x k : a_{u,s} rows, then c_{col,s} rows (one allocation; GV variant)
     float *ccoef = nullptr;      // = acoef + Nu*k
     float *dWpart = nullptr;     // nchunks x Kp x Np
     double *tp_cost = nullptr;   // ntiles
@@ -163,6 +167,7 @@ void ntn_launch_entity_build(ntn_handle* h, const float* wvt);
 void ntn_launch_w_prep(ntn_handle* h, const float* theta, cudaStream_t st);
 void ntn_launch_gemm_fwd_simt(ntn_handle* h);
 void ntn_launch_score(ntn_handle* h, const float* theta);
+int ntn_score2_rows(int k);   // tile height of the default score kernel
 void ntn_launch_gemm_dw_simt(ntn_handle* h, cudaStream_t st);
 void ntn_launch_gemm_ge_simt(ntn_handle* h);
 void ntn_launch_entity_pull(ntn_handle* h);

@@ -28,6 +28,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
+__device__ __forceinline__ float dot4_acc(const float4& a, const float4& b, float acc) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+}
 __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
     acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y);
     acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
@@ -81,15 +84,8 @@ template <int ACT> __device__ __forceinline__ float act_diff(float z) {   // NTN
 //     E[n, 0:d] = (1/cnt) sum_j WVt[word_j(n), :],  E[n, d] = 1,  E[n, d+1:Kp] = 0
 //     One thread per (entity, float4 chunk).  HBM-bound: reads nnz*dq, writes Ne*Kp.
 // ==========================================================================================
-__global__ void __launch_bounds__(256) k_entity_build(const float* __restrict__ wvt, const int4* __restrict__ rec,
-                                                      const int* __restrict__ idx, float* __restrict__ E,
-                                                      int Ne, int d, int dq, int Kp, FastDiv fd) {
-    // flat mapping: one thread per (entity, float4 chunk of the Kp-wide row).  rec = {first index into idx, word
-    // count, word 0, word 1}: entities of one or two words (92 %) need no second dependent index load.
-    const unsigned gid = flat_index();
-    const int n = (int)fd_div(gid, fd), c = (int)(gid - (unsigned)n * fd.d);       // fd.d = Kp / 4 chunks per row
-    if (n >= Ne) return;
-    const int4 r = __ldg(rec + n);
+__device__ __forceinline__ float4 entity_mean_chunk(const float* __restrict__ wvt, const int4& r, const int* __restrict__ idx,
+                                                    int c, int d, int dq) {
     const int cnt = r.y;
     float4 acc = zero4();
     if (c * 4 < dq) {
@@ -117,7 +113,26 @@ __global__ void __launch_bounds__(256) k_entity_build(const float* __restrict__ 
         int p = c * 4 + i;
         if (p == d) av[i] = 1.0f; else if (p > d) av[i] = 0.0f;
     }
-    *reinterpret_cast<float4*>(E + (size_t)n * Kp + c * 4) = acc;
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) k_entity_build(const float* __restrict__ wvt, const int4* __restrict__ rec,
+                                                      const int* __restrict__ idx, float* __restrict__ E,
+                                                      int Ne, int half, int d, int dq, int Kp, FastDiv fd) {
+    // flat mapping: one thread per (entity pair, float4 chunk of the Kp-wide row): entities n and n + half, so that two
+    // independent record -> word-row chains are in flight per thread (the kernel is a few waves of two dependent
+    // round trips).  rec = {first index into idx, word count, word 0, word 1}: entities of one or two words (92 %)
+    // need no second dependent index load.
+    const unsigned gid = flat_index();
+    const int n = (int)fd_div(gid, fd), c = (int)(gid - (unsigned)n * fd.d);       // fd.d = Kp / 4 chunks per row
+    if (n >= half) return;
+    const int n2 = n + half;
+    const int4 r1 = __ldg(rec + n);
+    const int4 r2 = (n2 < Ne) ? __ldg(rec + n2) : r1;
+    const float4 a1 = entity_mean_chunk(wvt, r1, idx, c, d, dq);
+    const float4 a2 = entity_mean_chunk(wvt, r2, idx, c, d, dq);
+    *reinterpret_cast<float4*>(E + (size_t)n * Kp + c * 4) = a1;
+    if (n2 < Ne) *reinterpret_cast<float4*>(E + (size_t)n2 * Kp + c * 4) = a2;
 }
 
 // ==========================================================================================
@@ -562,6 +577,277 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
 }
 
 // ==========================================================================================
+// K4' score / hinge / backward-coefficient kernel (default; k_score above serves the large-batch GV variant)
+//     NTN.java:200-222 (activation, u-dot, hinge, cost, update), :272-289 (dU, temp, db), column halves of :301-388.
+//     Eight lanes share a unique triple: lane l takes the float4 chunks p = l, l+8, ... of every row, so a warp-wide
+//     load covers whole 128-byte lines (4 triples x 128 B) -- a lane-per-(triple, slice) variant measured 68 us because
+//     its 16-byte gathers cost one L1 wavefront each -- and every lane accumulates ALL dot products of its chunks
+//     (slices x {10 corrupt columns + the positive entity}), so the d-reduction is a 3-level butterfly over 8 lanes
+//     instead of a 32-lane transpose, and nothing is predicated per column.  Slot j of a group is then owned by lane
+//     j % 8: activation, score, hinge and coefficients are evaluated once per column, not once per lane, and the
+//     coefficients are broadcast back for pass 2, which rebuilds the M row  M_u[s,:] = a_{u,s} E_O + sum_c c_{c,s} E_c
+//     from the same entity rows (L1/L2 hits; columns with zero coefficients -- hinge inactive, NTN.java:229-239 -- are
+//     redirected to the positive row and cost no traffic).  k > 3: the slices are split over SG lane groups.
+//     Coefficients go out as one packed record per incident for the entity pull:
+//       crec[u]      = {a_{u,0..KS-1}, anchor role (0: e1, 1: e2), pad}        unique triple u
+//       crec[Nu + c] = {c_{c,0..KS-1}, -1, pad}                                corrupt column c
+// ==========================================================================================
+#define SC2_NC 10                  // corrupt columns per group (the reference's corrupt_size, Run_NTN.java:77)
+#define SC2_WARPS 2
+
+struct Score2Args {
+    const float *theta, *E, *T;
+    float *M, *crec;
+    int Nu, RS;                    // RS = floats per coefficient record (KS + 1 rounded up to 4)
+    const int *t_rel, *t_u0, *t_n, *u_e1, *u_e2, *c_off, *c_e3;
+    const uint8_t* side;
+    double* tp_cost; int* tp_nact; float* tp_dU;
+    int d, dq, Kp, Np;
+    int64_t oU;
+};
+
+template <int KS> struct Score2Shape {
+    static constexpr int SG = KS <= 3 ? 1 : (KS <= 6 ? 2 : 4);     // lane groups over the slices
+    static constexpr int SPL = (KS + SG - 1) / SG;                 // slices per lane
+    static constexpr int L = 8;                                    // lanes over the float4 chunks of a row (16 measured equal: +40 % instructions)
+    static constexpr int G = 32 / (L * SG);                        // unique triples per warp: 4, 2, 1
+};
+
+// 16-byte asynchronous copy global -> shared (L2 only: a row is used once per triple), and its completion
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int KS, int ACT, int DQT>                  // DQT: the row width dq when it is known at compile time (the reference's
+__global__ void __launch_bounds__(SC2_WARPS * 32) k_score2(Score2Args a) {   // d = 100 and the scaled d = 256), else 0
+    constexpr int L = Score2Shape<KS>::L, SG = Score2Shape<KS>::SG, SPL = Score2Shape<KS>::SPL, G = Score2Shape<KS>::G;
+    constexpr int LT = L * SG;                       // lanes of one unique triple
+    constexpr int NC = SC2_NC, NS = NC + 1;          // slots of a group: NC corrupt columns + the positive entity (slot NC)
+    constexpr int NR = (NS + L - 1) / L;             // owner rounds: slot j belongs to lane j % L in round j / L
+    constexpr int PR = NC / L, PO = NC % L;          // the positive slot NC is owned by lane PO in round PR
+    constexpr unsigned LMASK = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
+    // Row staging: the KS T' slices and the NS entity rows of every triple of the warp are copied to shared memory with
+    // cp.async -- all of a triple's ~5.6 KB in flight at once without holding a register, where the register-staged
+    // version of this kernel serialised its loads under the 128-register cap (72 % long-scoreboard stalls) -- and both
+    // passes read them from there, so the entity rows cross the L2 once.
+    extern __shared__ __align__(16) float sc2_smem[];
+    __shared__ double s_cost[SC2_WARPS];
+    __shared__ int s_nact[SC2_WARPS];
+    __shared__ float s_dU[SC2_WARPS][32][SPL];
+    const int tile = blockIdx.x;
+    const int r = a.t_rel[tile], u0 = a.t_u0[tile], rows = a.t_n[tile];
+    const bool tail = a.side[r] != 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / LT, sg = (lane / L) % SG, l = lane % L, lt = lane % LT;
+    const int lbase = lane - l;                      // first lane of this (triple, slice group)
+    const bool valid = warp * G + g < rows;
+    const int u = u0 + (valid ? warp * G + g : 0);   // idle lane groups shadow the tile's first triple and never store
+    const int dq = DQT ? DQT : a.dq, nch = dq >> 2, RS = a.RS;   // compile-time dq: every shared-memory offset is an immediate
+    const int nit = (nch + L - 1) / L;
+    const float* __restrict__ E = a.E;
+    const float* Tr = a.T + (size_t)u * a.Np;
+    float* S = sc2_smem + (size_t)(warp * G + g) * (KS + NS) * dq;       // this triple's rows: KS slices, then NS slots
+    bool sv[SPL]; float Us[SPL], beta[SPL]; int so[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+        const int s = sg * SPL + i;
+        sv[i] = s < KS;
+        const int sc = sv[i] ? s : 0;
+        so[i] = sc * dq;
+        Us[i] = sv[i] ? __ldg(a.theta + a.oU + (int64_t)r * KS + sc) : 0.f;
+        beta[i] = sv[i] ? __ldg(Tr + KS * dq + sc) : 0.f;
+    }
+    const int c0 = __ldg(a.c_off + u), c1 = __ldg(a.c_off + u + 1);
+    const int eo_other = __ldg((tail ? a.u_e2 : a.u_e1) + u) * a.Kp;      // element offset of the positive row
+    const int ncol = valid ? c1 - c0 : 0;
+    const int maxcol = __reduce_max_sync(FULL, ncol);                      // warp-uniform trip count of the group loop
+    // the T' slices: staged once (KS * dq floats are contiguous in a T' row)
+#pragma unroll (DQT ? 4 : 1)
+    for (int p = lt; p < KS * nch; p += LT) cp_async16(S + 4 * p, Tr + 4 * p);
+
+    float zp[SPL], cost_l = 0.f, dU_l[SPL], csum[SPL], sp = 0.f;
+    int cnt = 0, nact_l = 0;
+    float cc[SPL][NC];                               // group 0 stays in registers (and its rows in shared memory) for pass 2
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) { zp[i] = 0.f; dU_l[i] = 0.f; csum[i] = 0.f; }
+
+    // ---- pass 1: pre-activations, scores, hinge, coefficients; group gb covers columns [c0+gb, c0+gb+NC)
+    for (int gb = max(maxcol, 1) - 1 - (max(maxcol, 1) - 1) % NC; gb >= 0; gb -= NC) {   // last group first: group 0's rows stay staged
+        if (gb + NC < max(maxcol, 1)) __syncwarp();                      // every lane is done reading the previous group
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            int eg = eo_other;
+            if (j < NC && gb + j < ncol) eg = __ldg(a.c_e3 + c0 + gb + j) * a.Kp;
+            float* dst = S + (KS + j) * dq;
+#pragma unroll (DQT ? 8 : 1)
+            for (int p = lt; p < nch; p += LT) cp_async16(dst + 4 * p, E + eg + 4 * p);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        float acc[SPL][NS];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i)
+#pragma unroll
+            for (int j = 0; j < NS; ++j) acc[i][j] = 0.f;
+#pragma unroll (DQT ? 8 : 1)
+        for (int it = 0; it < nit; ++it) {
+            const int p = l + L * it;
+            if (p < nch) {
+                float4 t[SPL];
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) t[i] = *reinterpret_cast<const float4*>(S + so[i] + 4 * p);
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    const float4 v = *reinterpret_cast<const float4*>(S + (KS + j) * dq + 4 * p);
+#pragma unroll
+                    for (int i = 0; i < SPL; ++i) acc[i][j] = dot4_acc(t[i], v, acc[i][j]);
+                }
+            }
+        }
+        // the T' columns beyond d are zero (Waug has no such rows), so the 1.0 at E[n][d] never enters a dot product.
+        // butterfly over the L lanes of the triple: every lane ends with the same totals (x + y == y + x)
+#pragma unroll
+        for (int o = 1; o < L; o <<= 1)
+#pragma unroll
+            for (int i = 0; i < SPL; ++i)
+#pragma unroll
+                for (int j = 0; j < NS; ++j) acc[i][j] += __shfl_xor_sync(FULL, acc[i][j], o);
+        // owner lanes: slot j = rd*L + l
+        float z[NR][SPL], tot[NR];
+#pragma unroll
+        for (int rd = 0; rd < NR; ++rd) {
+            float ps = 0.f;
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+                float pre = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < L; ++jj) if (rd * L + jj < NS) pre = (l == jj) ? acc[i][rd * L + jj] : pre;
+                z[rd][i] = act_fn<ACT>(pre + beta[i]);                   // :200-201
+                ps = fmaf(Us[i], z[rd][i], ps);                          // :204-205 (Us = 0 for a padding slice)
+            }
+#pragma unroll
+            for (int o = L; o < L * SG; o <<= 1) ps += __shfl_xor_sync(FULL, ps, o);   // the other slice groups
+            tot[rd] = ps;
+        }
+        sp = __shfl_sync(FULL, tot[PR], lbase + PO);                     // (restaged with every group: same value)
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) zp[i] = __shfl_sync(FULL, z[PR][i], lbase + PO);
+        float cmine[NR][SPL];
+#pragma unroll
+        for (int rd = 0; rd < NR; ++rd) {
+            const int j = rd * L + l;
+            const bool ok = j < NC && gb + j < ncol;
+            const bool act = ok && ((sp + 1.0f) > tot[rd]);              // :213 (strict, FP32)
+            const unsigned amask = __ballot_sync(FULL, act);
+            if (act && sg == 0) { cost_l += (sp - tot[rd]) + 1.0f; nact_l++; }    // :221-222
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+                cmine[rd][i] = act ? -act_diff<ACT>(z[rd][i]) * Us[i] : 0.f;       // :281
+                if (act) dU_l[i] += zp[i] - z[rd][i];                    // :273
+            }
+            if (ok) {
+                float* cr = a.crec + (size_t)(a.Nu + c0 + gb + j) * RS;
+                if (SG == 1 && SPL == 3) {
+                    *reinterpret_cast<float4*>(cr) = make_float4(cmine[rd][0], cmine[rd][1], cmine[rd][2], -1.f);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < SPL; ++i) if (sv[i]) cr[sg * SPL + i] = cmine[rd][i];
+                    if (sg == 0) cr[KS] = -1.f;
+                }
+            }
+            cnt += __popc((amask >> lbase) & LMASK);
+        }
+        // coefficients of every slot back to all L lanes (pass 2 needs them for its own chunks)
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+                const float c = __shfl_sync(FULL, cmine[j / L][i], lbase + (j % L));
+                csum[i] += c;
+                cc[i][j] = c;                                            // the last iteration is group 0
+            }
+    }
+    float as[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) { as[i] = (float)cnt * (act_diff<ACT>(zp[i]) * Us[i]); csum[i] += as[i]; }   // :280
+
+    // ---- pass 2: the M row, from the rows of group 0 still in shared memory
+    if (maxcol > NC) __syncwarp();                   // the rare path below re-reads records stored by other lanes of this warp
+    const bool masked = dq != a.d;
+    float4 msk = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (masked) { const int p = dq - 4; msk = make_float4(p < a.d ? 1.f : 0.f, p + 1 < a.d ? 1.f : 0.f, p + 2 < a.d ? 1.f : 0.f, 0.f); }
+    float* Mr = a.M + (size_t)u * a.Np;
+#pragma unroll (DQT ? 8 : 1)
+    for (int it = 0; it < nit; ++it) {
+        const int p = l + L * it;
+        if (p >= nch) continue;
+        const int p4 = 4 * p;
+        const float4 vo = *reinterpret_cast<const float4*>(S + (KS + NC) * dq + p4);
+        float4 m[SPL];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) m[i] = make_float4(as[i] * vo.x, as[i] * vo.y, as[i] * vo.z, as[i] * vo.w);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(S + (KS + j) * dq + p4);
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) fma4(m[i], cc[i][j], v);
+        }
+        if (maxcol > NC) {                                               // rare: duplicate training triples merged into one unique triple
+            for (int c = c0 + NC; c < c0 + ncol; ++c) {
+                const float4 ve = ldg4(E + (size_t)__ldg(a.c_e3 + c) * a.Kp + p4);
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) {
+                    const float cx = sv[i] ? a.crec[(size_t)(a.Nu + c) * RS + sg * SPL + i] : 0.f;   // written in pass 1 by this warp
+                    fma4(m[i], cx, ve);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+            if (masked && p == nch - 1) { m[i].x *= msk.x; m[i].y *= msk.y; m[i].z *= msk.z; m[i].w *= msk.w; }
+            if (valid && sv[i]) *reinterpret_cast<float4*>(Mr + so[i] + p4) = m[i];
+        }
+    }
+    if (valid && l == 0) {
+#pragma unroll
+        for (int i = 0; i < SPL; ++i)
+            if (sv[i]) {
+                Mr[KS * dq + sg * SPL + i] = csum[i];                    // coefficient sums ride after the slices
+                a.crec[(size_t)u * RS + sg * SPL + i] = as[i];
+            }
+        if (sg == 0) {
+            a.crec[(size_t)u * RS + KS] = tail ? 0.f : 1.f;              // anchor role: e1 when the tail is corrupted
+            for (int n = KS * dq + KS; n < a.Np; ++n) Mr[n] = 0.f;
+        }
+    }
+    // ---- tile partials, fixed order: lanes, then warps
+    double cost_w = valid ? (double)cost_l : 0.0;
+    int nact_w = valid ? nact_l : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cost_w += __shfl_xor_sync(FULL, cost_w, o); nact_w += __shfl_xor_sync(FULL, nact_w, o); }
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) s_dU[warp][lane][i] = (valid && sv[i]) ? dU_l[i] : 0.f;
+    if (lane == 0) { s_cost[warp] = cost_w; s_nact[warp] = nact_w; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0.0; int n = 0;
+        for (int w = 0; w < SC2_WARPS; ++w) { c += s_cost[w]; n += s_nact[w]; }
+        a.tp_cost[tile] = c; a.tp_nact[tile] = n;
+    }
+    if (threadIdx.x < KS) {
+        const int s = threadIdx.x, ssg = s / SPL, si = s - ssg * SPL;
+        float vv = 0.f;
+        for (int w = 0; w < SC2_WARPS; ++w)
+            for (int ln = 0; ln < 32; ++ln)
+                if ((ln / L) % SG == ssg) vv += s_dU[w][ln][si];
+        a.tp_dU[(size_t)tile * KS + s] = vv;
+    }
+}
+
+// ==========================================================================================
 // K7  entity-gradient pull (replaces the 8*k*R dense scatter products of Util.java:74-98 and the
 //     dense adds of NTN.java:372,388).  One thread per (entity, float4 chunk) walks the entity's
 //     incident list in a fixed order -- no float atomics, bit-reproducible.  An incident is a packed
@@ -671,6 +957,100 @@ __global__ void __launch_bounds__(256, (KS <= 4) ? 6 : 2) k_entity_pull(PullArgs
 }
 
 // ==========================================================================================
+// K7' entity-gradient pull over packed coefficient records (the default; the kernels above serve the GV variant).
+//     Same sorted-segment pull (Util.java:74-98, NTN.java:372,388; no float atomics), trimmed for issue slots:
+//       * one 16-byte coefficient record per incident (k_score2) instead of k scalar loads, and the record of a unique
+//         triple names its anchor role, so no corrupt-side lookup;
+//       * entities are visited in descending order of their incident count (ent_order, built per batch job): the
+//         threads of a warp -- which span two entities -- run the same number of iterations;
+//       * the rows of an incident are requested right after its record: a positive-role incident requests its GA row
+//         AND its k T' rows and picks when the coefficient record arrives (17 % of the incidents, +5 % row traffic),
+//         so no incident waits for record -> coefficients -> rows.
+// ==========================================================================================
+struct Pull2Args {
+    const float *T, *crec, *GA;
+    const int4* inc;                     // {u, coefficient record, role (0: e1, 1: e2, 2: e3), rel}
+    const int *inc_off, *order;
+    float* gE;
+    const int *eh_first, *eh_count, *eh_begin, *eh_end;
+    float* eh_part;
+    int Ne, dq, Kp, Np, RS, n_segs;
+    FastDiv fd;                          // threads per row = dq / 4
+};
+
+template <int KS, int N>
+__device__ __forceinline__ void pull2_batch(const Pull2Args& a, int jb, int c4, float4& acc) {
+    constexpr int RQ = (KS + 4) / 4;                                  // float4s per record: KS coefficients + the role
+    float4 co[N][RQ], rows[N][KS], ga[N];
+    int role[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int4 rec = __ldg(a.inc + jb + i);
+        role[i] = rec.z;
+        const float* cr = a.crec + (size_t)rec.y * a.RS;
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) co[i][q] = ldg4(cr + 4 * q);
+        const float* Trow = a.T + (size_t)rec.x * a.Np + c4;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) rows[i][s] = ldg4(Trow + s * a.dq);
+        ga[i] = (rec.z != 2) ? ldg4(a.GA + (size_t)rec.x * a.Kp + c4) : zero4();
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const float* cf = reinterpret_cast<const float*>(&co[i][0]);
+        const bool anchor = role[i] != 2 && cf[KS] == (float)role[i];
+        const float wg = anchor ? 1.f : 0.f;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) fma4(acc, anchor ? 0.f : cf[s], rows[i][s]);
+        fma4(acc, wg, ga[i]);
+    }
+}
+
+template <int KS>
+__device__ __forceinline__ float4 pull2_range(const Pull2Args& a, int j0, int j1, int c4) {
+    constexpr int NB = (KS <= 4) ? 2 : 1;                             // incidents in flight
+    float4 acc = zero4();
+    int jb = j0;
+    for (; jb + NB <= j1; jb += NB) pull2_batch<KS, NB>(a, jb, c4, acc);
+    for (; jb < j1; ++jb) pull2_batch<KS, 1>(a, jb, c4, acc);
+    return acc;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256) k_entity_pull2_hub(Pull2Args a) {
+    const unsigned gid = flat_index();
+    const int seg = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)seg * a.fd.d);
+    if (seg >= a.n_segs) return;
+    float4 acc = pull2_range<KS>(a, a.eh_begin[seg], a.eh_end[seg], c * 4);
+    *reinterpret_cast<float4*>(a.eh_part + (size_t)seg * a.dq + c * 4) = acc;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256, (KS <= 4) ? 4 : 2) k_entity_pull2(Pull2Args a) {
+    const unsigned gid = flat_index();
+    const int slot = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)slot * a.fd.d);
+    if (slot >= a.Ne) return;
+    const int n = __ldg(a.order + slot);
+    float4 acc;
+    const int nseg = a.eh_count ? a.eh_count[n] : 0;
+    if (nseg == 0) {
+        acc = pull2_range<KS>(a, __ldg(a.inc_off + n), __ldg(a.inc_off + n + 1), c * 4);
+    } else {
+        acc = zero4();
+        const int s0 = a.eh_first[n];
+        for (int sg = 0; sg < nseg; sg += 4) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                v[i] = (sg + i < nseg) ? ldg4(a.eh_part + (size_t)(s0 + sg + i) * a.dq + c * 4) : zero4();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
+        }
+    }
+    *reinterpret_cast<float4*>(a.gE + (size_t)n * a.dq + c * 4) = acc;
+}
+
+// ==========================================================================================
 // K8  word-gradient pull + regulariser for the word block          NTN.java:411-430,437-438
 //     gWV[w] = (1/B) sum_{n : w in words(n)} gE[n]/len_n  + lambda*theta_w ;  reg += theta_w^2
 //     Sorted-segment pull over the inverse (word -> entity) CSR: deterministic, no float atomics.
@@ -686,7 +1066,7 @@ struct WordArgs {
     const int *wh_first, *wh_count, *wh_begin, *wh_end, *hub_words;
     float* wh_part;
     double* reg_part;      // [word blocks | hub words | small-block finalize]
-    int Nw, dq, n_segs, n_hub_words, n_word_blocks;
+    int Nw, d, dq, n_segs, n_hub_words, n_word_blocks;
     int64_t oWV;
     float inv_B, lam;
     FastDiv fd;                          // threads per row = dq / 4
@@ -717,7 +1097,16 @@ __device__ __forceinline__ float4 word_range(const WordArgs& a, int j0, int j1, 
     return acc;
 }
 
-__device__ __forceinline__ float word_store(const WordArgs& a, size_t o, const float4& th, const float4& acc) {
+// c4 = first column of this float4 chunk.  The internal word rows are dq = ceil4(d) wide: the padding columns are not
+// parameters (the host layout has none), so their gradient is written as 0 and they stay out of the regulariser --
+// gE's padding columns carry the bias product of the anchor rows (GA[u][d]) and must not leak into the optimiser.
+__device__ __forceinline__ float word_store(const WordArgs& a, size_t o, float4 th, float4 acc, int c4) {
+    if (c4 + 4 > a.d) {
+        if (c4 + 1 > a.d) { th.x = 0.f; acc.x = 0.f; }
+        if (c4 + 2 > a.d) { th.y = 0.f; acc.y = 0.f; }
+        if (c4 + 3 > a.d) { th.z = 0.f; acc.z = 0.f; }
+        th.w = 0.f; acc.w = 0.f;
+    }
     float4 g = make_float4(fmaf(a.lam, th.x, acc.x * a.inv_B), fmaf(a.lam, th.y, acc.y * a.inv_B),
                            fmaf(a.lam, th.z, acc.z * a.inv_B), fmaf(a.lam, th.w, acc.w * a.inv_B));
     *reinterpret_cast<float4*>(a.grad + o) = g;                      // :429,438
@@ -773,7 +1162,7 @@ __global__ void __launch_bounds__(1024) k_word_finish_hub(WordArgs a) {
             for (int ww = 1; ww < 32; ++ww) { float4 v = s_acc[ww][c][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
             if (cv[c]) {
                 size_t o = (size_t)a.oWV + (size_t)w * a.dq + (lane + 32 * c) * 4;
-                reg += word_store(a, o, ldg4(a.theta + o), t);
+                reg += word_store(a, o, ldg4(a.theta + o), t, (lane + 32 * c) * 4);
             }
         }
         reg = warp_sum(reg);
@@ -781,27 +1170,34 @@ __global__ void __launch_bounds__(1024) k_word_finish_hub(WordArgs a) {
     }
 }
 
-// one thread per (word, float4 chunk); hub words are finished by k_word_finish_hub
-__global__ void __launch_bounds__(256, 5) k_word_pull(WordArgs a) {
+// one thread per (word pair, float4 chunk): words w and w + half, two independent record -> entity-row chains in flight
+// per thread (the kernel is a few waves of dependent DRAM round trips); hub words are finished by k_word_finish_hub
+__device__ __forceinline__ float word_one(const WordArgs& a, int w, int c, const int4& rec, const float4& th, size_t o) {
+    if (rec.w != 0) return 0.f;                                      // hub words are finished elsewhere
+    float4 acc = zero4();
+    if (rec.y - rec.x == 1) {                                        // the common case: exactly one entity
+        const float inv = __ldg(a.inv_len + rec.z);
+        float4 v = ldg4(a.gE + (size_t)rec.z * a.dq + c * 4);
+        acc = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    } else if (rec.y > rec.x) {
+        acc = word_range<4>(a, rec.x, rec.y, c);
+    }
+    return word_store(a, o, th, acc, c * 4);
+}
+__global__ void __launch_bounds__(256, 4) k_word_pull(WordArgs a, int half) {
     __shared__ double s_reg[8];
     const unsigned gid = flat_index();
     const int w = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)w * a.fd.d);
     float reg = 0.f;
-    if (w < a.Nw) {
-        const int4 rec = __ldg(a.w_rec + w);
-        if (rec.w == 0) {                                            // hub words are finished elsewhere
-            size_t o = (size_t)a.oWV + (size_t)w * a.dq + c * 4;
-            float4 th = ldg4(a.theta + o);
-            float4 acc = zero4();
-            if (rec.y - rec.x == 1) {                                // the common case: exactly one entity
-                const float inv = __ldg(a.inv_len + rec.z);
-                float4 v = ldg4(a.gE + (size_t)rec.z * a.dq + c * 4);
-                acc = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
-            } else if (rec.y > rec.x) {
-                acc = word_range<4>(a, rec.x, rec.y, c);                // main kernel: keep registers (occupancy) low
-            }
-            reg = word_store(a, o, th, acc);
-        }
+    if (w < half) {
+        const int w2 = w + half;
+        const bool two = w2 < a.Nw;
+        const size_t o1 = (size_t)a.oWV + (size_t)w * a.dq + c * 4, o2 = (size_t)a.oWV + (size_t)(two ? w2 : w) * a.dq + c * 4;
+        const int4 r1 = __ldg(a.w_rec + w);
+        const int4 r2 = __ldg(a.w_rec + (two ? w2 : w));
+        const float4 t1 = ldg4(a.theta + o1), t2 = ldg4(a.theta + o2);
+        reg = word_one(a, w, c, r1, t1, o1);
+        if (two) reg += word_one(a, w2, c, r2, t2, o2);
     }
     reg = warp_sum(reg);
     if ((threadIdx.x & 31) == 0) s_reg[threadIdx.x >> 5] = (double)reg;
@@ -1007,8 +1403,9 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 void ntn_launch_entity_build(ntn_handle* h, const float* wvt) {
     const NtnDims& dm = h->dm;
-    k_entity_build<<<cdiv((int64_t)dm.Ne * (dm.Kp / 4), 256), 256, 0, h->stream>>>(wvt, h->w.fwd_rec, h->w.fwd_idx, h->E,
-                                                                                   dm.Ne, dm.d, dm.dq, dm.Kp, make_fastdiv((unsigned)(dm.Kp / 4)));
+    const int half = (dm.Ne + 1) / 2;
+    k_entity_build<<<cdiv((int64_t)half * (dm.Kp / 4), 256), 256, 0, h->stream>>>(wvt, h->w.fwd_rec, h->w.fwd_idx, h->E,
+                                                                                 dm.Ne, half, dm.d, dm.dq, dm.Kp, make_fastdiv((unsigned)(dm.Kp / 4)));
     h->launches++;
 }
 
@@ -1070,6 +1467,28 @@ void ntn_launch_score(ntn_handle* h, const float* theta) {
                 dm.d, dm.dq, dm.Kp, dm.Np, dm.oU};
     int ch = cdiv(dm.dq / 4, 32);
     const bool tanh_act = h->cfg.activation == NTN_ACT_TANH;
+    if (!h->b.use_gv) {
+        // default: lane-per-(triple, slice) kernel writing packed coefficient records (tiles of ntn_score2_rows(k) triples)
+        Score2Args s2{theta, h->E, h->b.T, h->b.M, h->b.crec, h->b.Nu, h->b.RS, h->b.st_rel, h->b.st_u0, h->b.st_n,
+                      h->b.u_e1, h->b.u_e2, h->b.c_off, h->b.c_e3, h->side, h->b.tp_cost, h->b.tp_nact, h->b.tp_dU,
+                      dm.d, dm.dq, dm.Kp, dm.Np, dm.oU};
+#define SC2_LAUNCH(KSv, ACTv, DQv)                                                                                       \
+        do {                                                                                                             \
+            const size_t smem = (size_t)SC2_WARPS * Score2Shape<KSv>::G * (KSv + SC2_NC + 1) * dm.dq * sizeof(float);    \
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k_score2<KSv, ACTv, DQv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            k_score2<KSv, ACTv, DQv><<<h->b.nstiles, SC2_WARPS * 32, smem, h->stream>>>(s2);                             \
+        } while (0)
+        if (dm.k == 3 && dm.dq == 100) {
+            if (tanh_act) SC2_LAUNCH(3, NTN_ACT_TANH, 100); else SC2_LAUNCH(3, NTN_ACT_SIGMOID, 100);
+        } else if (dm.k == 8 && dm.dq == 256) {
+            if (tanh_act) SC2_LAUNCH(8, NTN_ACT_TANH, 256); else SC2_LAUNCH(8, NTN_ACT_SIGMOID, 256);
+        } else {
+            DISPATCH_KS(dm.k, { if (tanh_act) SC2_LAUNCH(KS, NTN_ACT_TANH, 0); else SC2_LAUNCH(KS, NTN_ACT_SIGMOID, 0); });
+        }
+#undef SC2_LAUNCH
+        h->launches++;
+        return;
+    }
     DISPATCH_KS(dm.k, DISPATCH_CH(ch, {
         if (h->b.use_gv) {
             if (tanh_act) k_score<KS, CH, NTN_ACT_TANH, true><<<h->b.nstiles, 256, 0, h->stream>>>(a);
@@ -1082,9 +1501,31 @@ void ntn_launch_score(ntn_handle* h, const float* theta) {
     h->launches++;
 }
 
+int ntn_score2_rows(int k) {
+    int g = 4;
+    DISPATCH_KS(k, { g = Score2Shape<KS>::G; });
+    return SC2_WARPS * g;
+}
+
 void ntn_launch_entity_pull(ntn_handle* h) {
     const NtnDims& dm = h->dm;
     const DeviceBatch& b = h->b;
+    if (!b.use_gv) {
+        Pull2Args a{b.T, b.crec, b.GA, b.inc, b.inc_off, b.ent_order, h->gE,
+                    b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
+                    b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.RS, b.n_ent_hub_segs,
+                    make_fastdiv((unsigned)(dm.dq / 4))};
+        const int cpr2 = dm.dq / 4;
+        DISPATCH_KS(dm.k, {
+            if (b.n_ent_hub_segs) {
+                k_entity_pull2_hub<KS><<<cdiv((int64_t)b.n_ent_hub_segs * cpr2, 256), 256, 0, h->stream>>>(a);
+                h->launches++;
+            }
+            k_entity_pull2<KS><<<cdiv((int64_t)dm.Ne * cpr2, 256), 256, 0, h->stream>>>(a);
+        });
+        h->launches++;
+        return;
+    }
     PullArgs a{b.T, b.acoef, b.GV, b.GA, b.inc, b.inc_off, h->side, h->gE,
                b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
                b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.n_ent_hub_segs, make_fastdiv((unsigned)(dm.dq / 4))};
@@ -1101,13 +1542,13 @@ void ntn_launch_entity_pull(ntn_handle* h) {
     h->launches++;
 }
 
-static int word_pull_blocks(const NtnDims& dm) { return cdiv((int64_t)dm.Nw * (dm.dq / 4), 256); }
+static int word_pull_blocks(const NtnDims& dm) { return cdiv((int64_t)((dm.Nw + 1) / 2) * (dm.dq / 4), 256); }   // two words per thread
 
 void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad) {
     const NtnDims& dm = h->dm;
     const DeviceWords& w = h->w;
     WordArgs a{h->gE, w.len_bwd /* reciprocals */, theta, grad, w.w_off, w.w_ent, w.w_rec, w.wh_first, w.wh_count, w.wh_begin, w.wh_end,
-               w.hub_words, w.wh_part, h->reg_part, dm.Nw, dm.dq, w.n_hub_segs, w.n_hub_words, word_pull_blocks(dm),
+               w.hub_words, w.wh_part, h->reg_part, dm.Nw, dm.d, dm.dq, w.n_hub_segs, w.n_hub_words, word_pull_blocks(dm),
                dm.oWVint, 1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale, make_fastdiv((unsigned)(dm.dq / 4))};
     const int cpr = dm.dq / 4;
     int ch = cdiv(cpr, 32);
@@ -1120,7 +1561,7 @@ void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad) {
         cudaEventRecord(h->ev_join, h->stream2);
         h->launches += 2;
     }
-    k_word_pull<<<word_pull_blocks(dm), 256, 0, h->stream>>>(a);
+    k_word_pull<<<word_pull_blocks(dm), 256, 0, h->stream>>>(a, (dm.Nw + 1) / 2);
     if (w.n_hub_segs) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
     h->launches++;
 }

@@ -7,11 +7,13 @@ from oracle.java_random import JavaRandom
 
 
 def small_problem(Ne=40, R=3, T=60, Nw=30, d=6, k=3, batch=25, corrupt=3, lam=1e-4,
-                  seed=0, activation="tanh", oov_frac=0.05):
+                  seed=0, activation="tanh", oov_frac=0.05, divisor=None):
+    """divisor: the reference's batchSize, the divisor of cost and gradient (NTN.java:398-401,429-430); defaults to
+    the number of training triples in the batch job."""
     kb = synth.make_kb(Ne, R, T, Nw, d, oov_frac=oov_frac, seed=seed)
     vocab = {w: i for i, w in enumerate(kb.vocab_words)}
     fo, fi, bo, bi, lb = data_ref.build_entity_word_maps(kb.entity_names, vocab)
-    p = ntn_ref.NTNProblem(d=d, k=k, R=R, Ne=Ne, Nw=Nw, lam=lam, batch_size=batch,
+    p = ntn_ref.NTNProblem(d=d, k=k, R=R, Ne=Ne, Nw=Nw, lam=lam, batch_size=divisor or batch,
                            fwd_off=fo, fwd_idx=fi, bwd_off=bo, bwd_idx=bi, len_bwd=lb,
                            activation=activation)
     e1, rel, e2, e3 = data_ref.generate_batch_job(kb.train[:, 0], kb.train[:, 1], kb.train[:, 2],
