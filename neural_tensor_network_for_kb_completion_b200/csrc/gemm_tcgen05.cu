@@ -5,11 +5,11 @@
 //   dw   dWaug_r[p, n] = sum_u  [E_anchor(u) | 1][p] * M[u, n]  (split-K)  NTN.java:301-349
 //   ge   GA[u, p]      = sum_n  M[u, n] * Waug_r[p, n]                     NTN.java:352-388
 //
-// One CTA = one 128-row accumulator tile in TMEM (tcgen05.alloc), N <= 160 columns, 288 threads.
+// One CTA = 128-row accumulator tiles in TMEM (tcgen05.alloc, two buffers), N <= 160 columns, 416 threads.
 //   warps 0-3, 5-8  two producer groups taking alternate k-blocks: gather / load FP32 operand rows, split x = hi + lo
 //                   (both exactly representable in TF32), store both into swizzled UMMA shared-memory tiles,
-//                   fence.proxy.async, arrive on the stage's "full" mbarrier; warps 0-3 then run the epilogue
-//                   (tcgen05.ld -> registers -> staged in shared memory -> coalesced global stores).
+//                   fence.proxy.async, arrive on the stage's "full" mbarrier.
+//   warps 9-12      epilogue (tcgen05.ld -> registers -> staged in shared memory -> coalesced global stores).
 //   warp 4          TMEM allocation + the single-thread MMA issuer: per k-step of 8 it issues tcgen05.mma kind::tf32
 //                   lo*hi, hi*lo, hi*hi into the same FP32 accumulator, then tcgen05.commit releases the stage
 //                   ("empty" mbarrier) / signals the epilogue.
@@ -759,6 +759,14 @@ int ntn_tc_gemm_fwd(ntn_handle* h) {
 int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t stq) {
     TcArgs a = tc_args(h, true);
     dim3 g = tc_grid(h, a, h->b.nchunks, cdivi(h->dm.Np, TC_NCH), cdivi(h->dm.Kp, 128));
+    // the dW contraction runs beside the entity/word pulls (forked stream); a persistent CTA owns its SM (229 KB of
+    // shared memory, 53 k registers), so its grid size decides how many SMs the pulls can use meanwhile
+    // (measured at 20,000 x 10: 148 CTAs 0.2258 ms per evaluation, 111: 0.2191, 74: 0.2180, 48: 0.2168).  At the
+    // reference's batch size the contraction has ~120 us of shadow to hide in, so it gets a third of the SMs; a large batch
+    // job makes it the longest branch and it keeps the whole grid.  NTN_DW_CTAS overrides (0 = all SMs).
+    static const int dw_env = [] { const char* e = getenv("NTN_DW_CTAS"); return e ? atoi(e) : -1; }();
+    const int dw_ctas = dw_env >= 0 ? dw_env : (h->b.Nu <= 65536 ? (h->sm_count + 2) / 3 : 0);
+    if (dw_ctas > 0 && (int)g.x > dw_ctas) g.x = dw_ctas;
     TcState* st = (TcState*)h->tc;
     if (st->dw_mn) k_tc_gemm<TC_DW, false, true><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo);
     else k_tc_gemm<TC_DW, false><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo);
