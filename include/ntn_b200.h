@@ -84,8 +84,9 @@ int64_t ntn_dimension(const ntn_handle* h);
  * (DataFactory.java:405-434, with multiplicity, "unknown" fallback already applied);
  * bwd_* is getWordIndexes(i) (DataFactory.java:646-684) and len_bwd[i] = entityLength(i)
  * (:583-595), the divisor in NTN.java:420.  bwd_off/bwd_idx may be NULL (= forward lists).
- * Word ids in [0,Nw); every entity needs >= 1 forward word; len_bwd[i] <= 0 is rejected
- * (the reference divides by zero there, App. B8).  Host pointers; copied. */
+ * Word ids in [0,Nw); every entity needs >= 1 forward word; len_bwd[i] < 0 is rejected.  len_bwd[i] == 0 (the
+ * Wordnet name "__2", DataFactory.java:650: the reference divides by zero there, App. B8) is accepted and that
+ * entity contributes nothing to the word gradient.  Host pointers; copied. */
 int ntn_set_entity_words(ntn_handle* h,
                          const int32_t* fwd_off /* Ne+1 */, const int32_t* fwd_idx,
                          const int32_t* bwd_off /* Ne+1 or NULL */, const int32_t* bwd_idx,
@@ -235,6 +236,11 @@ int ntn_host_fastdiv(uint32_t d, int64_t count, const uint32_t* n, uint32_t* q);
  * Util.java:49-55 rounding), exposed so that the CPU tests can check them on unaligned and ragged ranges. */
 int ntn_host_convert_f64_f32(const double* src, float* dst, int64_t n);
 int ntn_host_convert_f32_f64(const float* src, double* dst, int64_t n);
+
+/* Theta checkpoints of the C++ host (Run_NTN.java:133-139; resume :108): write n values to `path` as the reference's
+ * comma-separated text (binary == 0) or as the binary fast path ("NTNTHETA" | u32 1 | u32 32 | i64 P | P x f32), then read
+ * them back -- every FP32 value must round-trip bit for bit. */
+int ntn_host_theta_checkpoint_roundtrip(const char* path, int32_t binary, const double* theta, int64_t n, double* back);
 
 const char* ntn_version(void);
 

@@ -96,6 +96,7 @@ SYMBOLS = {
     "ntn_host_convert_f64_f32": (C.c_int, [_P, _P, C.c_int64]),
     "ntn_host_convert_f32_f64": (C.c_int, [_P, _P, C.c_int64]),
     "ntn_host_generate_batch": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),
+    "ntn_host_theta_checkpoint_roundtrip": (C.c_int, [C.c_char_p, C.c_int32, _P, C.c_int64, _P]),
     "ntn_version": (C.c_char_p, []),
 }
 

@@ -3,6 +3,7 @@
 // and the NTN function object -- so that a compiled host can drive libntn_b200.so the way Run_NTN.java does.
 // Header-only; used by run_ntn.cpp (CLI) and host_capi.cpp (test hooks checked against the oracle).
 #pragma once
+#include <sys/stat.h>
 #include <cmath>
 #include <cstdint>
 #include <fstream>
@@ -183,6 +184,57 @@ public:
 };
 
 // The NTN function object (NTN.java:19-84, 92-448) over the C-ABI.
+// ---- theta checkpoints (Run_NTN.java:133-139: Nd4j.writeTxt(theta, path, ","); resume: the commented :108) ----------
+// Text: one comma-separated line of P floats, 9 significant digits (every FP32 value round-trips bit for bit).
+// Binary fast path: "NTNTHETA" | uint32 version = 1 | uint32 dtype = 32 | int64 P | P little-endian float32.
+inline void writeThetaTxt(const std::vector<double>& th, const std::string& path) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("cannot write " + path);
+    for (size_t i = 0; i < th.size(); ++i) fprintf(f, i ? ",%.9g" : "%.9g", (double)(float)th[i]);
+    fclose(f);
+}
+inline void writeThetaBin(const std::vector<double>& th, const std::string& path) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot write " + path);
+    const uint32_t hdr[2] = {1u, 32u};
+    const int64_t P = (int64_t)th.size();
+    std::vector<float> v(th.begin(), th.end());
+    fwrite("NTNTHETA", 1, 8, f); fwrite(hdr, 4, 2, f); fwrite(&P, 8, 1, f); fwrite(v.data(), 4, v.size(), f);
+    fclose(f);
+}
+// reads either format (the binary one is recognised by its magic); returns false if the file does not exist
+inline bool readTheta(const std::string& path, std::vector<double>& th) {
+    struct stat sb;
+    if (stat(path.c_str(), &sb) != 0 || !S_ISREG(sb.st_mode)) return false;     // missing, or a directory
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char magic[8] = {0};
+    size_t got = fread(magic, 1, 8, f);
+    if (got == 8 && std::string(magic, 8) == "NTNTHETA") {
+        uint32_t hdr[2]; int64_t P = 0;
+        if (fread(hdr, 4, 2, f) != 2 || fread(&P, 8, 1, f) != 1 || hdr[0] != 1u || hdr[1] != 32u || P < 0) { fclose(f); throw std::runtime_error("bad theta header in " + path); }
+        std::vector<float> v((size_t)P);
+        if (fread(v.data(), 4, (size_t)P, f) != (size_t)P) { fclose(f); throw std::runtime_error("truncated theta file " + path); }
+        th.assign(v.begin(), v.end());
+    } else {
+        fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+        std::string buf((size_t)n, '\0');
+        if (fread(&buf[0], 1, (size_t)n, f) != (size_t)n) { fclose(f); throw std::runtime_error("cannot read " + path); }
+        th.clear();
+        const char* p = buf.c_str();
+        while (*p) {
+            char* e = nullptr;
+            double v = strtod(p, &e);
+            if (e == p) break;
+            th.push_back((double)(float)v);
+            p = e;
+            while (*p == ',' || *p == ' ' || *p == '\n' || *p == '\r') ++p;
+        }
+    }
+    fclose(f);
+    return true;
+}
+
 class NTN {
     ntn_handle* h_ = nullptr;
     DataFactory* tbj_;

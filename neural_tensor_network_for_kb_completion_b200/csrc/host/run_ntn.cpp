@@ -3,6 +3,7 @@
 // sampler: "reference" (default: host java.util.Random stream, first batch_size triples, DataFactory.java:116-136),
 // "shuffle" (re-enables the Collections.shuffle commented out at :118), "device" / "device-filter" (batch job generated
 // and indexed in HBM by the counter-based sampler, ntn_generate_batch_dev; with "-filter" known true triples are redrawn).
+// theta_load_path: a checkpoint to resume from (text as written below, or its .bin twin); ignored if it does not exist.
 // data_path holds entities.txt, relations.txt, train.txt, dev.txt, test.txt (Socher layout) and wordvectors.txt
 // ("word v0 ... v{d-1}" per line; export of initEmbed.mat).  Training runs the device L-BFGS with maxIters = 5
 // per batch job (Run_NTN.java:119-124), checkpoints theta as comma-separated text (:133-139), then thresholds and
@@ -16,11 +17,10 @@
 
 using namespace ntnhost;
 
+// text checkpoint in the reference's format + the binary fast path beside it (same name, .bin)
 static void writeTheta(const std::vector<double>& th, const std::string& path) {
-    FILE* f = fopen(path.c_str(), "w");
-    if (!f) return;
-    for (size_t i = 0; i < th.size(); ++i) fprintf(f, i ? ",%.9g" : "%.9g", (double)(float)th[i]);
-    fclose(f);
+    writeThetaTxt(th, path);
+    writeThetaBin(th, path.substr(0, path.size() - 4) + ".bin");
 }
 
 int main(int argc, char** argv) {
@@ -56,6 +56,16 @@ int main(int argc, char** argv) {
         for (int i = 0; i < R * k; ++i) theta[o++] = 0.01;
         for (int i = 0; i < R * k; ++i) theta[o++] = 0.8;
         for (float v : tbj.wordVectorMaxtrixLoaded) theta[o++] = v;
+        // resume (the reference parses theta_load_path but only has the load commented out, Run_NTN.java:64,108):
+        // a text or binary checkpoint of the right dimension replaces the initial theta
+        {
+            std::vector<double> loaded;
+            if (readTheta(theta_load_path, loaded)) {
+                if ((int64_t)loaded.size() != P) throw std::runtime_error("theta_load_path holds " + std::to_string(loaded.size()) + " values, the model has " + std::to_string(P));
+                theta = loaded;
+                printf("theta loaded from %s\n", theta_load_path.c_str());
+            }
+        }
         float* d_theta = nullptr;
         if (cudaMalloc((void**)&d_theta, (size_t)ntn_internal_dimension(t.handle()) * sizeof(float)) != cudaSuccess) throw std::runtime_error("cudaMalloc");
         if (ntn_upload_theta(t.handle(), theta.data(), d_theta)) throw std::runtime_error(ntn_last_error(t.handle()));

@@ -86,4 +86,17 @@ int ntn_host_collections_shuffle(int64_t seed, int32_t n, int32_t* perm) {
     for (int i = n; i > 1; --i) std::swap(perm[i - 1], perm[r.nextInt(i)]);
     return NTN_OK;
 }
+
+// theta checkpoints of the C++ host (csrc/host/ntn_host.hpp; Run_NTN.java:133-139 and the resume of :108):
+// write n values as text (binary != 0: the binary fast path) to `path`, read them back into `back`
+int ntn_host_theta_checkpoint_roundtrip(const char* path, int32_t binary, const double* theta, int64_t n, double* back) {
+    if (!path || n < 0 || (n > 0 && (!theta || !back))) return NTN_EINVAL;
+    try {
+        std::vector<double> th(theta, theta + n), got;
+        if (binary) writeThetaBin(th, path); else writeThetaTxt(th, path);
+        if (!readTheta(path, got) || (int64_t)got.size() != n) return NTN_EINVAL;
+        for (int64_t i = 0; i < n; ++i) back[i] = got[(size_t)i];
+        return NTN_OK;
+    } catch (...) { return NTN_EINVAL; }
+}
 }  // extern "C"

@@ -285,8 +285,8 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
     for (int n = 0; n < dm.Ne; ++n) {
         if (fwd_off[n + 1] <= fwd_off[n]) FAIL(NTN_EINVAL, "entity " + std::to_string(n) + " has no forward word");
         if (bwd_off[n + 1] < bwd_off[n]) FAIL(NTN_EINVAL, "backward CSR offsets not monotone");
-        if (len_bwd[n] <= 0)
-            FAIL(NTN_EINVAL, "entityLength(" + std::to_string(n) + ") <= 0: the reference divides by zero here (NTN.java:420)");
+        if (len_bwd[n] < 0)
+            FAIL(NTN_EINVAL, "entityLength(" + std::to_string(n) + ") < 0");
     }
     int nf = fwd_off[dm.Ne], nb = bwd_off[dm.Ne];
     for (int j = 0; j < nf; ++j) if (fwd_idx[j] < 0 || fwd_idx[j] >= dm.Nw) FAIL(NTN_EINVAL, "forward word index out of range");
@@ -306,7 +306,11 @@ extern "C" int ntn_set_entity_words(ntn_handle* h, const int32_t* fwd_off, const
             for (int j = bwd_off[n]; j < bwd_off[n + 1]; ++j) went[cur[bwd_idx[j]]++] = n;
     }
     std::vector<float> lb(dm.Ne);
-    for (int n = 0; n < dm.Ne; ++n) lb[n] = (float)(1.0 / (double)len_bwd[n]);   // the kernels multiply by 1/len (NTN.java:420 divides)
+    // the kernels multiply by 1/len (NTN.java:420 divides).  entityLength == 0 happens on the real Wordnet list (the
+    // name "__2", DataFactory.java:650): the reference divides that entity's gradient column by zero; here the entity
+    // simply contributes nothing to the word gradient (weight 0), which is what the guard at NTN.java:417 does for
+    // every entity whose column is zero.
+    for (int n = 0; n < dm.Ne; ++n) lb[n] = len_bwd[n] > 0 ? (float)(1.0 / (double)len_bwd[n]) : 0.f;
     std::vector<int> sr, sb, se, first, count;
     build_hub_segments(woff, dm.Nw, sr, sb, se, first, count, NTN_WORD_HUB_SEG, NTN_HUB_SEG);
     w.n_hub_segs = (int)sr.size();

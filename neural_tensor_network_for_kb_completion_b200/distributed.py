@@ -150,6 +150,28 @@ class GradientExchange:
     def all_reduce(self, t):
         self._ops()[self.variant](t)
 
+    def bind_fused(self, handles, buffers=None):
+        """Hand the symmetric gradient buffers (and their peers' addresses) to the library so that every ntn_eval_dev
+        into one of them ends with the full-batch gradient: the exchange runs inside the evaluation, on the library's
+        own peer-memory kernels (csrc/exchange.cu), overlapped with the word pull.  Returns False when symmetric memory
+        or the entry point is unavailable (the caller then all-reduces after the evaluation)."""
+        if not self.symm or self.world == 1:
+            return False
+        from . import _capi
+        lib = _capi.load()
+        if not hasattr(lib, "ntn_exchange_bind"):
+            return False
+        import torch.distributed._symmetric_memory as symm
+        buffers = self.buffers if buffers is None else buffers
+        ok = True
+        for h in handles:
+            for t in buffers:
+                hdl = symm.rendezvous(t, self.group_name)
+                ok = ok and h.exchange_bind(hdl.rank, hdl.world_size, [int(p) for p in hdl.buffer_ptrs],
+                                            [int(p) for p in hdl.signal_pad_ptrs], int(getattr(hdl, "multicast_ptr", 0) or 0),
+                                            t.numel())
+        return ok
+
 
 def device_view(ptr: int, n: int, device):
     """torch float32 view of n device floats at ``ptr`` (memory owned by the library)."""

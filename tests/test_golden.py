@@ -43,3 +43,30 @@ def test_cuda_path_matches_golden(tag, s, path):
     assert abs(cost - float(G[f"{tag}_{s}_cost"])) <= 1e-6 + 1e-4 * abs(float(G[f"{tag}_{s}_cost"]))
     assert np.all(np.abs(grad - G[f"{tag}_{s}_grad"]) <= 1e-6 + 1e-4 * np.abs(G[f"{tag}_{s}_grad"]))
     h.close()
+
+
+def test_headline_golden_vector_matches_the_oracle():
+    """tests/golden/c3_fullsize.npz (the headline workload of bench.py: Freebase shape, 20,000 x 10) against a fresh
+    float64 oracle run on inputs rebuilt from bench.py's own functions: the fixture is what the committed oracle and
+    generator (tests/golden/make_c3_golden.py) produce.  ~30 s of CPU."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from oracle import ntn_ref
+    g = np.load(bench.GOLDEN_C3)
+    kb, p, maps, batch, side, theta0 = bench.headline_problem()
+    theta = bench.theta_trained_like(theta0, seed=int(g["theta_seed"])).astype(np.float64)
+    assert [int(x.astype(np.int64).sum()) for x in batch] == g["batch_checksum"].tolist()
+    assert np.array_equal(side, g["side"])
+    cost, grad, aux = ntn_ref.compute_at(theta, p, *batch, side, return_aux=True)
+    assert aux["min_abs_margin"] > 2e-5                      # the guard the GPU test relies on
+    assert aux["n_active"] == int(g["n_active"])
+    assert cost == pytest.approx(float(g["cost"]), rel=1e-12)
+    assert np.allclose(grad[g["idx"].astype(np.int64)], g["grad_at_idx"], rtol=1e-10, atol=1e-16)
+    assert grad.sum() == pytest.approx(float(g["grad_sum"]), rel=1e-9)
+    # and bench.py's checker accepts the oracle's own result and rejects a perturbed one
+    ok = bench.check_against_golden(cost, grad, aux["n_active"], theta)
+    assert ok["status"] == "pass", ok
+    bad = grad.copy(); bad[int(g["idx"][1234])] += 1e-4
+    assert bench.check_against_golden(cost, bad, aux["n_active"], theta)["status"] == "FAIL"

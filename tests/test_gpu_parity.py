@@ -261,11 +261,42 @@ def test_errors_are_reported_not_fatal():
     with pytest.raises(_capi.NTNError) as ei:
         h.set_batch(batch[0], batch[1], batch[2], bad)
     assert ei.value.code == _capi.NTN_EINVAL
-    lb = p.len_bwd.copy(); lb[2] = 0
-    with pytest.raises(_capi.NTNError) as ei:                     # App. B8: division by zero in the reference
+    lb = p.len_bwd.copy(); lb[2] = -1
+    with pytest.raises(_capi.NTNError) as ei:
         h.set_entity_words(p.fwd_off, p.fwd_idx, p.bwd_off, p.bwd_idx, lb)
     assert ei.value.code == _capi.NTN_EINVAL
     h.close()
+
+
+def test_entity_with_zero_length_name_loads_and_is_skipped_in_the_word_gradient():
+    """The real Wordnet entity list holds the name "__2" (DataFactory.java:650 comments on it): entityLength = 0, where
+    the reference divides that entity's gradient column by zero (NTN.java:420, App. B8).  The library accepts it and gives
+    the entity weight 0 in the word gradient; everything else equals the oracle run in which that entity has an empty
+    backward list."""
+    kb, p, batch, side, theta0 = small_problem(Ne=200, R=3, T=300, Nw=100, d=12, k=3, batch=200, corrupt=4, seed=17)
+    names = list(kb.entity_names)
+    victim = int(batch[3][0])                                        # a corrupt entity of the batch: its gradient column is non-zero
+    names[victim] = "__2"
+    vocab = {w: i for i, w in enumerate(kb.vocab_words)}
+    fo, fi, bo, bi, lb = data_ref.build_entity_word_maps(names, vocab)
+    assert lb[victim] == 0 and fo[victim + 1] - fo[victim] == 1     # forward: the "unknown" fallback
+    theta = f32(spread(perturbed(theta0, 0.05), p, u=4.0, w=10.0, wv=3.0))
+    h = _capi.Handle(p.d, p.k, p.R, p.Ne, p.Nw, p.batch_size, p.lam, wv_source="theta")
+    h.set_entity_words(fo, fi, bo, bi, lb)
+    h.set_batch(*batch)
+    cost, grad, nact = h.eval(theta, side)
+    h.close()
+    assert np.all(np.isfinite(grad))
+    # oracle: same forward maps, the victim's backward list removed (and a harmless divisor)
+    keep = np.ones(len(bi), bool); keep[bo[victim]:bo[victim + 1]] = False
+    bo2 = bo.copy(); bo2[victim + 1:] -= (bo[victim + 1] - bo[victim])
+    lb2 = lb.copy(); lb2[victim] = 1
+    p2 = ntn_ref.NTNProblem(d=p.d, k=p.k, R=p.R, Ne=p.Ne, Nw=p.Nw, lam=p.lam, batch_size=p.batch_size,
+                            fwd_off=fo, fwd_idx=fi, bwd_off=bo2, bwd_idx=bi[keep], len_bwd=lb2)
+    c_ref, g_ref, aux = ntn_ref.compute_at(theta, p2, *batch, side, return_aux=True)
+    assert aux["min_abs_margin"] > 2e-5 and nact == aux["n_active"]
+    assert abs(cost - c_ref) <= ATOL + RTOL * abs(c_ref)
+    assert np.all(np.abs(grad - g_ref) <= ATOL + RTOL * np.abs(g_ref))
 
 
 @pytest.mark.parametrize("shape", [
@@ -608,3 +639,29 @@ def test_internal_padding_columns_stay_zero(d):
         t = d_theta[o_wv:].reshape(p.Nw, dq).cpu().numpy()
         assert np.all(t[:, d:] == 0.0), path
         h.close()
+
+
+def test_headline_config_full_size_against_golden():
+    """BASELINE.json configs[2] at FULL size -- the exact inputs bench.py times (75,043 entities, 13 relations, d=100,
+    k=3, 20,000 x 10 columns, tcgen05 contractions) -- against the committed float64-oracle golden vector
+    (tests/golden/c3_fullsize.npz; generator tests/golden/make_c3_golden.py) at the north-star tolerance
+    1e-6 + 1e-4|ref| on cost and every stored gradient entry (1 in 37 of the 7.1 M, plus all of V, b, U), n_active exact.
+    The generator picked theta's seed so that the oracle sees no hinge margin within 2e-5 of zero (same near-tie guard as
+    check()), hence no flip allowance here."""
+    import bench
+    g = np.load(bench.GOLDEN_C3)
+    assert float(g["min_abs_margin"]) > 2e-5
+    kb, p, maps, batch, side, theta0 = bench.headline_problem()
+    theta = bench.theta_trained_like(theta0, seed=int(g["theta_seed"])).astype(np.float64)
+    h = make_handle(p, "theta", "auto")
+    h.set_batch(*batch)
+    cost, grad, nact = h.eval(theta, side)
+    assert h.gemm_path == "tcgen05"
+    res = bench.check_against_golden(cost, grad, nact, theta)
+    print(res)
+    assert res["status"] == "pass", res
+    assert res["block_l2_rel_diff_max"] <= 2e-5
+    # the float32 host entry point returns the same numbers
+    c32, g32, n32 = h.eval_f32(theta.astype(np.float32), side)
+    assert n32 == nact and c32 == cost and np.array_equal(g32.astype(np.float64), grad)
+    h.close()

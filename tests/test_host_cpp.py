@@ -135,3 +135,32 @@ def test_invariant_division_of_the_flat_thread_index(d):
     q = np.empty_like(n)
     assert lib.ntn_host_fastdiv(d, len(n), n.ctypes.data, q.ctypes.data) == 0
     np.testing.assert_array_equal(q, (n.astype(np.uint64) // np.uint64(d)).astype(np.uint32))
+
+
+def test_theta_checkpoints_round_trip_bit_exact(tmp_path):
+    """Run_NTN.java:133-139 writes theta as comma-separated text; the resume (commented out at :108) reads it back.
+    Both hosts, both formats (text and the binary fast path), and across hosts: every FP32 value comes back bit for bit."""
+    import ctypes as C
+    from neural_tensor_network_for_kb_completion_b200 import _capi, run_ntn
+    lib = _capi.load()
+    rng = np.random.default_rng(0)
+    th = np.concatenate([rng.standard_normal(5000) * 10.0 ** rng.integers(-30, 30, 5000),
+                         [0.0, -0.0, 1e-45, 3.4028235e38, -1.17549435e-38, 0.1, 1.0 / 3.0]]).astype(np.float32)
+    th64 = th.astype(np.float64)
+    bits = th.view(np.uint32)
+    for binary in (0, 1):
+        path = str(tmp_path / ("c_theta.bin" if binary else "c_theta.txt"))
+        back = np.empty_like(th64)
+        rc = lib.ntn_host_theta_checkpoint_roundtrip(path.encode(), binary, th64.ctypes.data_as(C.c_void_p), th64.size,
+                                                     back.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        assert np.array_equal(back.astype(np.float32).view(np.uint32), bits), binary
+        # the Python host reads what the C++ host wrote
+        assert np.array_equal(run_ntn.read_theta(path).astype(np.float32).view(np.uint32), bits)
+    # ... and the other way round: Python writes, C++ reads (through its round trip helper's reader) and Python reads
+    ptxt, pbin = str(tmp_path / "py_theta.txt"), str(tmp_path / "py_theta.bin")
+    run_ntn.save_checkpoint(th64, ptxt)
+    assert os.path.exists(pbin)
+    for path in (ptxt, pbin):
+        assert np.array_equal(run_ntn.read_theta(path).astype(np.float32).view(np.uint32), bits)
+    assert open(ptxt).read().count(",") == th.size - 1 and "\n" not in open(ptxt).read()      # one comma-separated line

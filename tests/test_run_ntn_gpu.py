@@ -86,9 +86,25 @@ def test_socher_files_mat_vectors_and_theta_checkpoints(tmp_path):
         assert np.array_equal(a, b)
     out = run_ntn.train_and_evaluate(tbj, cfg, theta_save_path=d, log=lambda *_: None)
     ck = os.path.join(d, "theta_opt_iteration_0.txt")
-    assert os.path.exists(ck)
-    back = run_ntn.read_theta_txt(ck)
-    assert back.shape == out["theta"].shape and np.all(np.isfinite(back))
+    assert os.path.exists(ck) and os.path.exists(ck[:-4] + ".bin")
+    # checkpoints round-trip bit for bit in FP32, text (Nd4j.writeTxt layout, Run_NTN.java:134,139) and binary
+    import time as _time
+    final = os.path.join(d, f"theta_opt{_time.localtime().tm_mday}.txt")
+    bits = np.asarray(out["theta"], np.float32).view(np.uint32)
+    for path in (final, final[:-4] + ".bin"):
+        assert np.array_equal(run_ntn.read_theta(path).astype(np.float32).view(np.uint32), bits), path
+    assert np.array_equal(run_ntn.read_theta(ck), run_ntn.read_theta(ck[:-4] + ".bin"))
+    # resume through theta_load_path (the load the reference has commented out, Run_NTN.java:64,108): with no further
+    # training the resumed run reproduces thresholds, predictions and accuracy of the run that wrote the checkpoint
+    cfg0 = run_ntn.Config(batchSize=100, numWVdimensions=8, numIterations=0, batch_iterations=2, sliceSize=2, corrupt_size=2)
+    for path in (final, final[:-4] + ".bin"):
+        again = run_ntn.train_and_evaluate(run_ntn.load_data(d, cfg0), cfg0, theta=run_ntn.read_theta(path), log=lambda *_: None)
+        assert again["accuracy"] == out["accuracy"] and again["dev_accuracy"] == out["dev_accuracy"]
+        assert np.array_equal(again["thresholds"], out["thresholds"]) and np.array_equal(again["predictions"], out["predictions"])
+    # ... and training continues from it: one more outer iteration starts at the checkpointed parameters
+    cfg1 = run_ntn.Config(batchSize=100, numWVdimensions=8, numIterations=1, batch_iterations=2, sliceSize=2, corrupt_size=2)
+    more = run_ntn.train_and_evaluate(run_ntn.load_data(d, cfg1), cfg1, theta=run_ntn.read_theta(final), log=lambda *_: None)
+    assert np.isfinite(more["history"][0][0]) and more["history"][0][1] <= more["history"][0][0]
 
 
 def test_host_java_random_is_bit_exact_with_oracle():
@@ -126,4 +142,21 @@ def test_run_ntn_binary_with_every_sampler(tmp_path, sampler):
     assert 0.0 <= acc <= 1.0
     costs = [float(l.split("|")[1]) for l in r.stdout.splitlines() if l.startswith("res:")]
     assert len(costs) == 2 and all(np.isfinite(costs))
-    assert os.path.exists(os.path.join(d, "theta_opt_iteration_0.txt"))
+    ck = os.path.join(d, "theta_opt_iteration_0.txt")
+    assert os.path.exists(ck) and os.path.exists(ck[:-4] + ".bin")
+    if sampler == "reference":
+        # resume (theta_load_path, Run_NTN.java:64,108) from the final checkpoint, text and binary, with no further training:
+        # the same theta gives the same accuracy line
+        import time as _time
+        final = os.path.join(d, f"theta_opt{_time.localtime().tm_mday}.txt")
+        for path in (final, final[:-4] + ".bin"):
+            d2 = str(tmp_path / ("resume_" + path[-3:]))
+            os.makedirs(d2)
+            r2 = subprocess.run([exe, d, path, d2, "0", sampler], capture_output=True, text=True, timeout=240)
+            assert r2.returncode == 0, r2.stderr[-2000:]
+            assert "theta loaded from" in r2.stdout
+            assert float(r2.stdout.split("Accuracy of predictions:")[1].split()[0]) == acc
+        # a checkpoint of the wrong dimension is refused
+        open(os.path.join(d, "bad.txt"), "w").write("1.0,2.0,3.0")
+        r3 = subprocess.run([exe, d, os.path.join(d, "bad.txt"), d, "0", sampler], capture_output=True, text=True, timeout=240)
+        assert r3.returncode != 0 and "theta_load_path holds 3 values" in r3.stderr
