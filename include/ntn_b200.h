@@ -152,6 +152,25 @@ double* ntn_result_dev(ntn_handle* h);
  * d_grad[ntn_internal_dimension() .. +4) = {cost_hi, cost_lo, n_active >> 12, n_active & 4095} (exact float pairs),
  * so ONE sum all-reduce of Pint+4 floats carries the gradient and the scalars.  d_grad must then have Pint+4 floats. */
 int ntn_set_grad_tail(ntn_handle* h, int on);
+/* Data-parallel hosts, gradient exchange INSIDE the evaluation (csrc/exchange.cu; NTN.java:411-430 is linear, so the
+ * per-rank gradients of the column shards add up).  The gradient buffer is a symmetric allocation: the same numel floats
+ * on every GPU of the box, every rank's copy mapped into this process (buffer_ptrs[world], this rank's own copy at
+ * [rank]), a signal pad of >= 8 KiB of zero-initialised 32-bit flags per rank (signal_pad_ptrs[world]) and, optionally,
+ * the NVSwitch multicast alias of the buffer (0: none).  After the bind -- and ntn_set_grad_tail(h, 1) -- every
+ * ntn_eval_dev whose d_grad is buffer_ptrs[rank] ends with the SUM over the ranks of gradient and {cost, n_active} tail
+ * in every rank's buffer: the word pull is cut into chunks and the library's own peer-memory kernels all-reduce chunk c
+ * while chunk c+1 is pulled.  scratch_ptrs (optional, NULL: none) is a second symmetric allocation of
+ * >= ntn_exchange_scratch_numel() floats per rank; with it the exchange runs in PUSH mode: the word-pull kernel stores
+ * every 16-byte group another rank owns straight into that rank's scratch while it computes it, and the owner only
+ * reads local memory (no peer loads).  All ranks must evaluate in lock-step (same sequence of calls).
+ * ntn_exchange_check returns 1 when a peer did not show up within 2 s (the evaluation's results are then invalid). */
+int ntn_exchange_bind(ntn_handle* h, int32_t rank, int32_t world, const uint64_t* buffer_ptrs,
+                      const uint64_t* signal_pad_ptrs, uint64_t multicast_ptr, int64_t numel,
+                      const uint64_t* scratch_ptrs, int64_t scratch_numel);
+int64_t ntn_exchange_scratch_numel(const ntn_handle* h);
+int ntn_exchange_unbind(ntn_handle* h);
+int ntn_exchange_check(ntn_handle* h);
+const char* ntn_exchange_mode(const ntn_handle* h);   /* "none", "push", "p2p" (peer loads/stores) or "multimem" (NVLS) */
 
 int64_t ntn_internal_dimension(const ntn_handle* h);
 /* reference-order FP32 device vector (P) <-> internal-order device vector */
@@ -220,6 +239,9 @@ int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, int64_t cap
 int ntn_host_java_random(int64_t seed, int32_t bound, int64_t n, int32_t* ints, int64_t m, double* doubles);
 /* n consecutive java.util.Random.nextInt(bound) draws continuing from the 48-bit state *state (updated). */
 int ntn_host_random_ints(uint64_t* state, int32_t bound, int64_t n, int32_t* out);
+/* A native ntn_sides_fn (for ntn_lbfgs_minimize): ctx = uint64_t[2 + R] {java.util.Random state, R, presence flags};
+ * one nextDouble() > 0.5 per present relation (NTN.java:146); the state is advanced in place. */
+void ntn_host_sides_draw(void* ctx, uint8_t* corrupt_side);
 /* DataFactory name parsing: '\n'-separated entity names and vocabulary -> forward / backward CSRs. */
 int ntn_host_entity_word_maps(const char* names, const char* words, int32_t* fwd_off, int32_t* fwd_idx, int32_t* bwd_off,
                               int32_t* bwd_idx, int32_t* len_bwd, int64_t cap, int64_t* nf, int64_t* nb);

@@ -71,6 +71,11 @@ SYMBOLS = {
     "ntn_last_cost": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ntn_result_dev": (_P, [_P]),
     "ntn_set_grad_tail": (C.c_int, [_P, C.c_int]),
+    "ntn_exchange_bind": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_uint64, C.c_int64, _P, C.c_int64]),
+    "ntn_exchange_scratch_numel": (C.c_int64, [_P]),
+    "ntn_exchange_unbind": (C.c_int, [_P]),
+    "ntn_exchange_check": (C.c_int, [_P]),
+    "ntn_exchange_mode": (C.c_char_p, [_P]),
     "ntn_internal_dimension": (C.c_int64, [_P]),
     "ntn_to_internal_dev": (C.c_int, [_P, _P, _P]),
     "ntn_from_internal_dev": (C.c_int, [_P, _P, _P]),
@@ -89,6 +94,7 @@ SYMBOLS = {
     "ntn_debug_fetch": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64]),
     "ntn_host_java_random": (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _P, C.c_int64, _P]),
     "ntn_host_random_ints": (C.c_int, [C.POINTER(C.c_uint64), C.c_int32, C.c_int64, _P]),
+    "ntn_host_sides_draw": (None, [_P, _P]),
     "ntn_host_entity_word_maps": (C.c_int, [C.c_char_p, C.c_char_p, _P, _P, _P, _P, _P, C.c_int64,
                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ntn_host_collections_shuffle": (C.c_int, [C.c_int64, C.c_int32, _P]),
@@ -239,6 +245,29 @@ class Handle:
     def set_grad_tail(self, on=True):
         self._ck(self.lib.ntn_set_grad_tail(self.h, int(on)))
 
+    def exchange_bind(self, rank, world, buffer_ptrs, signal_pad_ptrs, multicast_ptr, numel, scratch_ptrs=None, scratch_numel=0):
+        """Bind one symmetric gradient buffer for the in-evaluation exchange (include/ntn_b200.h: ntn_exchange_bind)."""
+        bp = np.asarray(buffer_ptrs, np.uint64)
+        sp = np.asarray(signal_pad_ptrs, np.uint64)
+        cp = None if scratch_ptrs is None else np.asarray(scratch_ptrs, np.uint64)
+        self._ck(self.lib.ntn_exchange_bind(self.h, int(rank), int(world), _ptr(bp), _ptr(sp), int(multicast_ptr), int(numel),
+                                            _ptr(cp), int(scratch_numel)))
+        return True
+
+    @property
+    def exchange_scratch_numel(self):
+        return int(self.lib.ntn_exchange_scratch_numel(self.h))
+
+    def exchange_unbind(self):
+        self._ck(self.lib.ntn_exchange_unbind(self.h))
+
+    def exchange_check(self):
+        return bool(self.lib.ntn_exchange_check(self.h))
+
+    @property
+    def exchange_mode(self):
+        return self.lib.ntn_exchange_mode(self.h).decode()
+
     @staticmethod
     def unpack_tail(tail):
         """(cost, n_active) from the 4 summed tail floats."""
@@ -289,18 +318,25 @@ class Handle:
 
     def lbfgs_minimize(self, d_theta: int, draw_sides, max_iters=5, history=0, tol=0.0, reduce=None):
         """Device-resident L-BFGS on the current batch job; ``draw_sides()`` returns this evaluation's
-        corrupt sides (uint8[R]).  Returns the LbfgsResult; theta is updated in place on the device.
+        corrupt sides (uint8[R]), or ``draw_sides`` is the uint64 state array of the native drawer (see below).  Returns the LbfgsResult; theta is updated in place on the device.
         Data parallel: ``reduce(ptr, n)`` must SUM all-reduce the n device floats at ``ptr`` in place."""
         R = self.R
-
-        def _cb(_ctx, out):
-            s = np.ascontiguousarray(draw_sides(), np.uint8)
-            for r in range(R):
-                out[r] = int(s[r])
-        cb = SIDES_FN(_cb)
+        ctx = None
+        if isinstance(draw_sides, np.ndarray):
+            # native drawer (ntn_host_sides_draw): uint64[2 + R] = {java.util.Random state, R, presence flags}; the
+            # state is advanced in place -- no interpreter call per evaluation
+            assert draw_sides.dtype == np.uint64 and draw_sides.size == 2 + R and int(draw_sides[1]) == R
+            cb = C.cast(self.lib.ntn_host_sides_draw, SIDES_FN)
+            ctx = _ptr(draw_sides)
+        else:
+            def _cb(_ctx, out):
+                s = np.ascontiguousarray(draw_sides(), np.uint8)
+                for r in range(R):
+                    out[r] = int(s[r])
+            cb = SIDES_FN(_cb)
         rcb = REDUCE_FN(lambda _ctx, ptr, n: reduce(int(ptr), int(n))) if reduce is not None else REDUCE_FN()
         opts, res = LbfgsOpts(max_iters, history, tol, rcb, None), LbfgsResult()
-        self._ck(self.lib.ntn_lbfgs_minimize(self.h, d_theta, C.byref(opts), cb, None, C.byref(res)))
+        self._ck(self.lib.ntn_lbfgs_minimize(self.h, d_theta, C.byref(opts), cb, ctx, C.byref(res)))
         return res
 
     def debug_fetch(self, name):

@@ -19,6 +19,25 @@ int ntn_host_java_random(int64_t seed, int32_t bound, int64_t n, int32_t* ints, 
     } catch (...) { return NTN_EINVAL; }
 }
 
+// A native ntn_sides_fn for hosts that are not compiled code (the Python mirror): one Math.random() > 0.5 per non-empty
+// relation, increasing r (NTN.java:120,146), on the 48-bit java.util.Random state the host hands over -- so a device
+// L-BFGS run draws its corrupt sides without calling back into the interpreter.  state[0] is the LCG state (as JavaRandom
+// holds it; read back after the run to keep the host's stream in step), state[1] = R, then R presence flags.
+void ntn_host_sides_draw(void* ctx, uint8_t* side) {
+    uint64_t* st = static_cast<uint64_t*>(ctx);
+    const uint64_t kMult = 0x5DEECE66DULL, kAdd = 0xBULL, kMask = (1ULL << 48) - 1;
+    uint64_t s = st[0];
+    const int R = (int)st[1];
+    for (int r = 0; r < R; ++r) {
+        if (!st[2 + r]) { side[r] = 0; continue; }
+        s = (s * kMult + kAdd) & kMask; const int64_t hi = (int64_t)(s >> 22);      // next(26)
+        s = (s * kMult + kAdd) & kMask; const int64_t lo = (int64_t)(s >> 21);      // next(27)
+        const double v = (double)((hi << 27) + lo) * (1.0 / (double)(1LL << 53));
+        side[r] = v > 0.5 ? 1 : 0;
+    }
+    st[0] = s;
+}
+
 // n consecutive nextInt(bound) draws continuing from *state (the 48-bit LCG state, as JavaRandom holds it); the advanced
 // state is written back.  Lets the Python DataFactory mirror draw 200k corrupt entities at native speed.
 int ntn_host_random_ints(uint64_t* state, int32_t bound, int64_t n, int32_t* out) {

@@ -211,6 +211,10 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     for (cudaEvent_t e : {h->ev_f0, h->ev_j0, h->ev_f1, h->ev_j1}) if (e) cudaEventDestroy(e);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
+    if (h->stream4) cudaStreamDestroy(h->stream4);
+    for (int i = 0; i < NTN_MAX_WORD_CHUNKS; ++i) if (h->ev_x[i]) cudaEventDestroy(h->ev_x[i]);
+    if (h->ev_xdone) cudaEventDestroy(h->ev_xdone);
+    if (h->d_xerr) cudaFree(h->d_xerr);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -648,6 +652,10 @@ static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_gr
     cudaStream_t s0 = h->stream, s1 = h->stream3;
     const bool tc = h->gemm_path_active == NTN_GEMM_TCGEN05 && h->b.ntiles > 0;
     int rc;
+    // data-parallel: when the gradient buffer is a bound symmetric allocation (and carries the {cost, n_active} tail) the
+    // all-reduce over the ranks runs inside the evaluation, chunk by chunk beside the word pull (exchange.cu)
+    const ExchangeBinding* xb = h->grad_tail ? ntn_find_binding(h, d_grad) : nullptr;
+    h->word_chunks = xb ? h->x_chunks : 1;
     // ---- fork: weight preparation runs beside the entity build
     CK(cudaEventRecord(h->ev_f0, s0));
     CK(cudaStreamWaitEvent(s1, h->ev_f0, 0));
@@ -675,9 +683,25 @@ static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_gr
     if (tc) { if ((rc = ntn_tc_gemm_ge(h))) return rc; } else ntn_launch_gemm_ge_simt(h);     // :352-388
     end(P_GE, s0);
     begin(P_EP, s0); ntn_launch_entity_pull(h); end(P_EP, s0);                                // Util.java:74-98
-    begin(P_WPULL, s0); ntn_launch_word_pull(h, d_theta, d_grad); end(P_WPULL, s0);           // :411-430
+    begin(P_WPULL, s0); ntn_launch_word_pull(h, d_theta, d_grad, xb); end(P_WPULL, s0);       // :411-430
     CK(cudaStreamWaitEvent(s0, h->ev_j1, 0));
     ntn_launch_final_reduce(h, h->grad_tail ? d_grad + h->dm.Pint : nullptr);                 // :430,437
+    if (xb) {
+        // the last word chunk (everything when the pull is not chunked) and the tail; the earlier chunks went out on
+        // the side stream while the pull was running
+        const NtnDims& dm = h->dm;
+        int w0, wn, off, nb;
+        ntn_word_chunk(dm, h->word_chunks - 1, h->word_chunks, &w0, &wn, &off, &nb);
+        // (one chunk: the word block went out under range id 1 with the pull's pushes; the small blocks ride with the tail)
+        const bool pushed = h->x_mode == 2;
+        XRange r0{dm.oWVint + (int64_t)w0 * dm.dq, (int64_t)wn * dm.dq, h->word_chunks, pushed}, r1{dm.Pint, 4, h->word_chunks + 1, false};
+        if (h->word_chunks == 1) {
+            ntn_launch_exchange(h, xb, XRange{0, dm.oWVint, 0, false}, XRange{0, 0, 0, false}, false, s0);
+        } else {
+            CK(cudaStreamWaitEvent(s0, h->ev_xdone, 0));
+        }
+        ntn_launch_exchange(h, xb, r0, r1, true, s0);
+    }
     CK(cudaMemcpyAsync(h->h_out, h->d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, s0));
     return NTN_OK;
 }

@@ -19,6 +19,29 @@
 //   Kp  = d+1 rounded up to 8     pitch of an entity row (index d holds 1.0f)
 //   Np  = k*dq+k rounded up to 16 pitch of a T'/M row: k slices of dq, then k "beta"/coef-sum slots
 // ------------------------------------------------------------------------------------------
+// Division of the flat thread index by the run-time row width (threads per row), Granlund-Montgomery style: the
+// generic 64-bit division costs ~25 instructions in every thread of the gather kernels, which are issue-bound.
+// Exact for every 32-bit n; the host checks that the grid fits 32 bits.
+struct FastDiv {
+    unsigned d, m, s;                                              // divisor, magic, shift (= ceil(log2 d) - 1, or 0)
+};
+static inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f{d, 0u, 0u};
+    if (d <= 1) return f;                                          // handled in fd_div
+    unsigned l = 0; while ((1ull << l) < d) ++l;
+    f.m = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s = l - 1;
+    return f;
+}
+__host__ __device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
+    if (f.d <= 1) return n;
+#ifdef __CUDA_ARCH__
+    const unsigned t = __umulhi(f.m, n);
+#else
+    const unsigned t = (unsigned)(((unsigned long long)f.m * n) >> 32);
+#endif
+    return (t + ((n - t) >> 1)) >> f.s;
+}
 struct NtnDims {
     int d, k, R, Ne, Nw;
     int dq, Kp, Np;
@@ -36,6 +59,11 @@ struct NtnDims {
 #define NTN_WORD_HUB_SEG 16      // ... and for hub words (their branch is a short, latency-bound tail: more, shorter segments)
 #define NTN_ORDER_CLAMP 1023    // incident counts are clamped here when the pull's visiting order is sorted
 #define NTN_RING        8        // in-flight evaluations the host may enqueue without synchronising
+#define NTN_MAX_PEERS   8        // GPUs of one box (gradient exchange over peer memory, exchange.cu)
+#define NTN_MAX_WORD_CHUNKS 8    // the word pull is cut into chunks so that the exchange of chunk c overlaps the pull of c+1
+#define NTN_XCHG_MAX_BLOCKS 64   // blocks of one exchange kernel (each pairs with the same block index on every peer)
+#define NTN_XCHG_SIG_WORD0 1024  // first 32-bit word of the signal pad used by the exchange kernels (torch's own
+                                 // symmetric-memory kernels use the words below)
 
 struct DeviceBatch {
     int64_t N = 0;               // columns
@@ -93,6 +121,29 @@ struct DeviceWords {
     float *wh_part = nullptr;                      // n_hub_segs x dq
 };
 
+// One symmetric gradient buffer bound for the in-evaluation exchange (exchange.cu): the same allocation exists on every
+// rank of the box; peer[r] is rank r's copy mapped into this process, mc the NVSwitch multicast alias (or null).
+struct ExchangeBinding {
+    float* local = nullptr;
+    float* peer[NTN_MAX_PEERS] = {};
+    float* mc = nullptr;
+    uint32_t* sig[NTN_MAX_PEERS] = {};   // signal pads (32-bit flags), same indexing as peer[]
+    float* scratch[NTN_MAX_PEERS] = {};  // second symmetric allocation (push mode): rank r's copy receives the other ranks'
+    int64_t numel = 0;                   // contributions to the slices r owns
+    int64_t scratch_numel = 0;
+};
+
+// Push mode: where the producer of a gradient range (the word pull) also stores the 16-byte groups that another rank
+// owns -- straight into that rank's scratch, over NVLink.  A range [off, off + 4 n4) is cut into `world` slices of per4
+// groups; rank r owns slice r.  dst[r] already points at this rank's row of r's scratch for this range.
+struct XPushRange {
+    float* dst[NTN_MAX_PEERS];
+    int64_t off;                         // first float of the range in the gradient vector
+    unsigned per4, per_m, per_s;         // slice length in float4 groups and its invariant-division magic
+    int rank, world;                     // world == 0: nothing to push
+};
+#define NTN_XCHG_RANGE_PAD 64            // floats between the scratch regions of consecutive ranges (slices are rounded up)
+
 struct ntn_handle {
     ntn_config cfg;
     NtnDims dm;
@@ -147,12 +198,32 @@ struct ntn_handle {
     uint64_t *d_true_keys = nullptr;   // their packed keys, sorted (filtered corrupt sampling)
     void *lbfgs_ws = nullptr;     // L-BFGS workspace (lbfgs.cu), grow-only
     size_t lbfgs_ws_bytes = 0;
+    double* lbfgs_scal = nullptr; // pinned: the optimiser's scalars (g.dir, first step, history state)
     // CUDA graphs of the evaluation, one per (theta, grad, stream) triple
     struct GraphEntry { const float* theta; float* grad; cudaStream_t stream; cudaGraphExec_t exec; int launches; };
     std::vector<GraphEntry> graphs;
     bool use_graph = true;
     bool grad_tail = false;       // the caller's gradient buffer has 4 extra floats for {cost, n_active}
+    // in-evaluation gradient exchange over peer memory (exchange.cu)
+    int x_rank = 0, x_world = 1;
+    int x_chunks = 4, x_blocks = 32, x_mode = 0;   // word-pull chunks, blocks per exchange kernel, 0: peer loads/stores, 1: multimem, 2: push
+    std::vector<ExchangeBinding> xb;
+    cudaStream_t stream4 = nullptr;               // exchange of the finished chunks, beside the word pull (highest priority)
+    cudaEvent_t ev_x[NTN_MAX_WORD_CHUNKS] = {}, ev_xdone = nullptr;
+    unsigned* d_xerr = nullptr;                   // set when a bounded flag wait expired (results invalid)
+    int word_chunks = 1;                          // chunks of the word pull in the evaluation being enqueued
 };
+
+// word-pull chunk c of C: words [w0, w0 + wn) and the first of its blocks' regulariser-partial slots
+void ntn_word_chunk(const NtnDims& dm, int c, int C, int* w0, int* wn, int* block_off, int* blocks);
+int ntn_word_blocks_total(const NtnDims& dm, int C);
+// exchange.cu: all-reduce (SUM) of up to two float ranges of the bound buffer across the ranks, in place
+struct XRange { int64_t off, n; int id; bool pushed; };   // floats; off and n are multiples of 4; id: ordinal of the range in
+                                                          // the evaluation (its scratch region); pushed: the producer already
+                                                          // stored the other ranks' slices into their scratch
+void ntn_launch_exchange(ntn_handle* h, const ExchangeBinding* xb, XRange r0, XRange r1, bool last, cudaStream_t st);
+XPushRange ntn_push_range(const ntn_handle* h, const ExchangeBinding* xb, int64_t off, int64_t n, int id);
+const ExchangeBinding* ntn_find_binding(const ntn_handle* h, const float* d_grad);
 
 // ---- batch indexing on the device (batch_index.cu)
 int ntn_index_batch_dev(ntn_handle* h, int64_t n, const int* d_e1, const int* d_rel, const int* d_e2, const int* d_e3,
@@ -171,7 +242,7 @@ int ntn_score2_rows(int k);   // tile height of the default score kernel
 void ntn_launch_gemm_dw_simt(ntn_handle* h, cudaStream_t st);
 void ntn_launch_gemm_ge_simt(ntn_handle* h);
 void ntn_launch_entity_pull(ntn_handle* h);
-void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad);
+void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad, const ExchangeBinding* xb);
 void ntn_launch_finalize_small(ntn_handle* h, const float* theta, float* grad, cudaStream_t st);
 void ntn_launch_final_reduce(ntn_handle* h, float* tail);
 void ntn_launch_to_internal(ntn_handle* h, const float* d_ref, float* d_int);

@@ -13,6 +13,7 @@
 //   GA_u = [M | coefsum] Waug_r^T        -> gradient of the anchor entity     (NTN.java:352-388)
 //   gE[O] += sum_s a T',  gE[e3_c] += sum_s c_c T'                            (Util.java:74-98)
 #include <assert.h>
+#include <algorithm>
 #include <math.h>
 #include <stdio.h>
 
@@ -38,29 +39,6 @@ __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// Division of the flat thread index by the run-time row width (threads per row), Granlund-Montgomery style: the
-// generic 64-bit division costs ~25 instructions in every thread of the gather kernels, which are issue-bound.
-// Exact for every 32-bit n; the host checks that the grid fits 32 bits.
-struct FastDiv {
-    unsigned d, m, s;                                              // divisor, magic, shift (= ceil(log2 d) - 1, or 0)
-};
-static FastDiv make_fastdiv(unsigned d) {
-    FastDiv f{d, 0u, 0u};
-    if (d <= 1) return f;                                          // handled in fd_div
-    unsigned l = 0; while ((1ull << l) < d) ++l;
-    f.m = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
-    f.s = l - 1;
-    return f;
-}
-__host__ __device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
-    if (f.d <= 1) return n;
-#ifdef __CUDA_ARCH__
-    const unsigned t = __umulhi(f.m, n);
-#else
-    const unsigned t = (unsigned)(((unsigned long long)f.m * n) >> 32);
-#endif
-    return (t + ((n - t) >> 1)) >> f.s;
-}
 // test hook (CPU): q[i] = n[i] / d through the same magic numbers the kernels use
 extern "C" int ntn_host_fastdiv(uint32_t d, int64_t count, const uint32_t* n, uint32_t* q) {
     if (d == 0 || count < 0 || (count > 0 && (!n || !q))) return NTN_EINVAL;
@@ -1100,7 +1078,8 @@ __device__ __forceinline__ float4 word_range(const WordArgs& a, int j0, int j1, 
 // c4 = first column of this float4 chunk.  The internal word rows are dq = ceil4(d) wide: the padding columns are not
 // parameters (the host layout has none), so their gradient is written as 0 and they stay out of the regulariser --
 // gE's padding columns carry the bias product of the anchor rows (GA[u][d]) and must not leak into the optimiser.
-__device__ __forceinline__ float word_store(const WordArgs& a, size_t o, float4 th, float4 acc, int c4) {
+template <bool PUSH>
+__device__ __forceinline__ float word_store(const WordArgs& a, const XPushRange& xp, size_t o, float4 th, float4 acc, int c4) {
     if (c4 + 4 > a.d) {
         if (c4 + 1 > a.d) { th.x = 0.f; acc.x = 0.f; }
         if (c4 + 2 > a.d) { th.y = 0.f; acc.y = 0.f; }
@@ -1110,8 +1089,26 @@ __device__ __forceinline__ float word_store(const WordArgs& a, size_t o, float4 
     float4 g = make_float4(fmaf(a.lam, th.x, acc.x * a.inv_B), fmaf(a.lam, th.y, acc.y * a.inv_B),
                            fmaf(a.lam, th.z, acc.z * a.inv_B), fmaf(a.lam, th.w, acc.w * a.inv_B));
     *reinterpret_cast<float4*>(a.grad + o) = g;                      // :429,438
+    if (PUSH) {
+        // data parallel, push exchange (exchange.cu): a group that another rank owns also goes straight into that rank's
+        // scratch -- a posted store over NVLink, issued where the value is produced
+        const unsigned rel4 = (unsigned)((o - (size_t)xp.off) >> 2);
+        const unsigned owner = fd_div(rel4, FastDiv{xp.per4, xp.per_m, xp.per_s});
+        if ((int)owner != xp.rank) {
+            float* dst = xp.dst[0];                                  // (selects: a dynamic index would put the table on the stack)
+#pragma unroll
+            for (int s = 1; s < NTN_MAX_PEERS; ++s) dst = (owner == (unsigned)s) ? xp.dst[s] : dst;
+            *reinterpret_cast<float4*>(dst + 4 * (size_t)(rel4 - owner * xp.per4)) = g;
+        }
+    }
     return dot4(th, th);                                             // :437
 }
+
+struct XPushAll {                        // every word chunk's push descriptor (the hub words are spread over all of them)
+    XPushRange r[NTN_MAX_WORD_CHUNKS];
+    int w_end[NTN_MAX_WORD_CHUNKS];      // chunk c holds words [w_end[c-1], w_end[c])
+    int n;                               // 0: no push
+};
 
 // one thread per (hub segment, float4 chunk)
 __global__ void __launch_bounds__(256) k_word_pull_hub(WordArgs a) {
@@ -1124,8 +1121,8 @@ __global__ void __launch_bounds__(256) k_word_pull_hub(WordArgs a) {
 
 // one block (32 warps) per hub word: every warp sums an interleaved subset of the partial rows into
 // 8 independent accumulators (8 loads in flight), then a fixed-order combine.  Lanes over float4 chunks.
-template <int CH>
-__global__ void __launch_bounds__(1024) k_word_finish_hub(WordArgs a) {
+template <int CH, bool PUSH>
+__global__ void __launch_bounds__(1024) k_word_finish_hub(WordArgs a, XPushAll xa) {
     __shared__ float4 s_acc[32][CH][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = a.hub_words[blockIdx.x];
@@ -1156,13 +1153,18 @@ __global__ void __launch_bounds__(1024) k_word_finish_hub(WordArgs a) {
     __syncthreads();
     if (warp == 0) {
         float reg = 0.f;
+        XPushRange xp = xa.r[0];
+        if (PUSH) {
+#pragma unroll
+            for (int i = 1; i < NTN_MAX_WORD_CHUNKS; ++i) if (i < xa.n && w >= xa.w_end[i - 1]) xp = xa.r[i];
+        }
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             float4 t = s_acc[0][c][lane];
             for (int ww = 1; ww < 32; ++ww) { float4 v = s_acc[ww][c][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
             if (cv[c]) {
                 size_t o = (size_t)a.oWV + (size_t)w * a.dq + (lane + 32 * c) * 4;
-                reg += word_store(a, o, ldg4(a.theta + o), t, (lane + 32 * c) * 4);
+                reg += word_store<PUSH>(a, xp, o, ldg4(a.theta + o), t, (lane + 32 * c) * 4);
             }
         }
         reg = warp_sum(reg);
@@ -1172,7 +1174,8 @@ __global__ void __launch_bounds__(1024) k_word_finish_hub(WordArgs a) {
 
 // one thread per (word pair, float4 chunk): words w and w + half, two independent record -> entity-row chains in flight
 // per thread (the kernel is a few waves of dependent DRAM round trips); hub words are finished by k_word_finish_hub
-__device__ __forceinline__ float word_one(const WordArgs& a, int w, int c, const int4& rec, const float4& th, size_t o) {
+template <bool PUSH>
+__device__ __forceinline__ float word_one(const WordArgs& a, const XPushRange& xp, int w, int c, const int4& rec, const float4& th, size_t o) {
     if (rec.w != 0) return 0.f;                                      // hub words are finished elsewhere
     float4 acc = zero4();
     if (rec.y - rec.x == 1) {                                        // the common case: exactly one entity
@@ -1182,22 +1185,25 @@ __device__ __forceinline__ float word_one(const WordArgs& a, int w, int c, const
     } else if (rec.y > rec.x) {
         acc = word_range<4>(a, rec.x, rec.y, c);
     }
-    return word_store(a, o, th, acc, c * 4);
+    return word_store<PUSH>(a, xp, o, th, acc, c * 4);
 }
-__global__ void __launch_bounds__(256, 4) k_word_pull(WordArgs a, int half) {
+template <bool PUSH>
+__global__ void __launch_bounds__(256, 5) k_word_pull(WordArgs a, XPushRange xp, int w0, int wn, int half, int block_off) {
+    // words [w0, w0 + wn): the whole block (single GPU) or one chunk of it (the exchange of a finished chunk overlaps the
+    // pull of the next, exchange.cu); block_off = this chunk's first regulariser-partial slot
     __shared__ double s_reg[8];
     const unsigned gid = flat_index();
-    const int w = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)w * a.fd.d);
+    const int wl = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)wl * a.fd.d);
     float reg = 0.f;
-    if (w < half) {
-        const int w2 = w + half;
-        const bool two = w2 < a.Nw;
+    if (wl < half) {
+        const int w = w0 + wl, w2 = w + half;
+        const bool two = wl + half < wn;
         const size_t o1 = (size_t)a.oWV + (size_t)w * a.dq + c * 4, o2 = (size_t)a.oWV + (size_t)(two ? w2 : w) * a.dq + c * 4;
         const int4 r1 = __ldg(a.w_rec + w);
         const int4 r2 = __ldg(a.w_rec + (two ? w2 : w));
         const float4 t1 = ldg4(a.theta + o1), t2 = ldg4(a.theta + o2);
-        reg = word_one(a, w, c, r1, t1, o1);
-        if (two) reg += word_one(a, w2, c, r2, t2, o2);
+        reg = word_one<PUSH>(a, xp, w, c, r1, t1, o1);
+        if (two) reg += word_one<PUSH>(a, xp, w2, c, r2, t2, o2);
     }
     reg = warp_sum(reg);
     if ((threadIdx.x & 31) == 0) s_reg[threadIdx.x >> 5] = (double)reg;
@@ -1205,7 +1211,7 @@ __global__ void __launch_bounds__(256, 4) k_word_pull(WordArgs a, int half) {
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int i = 0; i < 8; ++i) t += s_reg[i];
-        a.reg_part[blockIdx.x] = t;
+        a.reg_part[block_off + blockIdx.x] = t;
     }
 }
 
@@ -1542,41 +1548,96 @@ void ntn_launch_entity_pull(ntn_handle* h) {
     h->launches++;
 }
 
-static int word_pull_blocks(const NtnDims& dm) { return cdiv((int64_t)((dm.Nw + 1) / 2) * (dm.dq / 4), 256); }   // two words per thread
+// The word pull covers the Nw words in C chunks of whole words (C = 1 unless a gradient exchange is bound): chunk c is
+// words [w0, w0 + wn), one thread per (word pair, float4 chunk), and owns `blocks` regulariser-partial slots from block_off.
+// The last chunk is the smallest (its exchange is the part nothing overlaps).
+void ntn_word_chunk(const NtnDims& dm, int c, int C, int* w0, int* wn, int* block_off, int* blocks) {
+    const int cpr = dm.dq / 4;
+    int64_t bound[NTN_MAX_WORD_CHUNKS + 1];
+    // weights 2 : 2 : ... : 2 : 1 (the last chunk half as long)
+    const int64_t wsum = 2 * (int64_t)C - 1;
+    bound[0] = 0;
+    for (int i = 1; i <= C; ++i) bound[i] = (i == C) ? dm.Nw : std::min<int64_t>(dm.Nw, ((int64_t)dm.Nw * 2 * i + wsum - 1) / wsum);
+    int off = 0;
+    for (int i = 0; i < c; ++i) off += cdiv(((bound[i + 1] - bound[i] + 1) / 2) * cpr, 256);
+    *w0 = (int)bound[c]; *wn = (int)(bound[c + 1] - bound[c]);
+    *block_off = off; *blocks = cdiv(((int64_t)(*wn + 1) / 2) * cpr, 256);
+}
+int ntn_word_blocks_total(const NtnDims& dm, int C) {
+    int w0, wn, off, nb;
+    ntn_word_chunk(dm, C - 1, C, &w0, &wn, &off, &nb);
+    return off + nb;
+}
 
-void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad) {
+void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad, const ExchangeBinding* xb) {
     const NtnDims& dm = h->dm;
     const DeviceWords& w = h->w;
+    const int C = h->word_chunks;
     WordArgs a{h->gE, w.len_bwd /* reciprocals */, theta, grad, w.w_off, w.w_ent, w.w_rec, w.wh_first, w.wh_count, w.wh_begin, w.wh_end,
-               w.hub_words, w.wh_part, h->reg_part, dm.Nw, dm.d, dm.dq, w.n_hub_segs, w.n_hub_words, word_pull_blocks(dm),
+               w.hub_words, w.wh_part, h->reg_part, dm.Nw, dm.d, dm.dq, w.n_hub_segs, w.n_hub_words, ntn_word_blocks_total(dm, C),
                dm.oWVint, 1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale, make_fastdiv((unsigned)(dm.dq / 4))};
     const int cpr = dm.dq / 4;
     int ch = cdiv(cpr, 32);
+    // range ids of an evaluation (their scratch regions, exchange.cu): 0 = the W/V/b/U blocks, 1 + c = word chunk c,
+    // C + 1 = the {cost, n_active} tail
+    XPushAll xa{};
+    for (int c = 0; c < C; ++c) {
+        int w0, wn, off, nb;
+        ntn_word_chunk(dm, c, C, &w0, &wn, &off, &nb);
+        xa.r[c] = ntn_push_range(h, xb, dm.oWVint + (int64_t)w0 * dm.dq, (int64_t)wn * dm.dq, 1 + c);
+        xa.w_end[c] = w0 + wn;
+    }
+    xa.n = (xb && xa.r[0].world) ? C : 0;
+    const bool pushed = xa.n != 0;
     if (w.n_hub_segs) {
         // hub branch on the forked stream: it only needs gE and writes rows the main kernel skips
         cudaEventRecord(h->ev_fork, h->stream);
         cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
         k_word_pull_hub<<<cdiv((int64_t)w.n_hub_segs * cpr, 256), 256, 0, h->stream2>>>(a);
-        DISPATCH_CH(ch, { k_word_finish_hub<CH><<<w.n_hub_words, 1024, 0, h->stream2>>>(a); });
+        DISPATCH_CH(ch, {
+            if (pushed) k_word_finish_hub<CH, true><<<w.n_hub_words, 1024, 0, h->stream2>>>(a, xa);
+            else k_word_finish_hub<CH, false><<<w.n_hub_words, 1024, 0, h->stream2>>>(a, xa);
+        });
         cudaEventRecord(h->ev_join, h->stream2);
         h->launches += 2;
     }
-    k_word_pull<<<word_pull_blocks(dm), 256, 0, h->stream>>>(a, (dm.Nw + 1) / 2);
+    for (int c = 0; c < C; ++c) {
+        int w0, wn, off, nb;
+        ntn_word_chunk(dm, c, C, &w0, &wn, &off, &nb);
+        if (nb > 0) {
+            if (pushed) k_word_pull<true><<<nb, 256, 0, h->stream>>>(a, xa.r[c], w0, wn, (wn + 1) / 2, off);
+            else k_word_pull<false><<<nb, 256, 0, h->stream>>>(a, xa.r[c], w0, wn, (wn + 1) / 2, off);
+            h->launches++;
+        }
+        if (xb && c + 1 < C) {
+            // chunk c is final in this rank's buffer (once the hub rows and, for the first chunk, the small blocks
+            // have landed): exchange it on the side stream while the pull goes on with chunk c + 1
+            cudaEventRecord(h->ev_x[c], h->stream);
+            cudaStreamWaitEvent(h->stream4, h->ev_x[c], 0);
+            XRange r0{dm.oWVint + (int64_t)w0 * dm.dq, (int64_t)wn * dm.dq, 1 + c, pushed}, r1{0, 0, 0, false};
+            if (c == 0) {
+                if (w.n_hub_segs) cudaStreamWaitEvent(h->stream4, h->ev_join, 0);
+                cudaStreamWaitEvent(h->stream4, h->ev_j1, 0);              // W, V, b, U blocks (k_finalize_small / _u)
+                r1 = XRange{0, dm.oWVint, 0, false};
+            }
+            ntn_launch_exchange(h, xb, r0, r1, false, h->stream4);
+        }
+    }
+    if (xb && C > 1) cudaEventRecord(h->ev_xdone, h->stream4);
     if (w.n_hub_segs) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
-    h->launches++;
 }
 
 int ntn_small_blocks(const NtnDims& dm) {
     int64_t nsmall = (int64_t)dm.R * dm.Kp * dm.Np + (int64_t)dm.R * dm.k + 4;
     return cdiv(nsmall, 256);
 }
-int ntn_word_blocks(const NtnDims& dm) { return word_pull_blocks(dm); }
+int ntn_word_blocks(const NtnDims& dm) { return ntn_word_blocks_total(dm, 1) + NTN_MAX_WORD_CHUNKS; }   // capacity (any chunking)
 
 void ntn_launch_finalize_small(ntn_handle* h, const float* theta, float* grad, cudaStream_t st) {
     const NtnDims& dm = h->dm;
     const DeviceBatch& b = h->b;
     int nb = ntn_small_blocks(dm);
-    int wb = word_pull_blocks(dm) + h->w.n_hub_words;
+    int wb = ntn_word_blocks_total(dm, h->word_chunks) + h->w.n_hub_words;
     FinArgs a{theta, b.dWpart, b.tp_dU, grad, b.relch_off, b.rels_off, h->side, h->reg_part + wb, dm,
               1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale};
     k_finalize_small<<<nb, 256, 0, st>>>(a);
@@ -1588,7 +1649,7 @@ void ntn_launch_final_reduce(ntn_handle* h, float* tail) {
     const NtnDims& dm = h->dm;
     const DeviceBatch& b = h->b;
     int nb = ntn_small_blocks(dm);
-    int wb = word_pull_blocks(dm) + h->w.n_hub_words;
+    int wb = ntn_word_blocks_total(dm, h->word_chunks) + h->w.n_hub_words;
     double lam = (double)h->cfg.lambda * (double)h->cfg.reg_scale;
     k_final_reduce<<<1, 1024, 0, h->stream>>>(b.tp_cost, b.tp_nact, b.nstiles, h->reg_part, wb + nb + dm.R * dm.k,
                                              1.0 / (double)h->cfg.batch_divisor, 0.5 * lam, h->d_out, tail);

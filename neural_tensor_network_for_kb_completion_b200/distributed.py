@@ -162,14 +162,28 @@ class GradientExchange:
         if not hasattr(lib, "ntn_exchange_bind"):
             return False
         import torch.distributed._symmetric_memory as symm
+        torch = self.torch
         buffers = self.buffers if buffers is None else buffers
         ok = True
+        # push mode needs a second symmetric allocation per gradient buffer: every rank's scratch receives the other
+        # ranks' contributions to the slices it owns (stores only -- no peer loads on the data path)
+        want = handles[0].exchange_scratch_numel
+        if not hasattr(self, "scratch"):
+            self.scratch = {}
+        for t in buffers:
+            if t.data_ptr() not in self.scratch:
+                sc = symm.empty(want, dtype=torch.float32, device=t.device)
+                sc.zero_()
+                self.scratch[t.data_ptr()] = (sc, symm.rendezvous(sc, self.group_name))
+        torch.cuda.synchronize()
+        self.dist.barrier()
         for h in handles:
             for t in buffers:
                 hdl = symm.rendezvous(t, self.group_name)
+                sc, shdl = self.scratch[t.data_ptr()]
                 ok = ok and h.exchange_bind(hdl.rank, hdl.world_size, [int(p) for p in hdl.buffer_ptrs],
                                             [int(p) for p in hdl.signal_pad_ptrs], int(getattr(hdl, "multicast_ptr", 0) or 0),
-                                            t.numel())
+                                            t.numel(), [int(p) for p in shdl.buffer_ptrs], sc.numel())
         return ok
 
 

@@ -47,9 +47,15 @@ class LBFGSMinimizer:
         d_theta = cache[0]
         if cache[1] is None or cache[1] is not theta:
             h.upload_theta(np.asarray(theta, np.float64), d_theta.data_ptr())
-        r = h.lbfgs_minimize(d_theta.data_ptr(), fn.drawCorruptSides, opts.maxIters, opts.maxHistorySize, opts.tol,
-                             reduce=reduce)
+        # corrupt sides: the seeded Math.random() stream is advanced natively (no interpreter call per evaluation) when
+        # the function object offers its state; any other object is called back per evaluation
+        st = fn.nativeSidesState() if hasattr(fn, "nativeSidesState") else None
+        r = h.lbfgs_minimize(d_theta.data_ptr(), st if st is not None else fn.drawCorruptSides, opts.maxIters,
+                             opts.maxHistorySize, opts.tol, reduce=reduce)
+        if st is not None:
+            fn.adoptSidesState(st)
         fn.update += int(r.n_active_last)
         out = h.download_theta(d_theta.data_ptr())
+        out.setflags(write=False)          # identity-keyed reuse of the device copy: an in-place edit would go unnoticed
         cache[1] = out
         return Result(out, r.min_obj_val, bool(r.did_converge), r.iters, r.evals, r.first_cost)

@@ -102,6 +102,22 @@ class NTN:
             side[r] = 1 if self.side_rand.nextDouble() > 0.5 else 0
         return side
 
+    def nativeSidesState(self):
+        """State array for the library's native corrupt-side drawer (ntn_host_sides_draw): the same seeded stream as
+        drawCorruptSides, advanced in C while the device L-BFGS runs; ``adoptSidesState`` takes the stream back."""
+        rel = self.tbj.batchjob[1] if self.global_relations is None else self.global_relations
+        if self._present_for is not rel:
+            self._present = np.bincount(np.asarray(rel), minlength=self.numberOfRelations)[:self.numberOfRelations] > 0
+            self._present_for = rel
+        st = np.zeros(2 + self.numberOfRelations, np.uint64)
+        st[0] = self.side_rand.s
+        st[1] = self.numberOfRelations
+        st[2:] = self._present.astype(np.uint64)
+        return st
+
+    def adoptSidesState(self, st):
+        self.side_rand.s = int(st[0])
+
     # ---- IDifferentiableFn (NTN.java:92-448) ----------------------------------------------------
     def computeAt(self, _theta, corrupt_side=None):
         """IPair<Double,double[]> computeAt(double[] theta) -> (cost, grad)."""

@@ -164,3 +164,25 @@ def test_theta_checkpoints_round_trip_bit_exact(tmp_path):
     for path in (ptxt, pbin):
         assert np.array_equal(run_ntn.read_theta(path).astype(np.float32).view(np.uint32), bits)
     assert open(ptxt).read().count(",") == th.size - 1 and "\n" not in open(ptxt).read()      # one comma-separated line
+
+
+def test_native_corrupt_side_drawer_continues_the_seeded_stream(lib):
+    """ntn_host_sides_draw (the ntn_sides_fn a non-compiled host hands to ntn_lbfgs_minimize) against the oracle's
+    java.util.Random: one nextDouble() > 0.5 per PRESENT relation in increasing r (NTN.java:120,146), state carried."""
+    from oracle.java_random import JavaRandom as RefRandom
+    R = 13
+    present = np.array([1, 1, 0, 1, 1, 1, 0, 0, 1, 1, 1, 0, 1], np.uint8)
+    ref = RefRandom(7)
+    from neural_tensor_network_for_kb_completion_b200.data_factory import JavaRandom as PyRandom
+    pr = PyRandom(7)
+    st = np.zeros(2 + R, np.uint64)
+    st[0], st[1] = pr.s, R
+    st[2:] = present
+    out = np.zeros(R, np.uint8)
+    for _ in range(50):
+        lib.ntn_host_sides_draw(st.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        want = np.array([(1 if ref.next_double() > 0.5 else 0) if present[r] else 0 for r in range(R)], np.uint8)
+        assert np.array_equal(out, want)
+    # the Python mirror adopts the advanced state and stays on the same stream
+    pr.s = int(st[0])
+    assert pr.nextDouble() == ref.next_double()
