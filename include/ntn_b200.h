@@ -170,6 +170,8 @@ int ntn_exchange_bind(ntn_handle* h, int32_t rank, int32_t world, const uint64_t
 int64_t ntn_exchange_scratch_numel(const ntn_handle* h);
 int ntn_exchange_unbind(ntn_handle* h);
 int ntn_exchange_check(ntn_handle* h);
+/* measurement hook: iters back-to-back all-reduce kernels over floats [off, off+n) of a bound buffer (same call on every rank) */
+int ntn_exchange_probe(ntn_handle* h, float* d_grad, int64_t off, int64_t n, int32_t last, int32_t iters);
 const char* ntn_exchange_mode(const ntn_handle* h);   /* "none", "push", "p2p" (peer loads/stores) or "multimem" (NVLS) */
 
 int64_t ntn_internal_dimension(const ntn_handle* h);

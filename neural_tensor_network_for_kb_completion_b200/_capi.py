@@ -75,6 +75,7 @@ SYMBOLS = {
     "ntn_exchange_scratch_numel": (C.c_int64, [_P]),
     "ntn_exchange_unbind": (C.c_int, [_P]),
     "ntn_exchange_check": (C.c_int, [_P]),
+    "ntn_exchange_probe": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "ntn_exchange_mode": (C.c_char_p, [_P]),
     "ntn_internal_dimension": (C.c_int64, [_P]),
     "ntn_to_internal_dev": (C.c_int, [_P, _P, _P]),
@@ -260,6 +261,9 @@ class Handle:
 
     def exchange_unbind(self):
         self._ck(self.lib.ntn_exchange_unbind(self.h))
+
+    def exchange_probe(self, d_grad, off, n, last, iters):
+        self._ck(self.lib.ntn_exchange_probe(self.h, d_grad, int(off), int(n), int(last), int(iters)))
 
     def exchange_check(self):
         return bool(self.lib.ntn_exchange_check(self.h))

@@ -41,9 +41,11 @@ struct XArgs {
     float* mc;
     uint32_t* sig[NTN_MAX_PEERS];
     float* scratch[NTN_MAX_PEERS];
-    int rank, world, mode, last;
-    XRange rg[2];
+    int rank, world, mode, last, mcst;
+    XRange rg[3];
     unsigned* err;
+    unsigned long long timeout_ns;
+    uint32_t* epoch;                     // {barriers completed by this binding / 1, blocks that have left the running kernel}
 };
 
 __device__ __forceinline__ unsigned long long x_now() {
@@ -51,40 +53,58 @@ __device__ __forceinline__ unsigned long long x_now() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define X_TIMEOUT_NS 2000000000ull            // 2 s: far beyond any skew between the ranks of one box
 
-// put: wait until the peer has consumed the previous signal (flag == 0), then raise it; release: this thread's (and,
-// through the preceding __syncthreads + fence, the block's) earlier writes are visible to whoever acquires the flag
-__device__ __forceinline__ bool x_put(uint32_t* flag) {
-    const unsigned long long t0 = x_now();
-    for (;;) {
-        uint32_t old;
-        asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(flag) : "memory");
-        if (old == 0) return true;
-        if (x_now() - t0 > X_TIMEOUT_NS) return false;
+// Flag barrier between block b of this kernel and block b of the same kernel on every peer.  Every barrier of a
+// binding's life has a number (its epoch: the ranks launch the same sequence of exchange kernels, so they count alike);
+// a rank SIGNALS by storing the epoch into its slot of every peer's signal pad -- a posted store with release semantics
+// at system scope, nothing comes back over NVLink -- and WAITS until every peer's slot in its own pad has reached the
+// epoch (acquire loads of local memory).  Slots only grow, so a peer that is already one barrier ahead still satisfies
+// the wait.  (A compare-and-swap handshake, which needs no counter, measured 9-10 us per barrier on 2 GPUs: every put
+// waits for its atomic's round trip; the store-based one costs one one-way trip.)  The epoch counter is device memory of
+// this rank: read by every block when the kernel starts, advanced by the last block to leave.
+__device__ __forceinline__ void x_signal(uint32_t* flag, uint32_t epoch) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ bool x_wait(const uint32_t* flag, uint32_t epoch, unsigned long long timeout_ns) {
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - epoch) >= 0) return true;
+        if ((spins & 255u) == 255u) {                          // the clock is only consulted now and then
+            const unsigned long long t = x_now();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > timeout_ns) return false;
+        }
     }
 }
-__device__ __forceinline__ bool x_wait(uint32_t* flag) {
-    const unsigned long long t0 = x_now();
-    for (;;) {
-        uint32_t old;
-        asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(flag) : "memory");
-        if (old == 1) return true;
-        if (x_now() - t0 > X_TIMEOUT_NS) return false;
-    }
-}
 
-// block b of this rank <-> block b of every peer
-__device__ __forceinline__ void x_barrier(const XArgs& a) {
+// block b of this rank <-> block b of every peer.  The block's earlier stores are ordered before the signal by the
+// __syncthreads (every thread's stores happen before the signalling thread goes on) and the release at system scope of
+// the signalling store (cumulative) -- no fence per thread (32 k of them measured ~5 us per barrier).
+__device__ __forceinline__ void x_barrier(const XArgs& a, uint32_t epoch) {
     __syncthreads();
     const int t = threadIdx.x;
     if (t < a.world && t != a.rank) {
         const size_t slot = NTN_XCHG_SIG_WORD0 + (size_t)blockIdx.x * a.world;
-        bool ok = x_put(a.sig[t] + slot + a.rank);
-        ok = ok && x_wait(a.sig[a.rank] + slot + t);
-        if (!ok) atomicExch(a.err, 1u);
+        x_signal(a.sig[t] + slot + a.rank, epoch);
+        if (!x_wait(a.sig[a.rank] + slot + t, epoch, a.timeout_ns)) atomicExch(a.err, 1u);
     }
     __syncthreads();
+}
+// epochs of this launch: base + 1 (start barrier), base + 2 (end barrier); the last block to leave advances the counter
+__device__ __forceinline__ uint32_t x_epoch_begin(const XArgs& a) {
+    __shared__ uint32_t s_base;
+    if (threadIdx.x == 0) s_base = *reinterpret_cast<volatile uint32_t*>(a.epoch);
+    __syncthreads();
+    return s_base;
+}
+__device__ __forceinline__ void x_epoch_end(const XArgs& a, uint32_t base) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.epoch + 1, 1u) == gridDim.x - 1) { a.epoch[1] = 0u; __threadfence(); a.epoch[0] = base + 2u; }
+    }
 }
 
 __device__ __forceinline__ float4 x_ld(const float* p) {      // peer data written by another GPU's earlier kernel: not through
@@ -112,9 +132,10 @@ template <int MODE, int G>                      // G = world size (compile time:
 __global__ void __launch_bounds__(X_THREADS) k_exchange(XArgs a) {
     constexpr int X_UNROLL = (MODE == 0 && G == 8) ? 2 : X_UNROLL_MAX;   // 8 peers x 4 float4 would not fit the registers
     const int world = G ? G : a.world;
-    x_barrier(a);                               // every rank has finished producing the ranges
+    const uint32_t ep = x_epoch_begin(a);
+    x_barrier(a, ep + 1);                       // every rank has finished producing the ranges
 #pragma unroll 1
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 3; ++q) {
         const int64_t n4 = a.rg[q].n >> 2;
         if (n4 == 0) continue;
         const int64_t per = (n4 + world - 1) / world;
@@ -172,8 +193,8 @@ __global__ void __launch_bounds__(X_THREADS) k_exchange(XArgs a) {
             }
         }
     }
-    __threadfence_system();                     // this thread's stores are performed at system scope before the block signals
-    x_barrier(a);                               // every rank's stores have landed
+    if (a.last) x_barrier(a, ep + 2);           // end of the evaluation: every rank's stores have landed everywhere
+    x_epoch_end(a, ep);
 }
 
 
@@ -186,10 +207,11 @@ __global__ void __launch_bounds__(X_THREADS) k_exchange_push(XArgs a) {
     const int world = G ? G : a.world;
     const int64_t stride = (int64_t)gridDim.x * X_THREADS;
     const int64_t tid = (int64_t)blockIdx.x * X_THREADS + threadIdx.x;
+    const uint32_t ep = x_epoch_begin(a);
     // phase 0: ranges whose producer did not push (the W/V/b/U blocks, the {cost, n_active} tail): store this rank's
     // groups of every other rank's slice into the owner's scratch
 #pragma unroll 1
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 3; ++q) {
         const int64_t n4 = a.rg[q].n >> 2;
         if (n4 == 0 || a.rg[q].pushed) continue;
         const int64_t per = (n4 + world - 1) / world;
@@ -201,45 +223,54 @@ __global__ void __launch_bounds__(X_THREADS) k_exchange_push(XArgs a) {
             for (int64_t i = lo + tid; i < hi; i += stride) dst[i - lo] = src[i];
         }
     }
-    __threadfence_system();
-    x_barrier(a);                               // every rank's contributions to my slices have landed in my scratch
+    x_barrier(a, ep + 1);                       // every rank's contributions to my slices have landed in my scratch
 #pragma unroll 1
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 3; ++q) {
         const int64_t n4 = a.rg[q].n >> 2;
         if (n4 == 0) continue;
         const int64_t per = (n4 + world - 1) / world;
         const int64_t lo = min(n4, (int64_t)a.rank * per), hi = min(n4, lo + per);
         const float* mine = a.peer[a.rank] + a.rg[q].off;
         const float* scr = a.scratch[a.rank] + x_scr_off(a.rg[q]);
-        for (int64_t i0 = lo + tid; i0 < hi; i0 += stride * 2) {
-            float4 acc[2];
+        constexpr int U = (G == 0 || G == 8) ? 2 : 4;                // 16-byte groups in flight per thread and source
+        for (int64_t i0 = lo + tid; i0 < hi; i0 += stride * U) {
+            float4 acc[U];
+            float4 v[U][G ? G : NTN_MAX_PEERS];
+            // (plain L2-cached loads: everything read here is local memory, complete since the barrier above; L1 holds
+            //  none of it -- the kernel has not touched these lines before)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < U; ++j) {
                 const int64_t i = i0 + j * stride;
-                if (i >= hi) continue;
-                float4 v[G ? G : NTN_MAX_PEERS];
 #pragma unroll
                 for (int s = 0; s < (G ? G : NTN_MAX_PEERS); ++s)
-                    if (s < world) v[s] = (s == a.rank) ? x_ld(mine + 4 * i) : x_ld(scr + 4 * ((int64_t)s * per + (i - lo)));
-                acc[j] = v[0];                                      // rank order: a fixed summation order
-#pragma unroll
-                for (int s = 1; s < (G ? G : NTN_MAX_PEERS); ++s)
-                    if (s < world) { acc[j].x += v[s].x; acc[j].y += v[s].y; acc[j].z += v[s].z; acc[j].w += v[s].w; }
+                    if (s < world && i < hi)
+                        v[j][s] = __ldcg(reinterpret_cast<const float4*>((s == a.rank) ? mine + 4 * i : scr + 4 * ((int64_t)s * per + (i - lo))));
             }
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < U; ++j) {
+                acc[j] = v[j][0];                                   // rank order: a fixed summation order
+#pragma unroll
+                for (int s = 1; s < (G ? G : NTN_MAX_PEERS); ++s)
+                    if (s < world) { acc[j].x += v[j][s].x; acc[j].y += v[j][s].y; acc[j].z += v[j][s].z; acc[j].w += v[j][s].w; }
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
                 const int64_t i = i0 + j * stride;
                 if (i >= hi) continue;
+                if (a.mcst) {
+                    // one store to the multicast alias: the NVSwitch replicates it into every rank's buffer, so the
+                    // all-gather half costs this rank one slice of NVLink bandwidth instead of G - 1
+                    x_mc_st(a.mc + a.rg[q].off + 4 * i, acc[j]);
+                } else {
 #pragma unroll
-                for (int s = 0; s < (G ? G : NTN_MAX_PEERS); ++s)
-                    if (s < world) x_st(a.peer[s] + a.rg[q].off + 4 * i, acc[j]);
+                    for (int s = 0; s < (G ? G : NTN_MAX_PEERS); ++s)
+                        if (s < world) *reinterpret_cast<float4*>(a.peer[s] + a.rg[q].off + 4 * i) = acc[j];
+                }
             }
         }
     }
-    if (a.last) {                               // end of the evaluation: every rank's sums have landed everywhere
-        __threadfence_system();
-        x_barrier(a);
-    }
+    if (a.last) x_barrier(a, ep + 2);           // end of the evaluation: every rank's sums have landed everywhere
+    x_epoch_end(a, ep);
 }
 
 // the push descriptor of a range for its producer kernel (ntn_kernels.cu)
@@ -259,22 +290,28 @@ const ExchangeBinding* ntn_find_binding(const ntn_handle* h, const float* d_grad
     return nullptr;
 }
 
-void ntn_launch_exchange(ntn_handle* h, const ExchangeBinding* xb, XRange r0, XRange r1, bool last, cudaStream_t st) {
+void ntn_launch_exchange(ntn_handle* h, const ExchangeBinding* xb, XRange r0, XRange r1, XRange r2, bool last, cudaStream_t st) {
     XArgs a{};
     for (int r = 0; r < h->x_world; ++r) { a.peer[r] = xb->peer[r]; a.sig[r] = xb->sig[r]; a.scratch[r] = xb->scratch[r]; }
     a.mc = xb->mc;
     a.rank = h->x_rank; a.world = h->x_world;
     a.mode = h->x_mode;
     a.last = last ? 1 : 0;
-    a.rg[0] = r0; a.rg[1] = r1;
+    a.mcst = (h->x_mcst && xb->mc) ? 1 : 0;
+    a.rg[0] = r0; a.rg[1] = r1; a.rg[2] = r2;
     a.err = h->d_xerr;
+    a.epoch = xb->epoch;
+    a.timeout_ns = h->x_timeout_ns;
     const int nb = h->x_blocks;
     h->launches++;
+    const int sslot = 2 * (NTN_NUM_PHASES + std::min(h->x_stamp++, NTN_MAX_WORD_CHUNKS));
+    ntn_stamp(h, sslot, st);
     if (a.mode == 2) {
         if (a.world == 2) k_exchange_push<2><<<nb, X_THREADS, 0, st>>>(a);
         else if (a.world == 4) k_exchange_push<4><<<nb, X_THREADS, 0, st>>>(a);
         else if (a.world == 8) k_exchange_push<8><<<nb, X_THREADS, 0, st>>>(a);
         else k_exchange_push<0><<<nb, X_THREADS, 0, st>>>(a);
+        ntn_stamp(h, sslot + 1, st);
         return;
     }
     if (a.mode == 1) k_exchange<1, 0><<<nb, X_THREADS, 0, st>>>(a);
@@ -282,6 +319,7 @@ void ntn_launch_exchange(ntn_handle* h, const ExchangeBinding* xb, XRange r0, XR
     else if (a.world == 4) k_exchange<0, 4><<<nb, X_THREADS, 0, st>>>(a);
     else if (a.world == 8) k_exchange<0, 8><<<nb, X_THREADS, 0, st>>>(a);
     else k_exchange<0, 0><<<nb, X_THREADS, 0, st>>>(a);
+    ntn_stamp(h, sslot + 1, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -318,6 +356,10 @@ extern "C" int ntn_exchange_bind(ntn_handle* h, int32_t rank, int32_t world, con
     }
     if (scratch_ptrs && !have_scratch) { h->err = "exchange: scratch too short (ntn_exchange_scratch_numel), null or misaligned"; return NTN_EINVAL; }
     b.scratch_numel = have_scratch ? scratch_numel : 0;
+    // barrier counter of this buffer: two words of this rank's own signal pad just below the flag slots (no peer writes
+    // there), so that every handle bound to the buffer counts on.  The pads must be zero when the first handle binds (a
+    // fresh symmetric allocation is) and every rank binds before any evaluates (the caller's barrier).
+    b.epoch = b.sig[rank] + NTN_XCHG_SIG_WORD0 - 2;
     if (!h->stream4) {
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -330,7 +372,8 @@ extern "C" int ntn_exchange_bind(ntn_handle* h, int32_t rank, int32_t world, con
     }
     h->x_rank = rank; h->x_world = world;
     // NTN_EXCHANGE=push|p2p|multimem, NTN_EXCHANGE_CHUNKS, NTN_EXCHANGE_BLOCKS override the defaults
-    // defaults: push when a scratch allocation is bound; otherwise NVLS on a large box, peer loads on a small one
+    // defaults: push when a scratch allocation is bound (its broadcast half through the multicast alias on a large box);
+    // otherwise NVLS loads on a large box, peer loads on a small one
     h->x_mode = have_scratch ? 2 : ((multicast_ptr && world >= 4) ? 1 : 0);
     if (const char* e = getenv("NTN_EXCHANGE")) {
         if (!strcmp(e, "p2p") || !strcmp(e, "pull")) h->x_mode = 0;
@@ -338,6 +381,10 @@ extern "C" int ntn_exchange_bind(ntn_handle* h, int32_t rank, int32_t world, con
         else if (!strcmp(e, "push") && have_scratch) h->x_mode = 2;
     }
     for (const auto& o : h->xb) if ((o.scratch_numel != 0) != have_scratch && h->x_mode == 2) { h->err = "exchange: all bound buffers need a scratch in push mode"; return NTN_EINVAL; }
+    for (const auto& o : h->xb) if (!o.mc && h->x_mode == 1) { h->err = "exchange: all bound buffers need a multicast alias in multimem mode"; return NTN_EINVAL; }
+    h->x_mcst = world >= 4 ? 1 : 0;          // push mode: broadcast the sums through the multicast alias (when there is one)
+    if (const char* e = getenv("NTN_EXCHANGE_MCST")) h->x_mcst = atoi(e) != 0;
+    if (const char* e = getenv("NTN_EXCHANGE_TIMEOUT_MS")) h->x_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
     if (const char* e = getenv("NTN_EXCHANGE_CHUNKS")) h->x_chunks = std::max(1, std::min(NTN_MAX_WORD_CHUNKS, atoi(e)));
     if (const char* e = getenv("NTN_EXCHANGE_BLOCKS")) h->x_blocks = std::max(1, std::min(NTN_XCHG_MAX_BLOCKS, atoi(e)));
     for (auto& o : h->xb) if (o.local == b.local) { o = b; ntn_drop_graphs(h); return NTN_OK; }
@@ -363,6 +410,19 @@ extern "C" int ntn_exchange_check(ntn_handle* h) {
     cudaStreamSynchronize(h->stream);
     if (v) cudaMemsetAsync(h->d_xerr, 0, sizeof(unsigned), h->stream);
     return v ? 1 : 0;
+}
+
+// Measurement hook: `iters` back-to-back exchange kernels over floats [off, off + n) of a bound buffer (not pushed by a
+// producer: the kernel's own phase 0 stores the other ranks' slices), each ending with the end barrier when last != 0.
+// Every rank must make the same call.  The buffer's content is summed over the ranks `iters` times.
+extern "C" int ntn_exchange_probe(ntn_handle* h, float* d_grad, int64_t off, int64_t n, int32_t last, int32_t iters) {
+    if (!h) return NTN_EINVAL;
+    const ExchangeBinding* xb = ntn_find_binding(h, d_grad);
+    if (!xb || (off & 3) || (n & 3) || off < 0 || off + n > xb->numel) { h->err = "exchange probe: unbound buffer or bad range"; return NTN_EINVAL; }
+    cudaSetDevice(h->device);
+    for (int i = 0; i < iters; ++i)
+        ntn_launch_exchange(h, xb, XRange{off, n, 0, false}, XRange{0, 0, 0, false}, XRange{0, 0, 0, false}, last != 0, h->stream);
+    return cudaGetLastError() == cudaSuccess ? NTN_OK : NTN_ECUDA;
 }
 
 extern "C" const char* ntn_exchange_mode(const ntn_handle* h) {

@@ -118,8 +118,8 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
     h->device = cfg->device;
     h->use_graph = getenv("NTN_NO_GRAPH") == nullptr;
     if (getenv("NTN_GRAPH_TIMELINE")) {
-        if (cudaMalloc((void**)&h->d_stamps, 2 * NTN_NUM_PHASES * sizeof(unsigned long long)) != cudaSuccess) h->d_stamps = nullptr;
-        else cudaMemset(h->d_stamps, 0, 2 * NTN_NUM_PHASES * sizeof(unsigned long long));
+        if (cudaMalloc((void**)&h->d_stamps, 2 * NTN_STAMP_SLOTS * sizeof(unsigned long long)) != cudaSuccess) h->d_stamps = nullptr;
+        else cudaMemset(h->d_stamps, 0, 2 * NTN_STAMP_SLOTS * sizeof(unsigned long long));
     }
     auto bail = [&](int rc) { g_create_err = h->err; ntn_destroy(h); return rc; };
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(NTN_ECUDA); } } while (0)
@@ -171,7 +171,7 @@ static void free_batch(DeviceBatch& b) {
     dev_free(b.t_rel); dev_free(b.t_u0); dev_free(b.t_n); dev_free(b.ch_rel); dev_free(b.ch_u0); dev_free(b.ch_n);
     dev_free(b.relch_off); dev_free(b.reltile_off); dev_free(b.inc_off); dev_free(b.inc);
     dev_free(b.eh_ent); dev_free(b.eh_begin); dev_free(b.eh_end); dev_free(b.eh_first); dev_free(b.eh_count);
-    dev_free(b.T); dev_free(b.M); dev_free(b.GA); dev_free(b.GV); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.crec); dev_free(b.ent_order); dev_free(b.dWpart);
+    dev_free(b.T); dev_free(b.M); dev_free(b.GA); dev_free(b.GV); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.crec); dev_free(b.ent_order); dev_free(b.pull_rng); dev_free(b.dWpart);
     dev_free(b.tp_cost); dev_free(b.tp_nact); dev_free(b.tp_dU); dev_free(b.eh_part);
     b = DeviceBatch();
 }
@@ -397,9 +397,27 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
         }
         if (const char* e = getenv("NTN_SCORE_ROWS")) score_rows = std::max(1, atoi(e));
     }
+    // Contraction tile height (rows of unique triples, <= 128 = the UMMA M).  The persistent tcgen05 grid deals
+    // (tile x N-chunk) items round-robin to one CTA per SM, so a kernel lasts ceil(items / SMs) item times: 163 tiles of
+    // 128 rows on 148 SMs are TWO rounds for the entity-gradient contraction (the second 10 % full) and three for the
+    // forward one (two N-chunks).  A lower tile (the MMA still runs M = 128; the gather, the epilogue and the stores
+    // scale with the valid rows) that fills the last round wins at the reference's batch size; long grids keep 128.
+    // Cost model: rounds x (rows + a fixed per-item cost worth ~24 rows), summed over the two kernels.
+    int tile_rows = NTN_TILE_ROWS;
+    {
+        const int ny_fwd = (dm.Np + 159) / 160, ny_ge = (dm.Kp + 159) / 160;     // N-chunks of <= 160 accumulator columns
+        auto tiles_at = [&](int rows) { int64_t t = 0; for (int r = 0; r < dm.R; ++r) t += (rel_count[r] + rows - 1) / rows; return t; };
+        double best = 1e300;
+        for (int rows = NTN_TILE_ROWS; rows >= 32; rows -= 8) {
+            const int64_t t = tiles_at(rows);
+            const double cost = (double)((t * ny_fwd + h->sm_count - 1) / h->sm_count + (t * ny_ge + h->sm_count - 1) / h->sm_count) * (rows + 24);
+            if (cost < best - 1e-9) { best = cost; tile_rows = rows; }
+        }
+        if (const char* e = getenv("NTN_TILE_ROWS")) tile_rows = std::max(8, std::min(NTN_TILE_ROWS, atoi(e) / 8 * 8));
+    }
     for (int r = 0; r < dm.R; ++r) {
-        for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += NTN_TILE_ROWS) {
-            t_rel.push_back(r); t_u0.push_back(u0); t_n.push_back(std::min(NTN_TILE_ROWS, rel_off[r + 1] - u0));
+        for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += tile_rows) {
+            t_rel.push_back(r); t_u0.push_back(u0); t_n.push_back(std::min(tile_rows, rel_off[r + 1] - u0));
         }
         for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += chunk_rows) {
             ch_rel.push_back(r); ch_u0.push_back(u0); ch_n.push_back(std::min(chunk_rows, rel_off[r + 1] - u0));
@@ -428,8 +446,10 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
         (rc = dev_alloc(h, &b.dWpart, (size_t)b.nchunks * dm.Kp * dm.Np)) ||
         (rc = dev_alloc(h, &b.tp_cost, (size_t)b.nstiles)) || (rc = dev_alloc(h, &b.tp_nact, (size_t)b.nstiles)) ||
         (rc = dev_alloc(h, &b.tp_dU, (size_t)b.nstiles * dm.k)) ||
-        (rc = dev_alloc(h, &b.eh_part, (size_t)b.n_ent_hub_segs * dm.dq)))
+        (rc = dev_alloc(h, &b.eh_part, (size_t)b.n_ent_hub_segs * dm.dq)) ||
+        (rc = dev_alloc(h, &b.pull_rng, (size_t)ntn_pull_ranges(h))))
         return rc;
+    ntn_launch_pull_ranges(h);
     b.ccoef = b.acoef + (use_gv ? (size_t)Nu * dm.k : 0);
     b.RS = (int)round_up(dm.k + 1, 4);
     CK(cudaStreamSynchronize(h->stream));            // the small tables above come from host vectors that die here
@@ -639,6 +659,10 @@ __global__ void k_stamp(unsigned long long* dst) {
     *dst = t;
 }
 
+void ntn_stamp(ntn_handle* h, int slot, cudaStream_t st) {
+    if (h->d_stamps && slot >= 0 && slot < 2 * NTN_STAMP_SLOTS) k_stamp<<<1, 1, 0, st>>>(h->d_stamps + slot);
+}
+
 static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_grad, const float* wvt, bool prof, int slot) {
     auto begin = [&](int p, cudaStream_t st) {
         if (prof) cudaEventRecord(h->ev[slot][p][0], st);
@@ -656,6 +680,8 @@ static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_gr
     // all-reduce over the ranks runs inside the evaluation, chunk by chunk beside the word pull (exchange.cu)
     const ExchangeBinding* xb = h->grad_tail ? ntn_find_binding(h, d_grad) : nullptr;
     h->word_chunks = xb ? h->x_chunks : 1;
+    h->x_stamp = 0;
+    if (h->d_stamps) cudaMemsetAsync(h->d_stamps, 0, 2 * NTN_STAMP_SLOTS * sizeof(unsigned long long), h->stream);
     // ---- fork: weight preparation runs beside the entity build
     CK(cudaEventRecord(h->ev_f0, s0));
     CK(cudaStreamWaitEvent(s1, h->ev_f0, 0));
@@ -692,15 +718,11 @@ static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_gr
         const NtnDims& dm = h->dm;
         int w0, wn, off, nb;
         ntn_word_chunk(dm, h->word_chunks - 1, h->word_chunks, &w0, &wn, &off, &nb);
-        // (one chunk: the word block went out under range id 1 with the pull's pushes; the small blocks ride with the tail)
         const bool pushed = h->x_mode == 2;
-        XRange r0{dm.oWVint + (int64_t)w0 * dm.dq, (int64_t)wn * dm.dq, h->word_chunks, pushed}, r1{dm.Pint, 4, h->word_chunks + 1, false};
-        if (h->word_chunks == 1) {
-            ntn_launch_exchange(h, xb, XRange{0, dm.oWVint, 0, false}, XRange{0, 0, 0, false}, false, s0);
-        } else {
-            CK(cudaStreamWaitEvent(s0, h->ev_xdone, 0));
-        }
-        ntn_launch_exchange(h, xb, r0, r1, true, s0);
+        XRange r0{dm.oWVint + (int64_t)w0 * dm.dq, (int64_t)wn * dm.dq, h->word_chunks, pushed};
+        XRange r1{0, dm.oWVint, 0, false}, r2{dm.Pint, 4, h->word_chunks + 1, false};
+        if (h->word_chunks > 1) CK(cudaStreamWaitEvent(s0, h->ev_xdone, 0));
+        ntn_launch_exchange(h, xb, r0, r1, r2, true, s0);
     }
     CK(cudaMemcpyAsync(h->h_out, h->d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, s0));
     return NTN_OK;
@@ -1005,9 +1027,9 @@ extern "C" int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, 
     else if (s == "graph_timeline") {
         // begin/end of every kernel group of the LAST evaluation, microseconds relative to the earliest stamp
         if (!h->d_stamps) return 0;
-        const int m = 2 * NTN_NUM_PHASES;
+        const int m = 2 * NTN_STAMP_SLOTS;
         if (out && cap >= m) {
-            unsigned long long t[2 * NTN_NUM_PHASES], t0 = ~0ull;
+            unsigned long long t[2 * NTN_STAMP_SLOTS], t0 = ~0ull;
             cudaMemcpy(t, h->d_stamps, sizeof(t), cudaMemcpyDeviceToHost);
             for (int i = 0; i < m; ++i) if (t[i] && t[i] < t0) t0 = t[i];
             for (int i = 0; i < m; ++i) out[i] = t[i] ? (float)((double)(t[i] - t0) * 1e-3) : -1.f;

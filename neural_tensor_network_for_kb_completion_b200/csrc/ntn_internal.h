@@ -61,6 +61,7 @@ struct NtnDims {
 #define NTN_RING        8        // in-flight evaluations the host may enqueue without synchronising
 #define NTN_MAX_PEERS   8        // GPUs of one box (gradient exchange over peer memory, exchange.cu)
 #define NTN_MAX_WORD_CHUNKS 8    // the word pull is cut into chunks so that the exchange of chunk c overlaps the pull of c+1
+#define NTN_STAMP_SLOTS (NTN_NUM_PHASES + NTN_MAX_WORD_CHUNKS + 1)   // timeline stamp pairs: kernel groups, then exchange kernels
 #define NTN_XCHG_MAX_BLOCKS 64   // blocks of one exchange kernel (each pairs with the same block index on every peer)
 #define NTN_XCHG_SIG_WORD0 1024  // first 32-bit word of the signal pad used by the exchange kernels (torch's own
                                  // symmetric-memory kernels use the words below)
@@ -96,6 +97,7 @@ struct DeviceBatch {
     float *GV = nullptr;         // (Nu + N) x dq   per-incident contribution rows (non-anchor roles), written by k_score
     float *crec = nullptr;       // (Nu + N) x RS packed coefficient records (k_score2 -> k_entity_pull2), RS = ceil4(k + 1)
     int RS = 4;
+    int4 *pull_rng = nullptr;    // entity ranges of the warp-per-range entity pull: {first entity, end entity, first incident, end incident}
     int *ent_order = nullptr;    // Ne: entities in descending order of their incident count (stable): the pull's visiting order
     float *acoef = nullptr;      // (Nu + N) x k : a_{u,s} rows, then c_{col,s} rows (one allocation; GV variant)
     float *ccoef = nullptr;      // = acoef + Nu*k
@@ -131,6 +133,7 @@ struct ExchangeBinding {
     float* scratch[NTN_MAX_PEERS] = {};  // second symmetric allocation (push mode): rank r's copy receives the other ranks'
     int64_t numel = 0;                   // contributions to the slices r owns
     int64_t scratch_numel = 0;
+    uint32_t* epoch = nullptr;           // two words of this rank's signal pad: {barrier epochs completed, blocks that have left the running kernel}
 };
 
 // Push mode: where the producer of a gradient range (the word pull) also stores the 16-byte groups that another rank
@@ -184,7 +187,8 @@ struct ntn_handle {
     bool ev_pending[NTN_RING] = {};
     double phase_acc[NTN_NUM_PHASES] = {};
     int phase_n = 0;
-    unsigned long long *d_stamps = nullptr;   // NTN_GRAPH_TIMELINE: %globaltimer at begin/end of every kernel group
+    unsigned long long *d_stamps = nullptr;   // NTN_GRAPH_TIMELINE: %globaltimer at begin/end of every kernel group, then of
+                                              // every exchange kernel (NTN_STAMP_SLOTS pairs in all)
     void *tc = nullptr;           // tcgen05 path state (gemm_tcgen05.cu)
     void *bi_ws = nullptr;        // batch-index workspace (batch_index.cu), grow-only
     size_t bi_ws_bytes = 0;
@@ -206,7 +210,10 @@ struct ntn_handle {
     bool grad_tail = false;       // the caller's gradient buffer has 4 extra floats for {cost, n_active}
     // in-evaluation gradient exchange over peer memory (exchange.cu)
     int x_rank = 0, x_world = 1;
-    int x_chunks = 4, x_blocks = 32, x_mode = 0;   // word-pull chunks, blocks per exchange kernel, 0: peer loads/stores, 1: multimem, 2: push
+    unsigned long long x_timeout_ns = 2000000000ull;   // bound of every flag wait (NTN_EXCHANGE_TIMEOUT_MS)
+    int x_mcst = 0;                               // push mode: broadcast through the multicast alias
+    int x_stamp = 0;                              // exchange kernels launched in the evaluation being enqueued (timeline slots)
+    int x_chunks = 2, x_blocks = 64, x_mode = 0;   // word-pull chunks, blocks per exchange kernel, 0: peer loads/stores, 1: multimem, 2: push
     std::vector<ExchangeBinding> xb;
     cudaStream_t stream4 = nullptr;               // exchange of the finished chunks, beside the word pull (highest priority)
     cudaEvent_t ev_x[NTN_MAX_WORD_CHUNKS] = {}, ev_xdone = nullptr;
@@ -221,7 +228,7 @@ int ntn_word_blocks_total(const NtnDims& dm, int C);
 struct XRange { int64_t off, n; int id; bool pushed; };   // floats; off and n are multiples of 4; id: ordinal of the range in
                                                           // the evaluation (its scratch region); pushed: the producer already
                                                           // stored the other ranks' slices into their scratch
-void ntn_launch_exchange(ntn_handle* h, const ExchangeBinding* xb, XRange r0, XRange r1, bool last, cudaStream_t st);
+void ntn_launch_exchange(ntn_handle* h, const ExchangeBinding* xb, XRange r0, XRange r1, XRange r2, bool last, cudaStream_t st);
 XPushRange ntn_push_range(const ntn_handle* h, const ExchangeBinding* xb, int64_t off, int64_t n, int id);
 const ExchangeBinding* ntn_find_binding(const ntn_handle* h, const float* d_grad);
 
@@ -241,7 +248,10 @@ void ntn_launch_score(ntn_handle* h, const float* theta);
 int ntn_score2_rows(int k);   // tile height of the default score kernel
 void ntn_launch_gemm_dw_simt(ntn_handle* h, cudaStream_t st);
 void ntn_launch_gemm_ge_simt(ntn_handle* h);
+void ntn_stamp(ntn_handle* h, int slot, cudaStream_t st);   // NTN_GRAPH_TIMELINE: store %globaltimer into stamp slot (no-op otherwise)
 void ntn_launch_entity_pull(ntn_handle* h);
+int ntn_pull_ranges(const ntn_handle* h);
+void ntn_launch_pull_ranges(ntn_handle* h);
 void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad, const ExchangeBinding* xb);
 void ntn_launch_finalize_small(ntn_handle* h, const float* theta, float* grad, cudaStream_t st);
 void ntn_launch_final_reduce(ntn_handle* h, float* tail);

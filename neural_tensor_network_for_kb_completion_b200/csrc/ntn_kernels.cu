@@ -1029,6 +1029,166 @@ __global__ void __launch_bounds__(256, (KS <= 4) ? 4 : 2) k_entity_pull2(Pull2Ar
 }
 
 // ==========================================================================================
+// K7'' entity-gradient pull, one WARP per range of entities (the default).  Same sorted-segment pull (Util.java:74-98,
+//     NTN.java:372,388; fixed summation order, no float atomics), re-cut for issue slots and latency:
+//       * work is dealt by INCIDENTS, not by entities: range r holds the consecutive entities whose key
+//         inc_off[n] + n falls in [32 r, 32 r + 32) -- at most 32 entities and (hubs aside) at most 63 incidents, so
+//         every warp has the same amount of work whatever the degree distribution, and empty entities (which only need
+//         their zero row) cost one unit each;
+//       * the lanes of the warp first fetch the range's incident records and coefficient records in ONE coalesced
+//         load each (lane l takes incident l) -- the record -> coefficient chain is paid once per 32 incidents, where a
+//         thread per (entity, chunk) paid it per incident and 25 threads decoded the same record -- and then walk the
+//         incidents with the lanes over the float4 chunks of a row, the decoded fields broadcast by shuffle, the rows of
+//         NB incidents requested before the first is consumed;
+//       * an anchor incident reads its GA row only, any other its k T' rows only (the role is known before the rows are
+//         requested).
+//     A hub entity (more than NTN_HUB_SEG incidents, pre-reduced per segment by k_entity_pull2_hub) is always the last
+//     entity of its range: the next key is more than 32 away.
+// ==========================================================================================
+struct Pull3Args {
+    const float *T, *crec, *GA;
+    const int4* inc;
+    const int* inc_off;
+    const int4* rng;                     // {first entity, end entity, first incident, end incident (a trailing hub's excluded)}
+    float* gE;
+    const int *eh_first, *eh_count;
+    const float* eh_part;
+    int nranges, dq, Kp, Np, RS;
+};
+
+__global__ void __launch_bounds__(256) k_pull_ranges(const int* __restrict__ inc_off, const int* __restrict__ eh_count, int Ne,
+                                                     int4* __restrict__ rng) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= Ne) return;
+    const int o = __ldg(inc_off + n), o1 = __ldg(inc_off + n + 1);
+    const int r = (o + n) >> 5;
+    const int rp = n ? ((__ldg(inc_off + n - 1) + n - 1) >> 5) : -1;
+    const int rn = (n + 1 < Ne) ? ((o1 + n + 1) >> 5) : -2;
+    if (r != rp) { rng[r].x = n; rng[r].z = o; }
+    if (r != rn) { rng[r].y = n + 1; rng[r].w = (eh_count && eh_count[n]) ? o : o1; }
+}
+
+template <int KS, int CPL>
+__global__ void __launch_bounds__(128) k_entity_pull3(Pull3Args a) {
+    constexpr int RQ = (KS + 4) / 4;                                  // float4s per coefficient record (KS coefficients + role)
+    constexpr int NB = (12 / (KS * CPL)) < 1 ? 1 : (12 / (KS * CPL)); // incidents whose rows are in flight together
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.nranges) return;
+    const int4 rg = __ldg(a.rng + warp);
+    if (rg.x < 0) return;                                             // no entity starts in this key interval
+    const int n_ent = rg.y - rg.x;
+    const bool last_hub = a.eh_count != nullptr && __ldg(a.eh_count + rg.y - 1) != 0;
+    const int n_flat = n_ent - (last_hub ? 1 : 0);
+    const int my_end = (lane < n_flat) ? __ldg(a.inc_off + rg.x + lane + 1) : 0x7fffffff;
+    int c4[CPL]; bool cv[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { c4[c] = (lane + 32 * c) * 4; cv[c] = c4[c] < a.dq; }
+    float4 acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] = zero4();
+    int e = 0, e_end = __shfl_sync(FULL, my_end, 0);
+    // entity e is complete once the next incident to consume is e_end: store its row, move on (empty entities: zeros)
+    auto flush_until = [&](int jj) {
+        while (e < n_flat && jj == e_end) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                if (cv[c]) *reinterpret_cast<float4*>(a.gE + (size_t)(rg.x + e) * a.dq + c4[c]) = acc[c];
+                acc[c] = zero4();
+            }
+            ++e;
+            e_end = __shfl_sync(FULL, my_end, e & 31);
+        }
+    };
+    for (int jb = rg.z; jb < rg.w; jb += 32) {
+        const int bend = min(jb + 32, rg.w);
+        int4 rec = make_int4(0, 0, 2, 0);
+        float cr[RQ * 4];
+#pragma unroll
+        for (int q = 0; q < RQ * 4; ++q) cr[q] = 0.f;
+        if (jb + lane < bend) {
+            rec = __ldg(a.inc + jb + lane);
+            const float* cp = a.crec + (size_t)rec.y * a.RS;
+#pragma unroll
+            for (int q = 0; q < RQ; ++q) {
+                const float4 t = ldg4(cp + 4 * q);
+                cr[4 * q] = t.x; cr[4 * q + 1] = t.y; cr[4 * q + 2] = t.z; cr[4 * q + 3] = t.w;
+            }
+        }
+        for (int j = jb; j < bend; j += NB) {
+            float4 rows[NB][KS][CPL];
+            float cf[NB][KS];
+            bool anchor[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const int src = (j + i - jb) & 31;
+                const int u = __shfl_sync(FULL, rec.x, src), role = __shfl_sync(FULL, rec.z, src);
+                const float crole = __shfl_sync(FULL, cr[KS], src);
+#pragma unroll
+                for (int s = 0; s < KS; ++s) cf[i][s] = __shfl_sync(FULL, cr[s], src);
+                anchor[i] = role != 2 && crole == (float)role;
+                if (j + i < bend) {
+                    if (anchor[i]) {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) if (cv[c]) rows[i][0][c] = ldg4(a.GA + (size_t)u * a.Kp + c4[c]);
+                    } else {
+                        const float* Trow = a.T + (size_t)u * a.Np;
+#pragma unroll
+                        for (int s = 0; s < KS; ++s)
+#pragma unroll
+                            for (int c = 0; c < CPL; ++c) if (cv[c]) rows[i][s][c] = ldg4(Trow + s * a.dq + c4[c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                if (j + i < bend) {
+                    flush_until(j + i);
+                    if (anchor[i]) {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) if (cv[c]) { acc[c].x += rows[i][0][c].x; acc[c].y += rows[i][0][c].y; acc[c].z += rows[i][0][c].z; acc[c].w += rows[i][0][c].w; }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < KS; ++s)
+#pragma unroll
+                            for (int c = 0; c < CPL; ++c) if (cv[c]) fma4(acc[c], cf[i][s], rows[i][s][c]);
+                    }
+                }
+            }
+        }
+    }
+    flush_until(rg.w);
+    // (rg.w is the end offset of the last flat entity: the loop above has stored it; anything left is an empty tail)
+    while (e < n_flat) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            if (cv[c]) *reinterpret_cast<float4*>(a.gE + (size_t)(rg.x + e) * a.dq + c4[c]) = acc[c];
+            acc[c] = zero4();
+        }
+        ++e;
+    }
+    if (last_hub) {                                                   // sum of the pre-reduced segment rows, in segment order
+        const int n = rg.y - 1, s0 = __ldg(a.eh_first + n), nseg = __ldg(a.eh_count + n);
+        float4 hacc[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) hacc[c] = zero4();
+        for (int sg = 0; sg < nseg; sg += 4) {
+            float4 v[4][CPL];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < CPL; ++c)
+                    v[i][c] = (sg + i < nseg && cv[c]) ? ldg4(a.eh_part + (size_t)(s0 + sg + i) * a.dq + c4[c]) : zero4();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) { hacc[c].x += v[i][c].x; hacc[c].y += v[i][c].y; hacc[c].z += v[i][c].z; hacc[c].w += v[i][c].w; }
+        }
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) if (cv[c]) *reinterpret_cast<float4*>(a.gE + (size_t)n * a.dq + c4[c]) = hacc[c];
+    }
+}
+
+// ==========================================================================================
 // K8  word-gradient pull + regulariser for the word block          NTN.java:411-430,437-438
 //     gWV[w] = (1/B) sum_{n : w in words(n)} gE[n]/len_n  + lambda*theta_w ;  reg += theta_w^2
 //     Sorted-segment pull over the inverse (word -> entity) CSR: deterministic, no float atomics.
@@ -1513,9 +1673,41 @@ int ntn_score2_rows(int k) {
     return SC2_WARPS * g;
 }
 
+int ntn_pull_ranges(const ntn_handle* h) { return (int)(((int64_t)h->b.n_inc + h->dm.Ne) >> 5) + 1; }
+
+// range table of k_entity_pull3, built once per batch job from the incident CSR (b.pull_rng holds ntn_pull_ranges(h) records)
+void ntn_launch_pull_ranges(ntn_handle* h) {
+    const DeviceBatch& b = h->b;
+    cudaMemsetAsync(b.pull_rng, 0xff, (size_t)ntn_pull_ranges(h) * sizeof(int4), h->stream);
+    k_pull_ranges<<<cdiv(h->dm.Ne, 256), 256, 0, h->stream>>>(b.inc_off, b.n_ent_hub_segs ? b.eh_count : nullptr, h->dm.Ne, b.pull_rng);
+}
+
 void ntn_launch_entity_pull(ntn_handle* h) {
     const NtnDims& dm = h->dm;
     const DeviceBatch& b = h->b;
+    // (the warp-per-range kernel is the opt-in variant: at 20,000 x 10 it measured 48.7 us against 42.3 us of the
+    //  thread-per-(entity, chunk) kernel -- 83 warp instructions per incident and 26 % occupancy, ncu profiles/r2_*)
+    static const int pull_variant = [] { const char* e = getenv("NTN_PULL"); return e ? atoi(e) : 2; }();
+    if (!b.use_gv && pull_variant == 3 && dm.dq <= 256) {
+        Pull2Args a2{b.T, b.crec, b.GA, b.inc, b.inc_off, b.ent_order, h->gE,
+                     b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
+                     b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.RS, b.n_ent_hub_segs,
+                     make_fastdiv((unsigned)(dm.dq / 4))};
+        Pull3Args a{b.T, b.crec, b.GA, b.inc, b.inc_off, b.pull_rng, h->gE, b.n_ent_hub_segs ? b.eh_first : nullptr,
+                    b.n_ent_hub_segs ? b.eh_count : nullptr, b.eh_part, ntn_pull_ranges(h), dm.dq, dm.Kp, dm.Np, b.RS};
+        const int cpr3 = dm.dq / 4;
+        const int blocks = cdiv((int64_t)a.nranges * 32, 128);
+        DISPATCH_KS(dm.k, {
+            if (b.n_ent_hub_segs) {
+                k_entity_pull2_hub<KS><<<cdiv((int64_t)b.n_ent_hub_segs * cpr3, 256), 256, 0, h->stream>>>(a2);
+                h->launches++;
+            }
+            if (cpr3 <= 32) k_entity_pull3<KS, 1><<<blocks, 128, 0, h->stream>>>(a);
+            else k_entity_pull3<KS, 2><<<blocks, 128, 0, h->stream>>>(a);
+        });
+        h->launches++;
+        return;
+    }
     if (!b.use_gv) {
         Pull2Args a{b.T, b.crec, b.GA, b.inc, b.inc_off, b.ent_order, h->gE,
                     b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
@@ -1550,14 +1742,13 @@ void ntn_launch_entity_pull(ntn_handle* h) {
 
 // The word pull covers the Nw words in C chunks of whole words (C = 1 unless a gradient exchange is bound): chunk c is
 // words [w0, w0 + wn), one thread per (word pair, float4 chunk), and owns `blocks` regulariser-partial slots from block_off.
-// The last chunk is the smallest (its exchange is the part nothing overlaps).
+// (Equal chunks: an exchange kernel costs ~10 us of launch + flag barrier before it moves a byte, so the schedule that
+// ends first is the one with the fewest kernels that still overlaps half of the bytes -- two chunks, measured.)
 void ntn_word_chunk(const NtnDims& dm, int c, int C, int* w0, int* wn, int* block_off, int* blocks) {
     const int cpr = dm.dq / 4;
     int64_t bound[NTN_MAX_WORD_CHUNKS + 1];
-    // weights 2 : 2 : ... : 2 : 1 (the last chunk half as long)
-    const int64_t wsum = 2 * (int64_t)C - 1;
     bound[0] = 0;
-    for (int i = 1; i <= C; ++i) bound[i] = (i == C) ? dm.Nw : std::min<int64_t>(dm.Nw, ((int64_t)dm.Nw * 2 * i + wsum - 1) / wsum);
+    for (int i = 1; i <= C; ++i) bound[i] = (i == C) ? dm.Nw : ((int64_t)dm.Nw * i + C - 1) / C;     // equal chunks
     int off = 0;
     for (int i = 0; i < c; ++i) off += cdiv(((bound[i + 1] - bound[i] + 1) / 2) * cpr, 256);
     *w0 = (int)bound[c]; *wn = (int)(bound[c + 1] - bound[c]);
@@ -1589,16 +1780,19 @@ void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad, const 
     }
     xa.n = (xb && xa.r[0].world) ? C : 0;
     const bool pushed = xa.n != 0;
+    // hub words: a forked branch that only needs gE and writes rows the main kernel skips.  With a chunked exchange the
+    // branch runs on the exchange's own (high-priority) stream AHEAD of the first chunk's exchange: hub rows lie in any
+    // chunk, and on the low-priority branch stream they would only finish when the main pull has drained.
+    cudaStream_t hub_st = (xb && C > 1) ? h->stream4 : h->stream2;
     if (w.n_hub_segs) {
-        // hub branch on the forked stream: it only needs gE and writes rows the main kernel skips
         cudaEventRecord(h->ev_fork, h->stream);
-        cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-        k_word_pull_hub<<<cdiv((int64_t)w.n_hub_segs * cpr, 256), 256, 0, h->stream2>>>(a);
+        cudaStreamWaitEvent(hub_st, h->ev_fork, 0);
+        k_word_pull_hub<<<cdiv((int64_t)w.n_hub_segs * cpr, 256), 256, 0, hub_st>>>(a);
         DISPATCH_CH(ch, {
-            if (pushed) k_word_finish_hub<CH, true><<<w.n_hub_words, 1024, 0, h->stream2>>>(a, xa);
-            else k_word_finish_hub<CH, false><<<w.n_hub_words, 1024, 0, h->stream2>>>(a, xa);
+            if (pushed) k_word_finish_hub<CH, true><<<w.n_hub_words, 1024, 0, hub_st>>>(a, xa);
+            else k_word_finish_hub<CH, false><<<w.n_hub_words, 1024, 0, hub_st>>>(a, xa);
         });
-        cudaEventRecord(h->ev_join, h->stream2);
+        cudaEventRecord(h->ev_join, hub_st);
         h->launches += 2;
     }
     for (int c = 0; c < C; ++c) {
@@ -1610,17 +1804,13 @@ void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad, const 
             h->launches++;
         }
         if (xb && c + 1 < C) {
-            // chunk c is final in this rank's buffer (once the hub rows and, for the first chunk, the small blocks
-            // have landed): exchange it on the side stream while the pull goes on with chunk c + 1
+            // chunk c is final in this rank's buffer (the hub rows precede it in stream4's order): exchange it on the side
+            // stream while the pull goes on with chunk c + 1.  The W/V/b/U blocks -- finished by a low-priority branch that
+            // ends with the evaluation -- and the tail go out with the last chunk.
             cudaEventRecord(h->ev_x[c], h->stream);
             cudaStreamWaitEvent(h->stream4, h->ev_x[c], 0);
-            XRange r0{dm.oWVint + (int64_t)w0 * dm.dq, (int64_t)wn * dm.dq, 1 + c, pushed}, r1{0, 0, 0, false};
-            if (c == 0) {
-                if (w.n_hub_segs) cudaStreamWaitEvent(h->stream4, h->ev_join, 0);
-                cudaStreamWaitEvent(h->stream4, h->ev_j1, 0);              // W, V, b, U blocks (k_finalize_small / _u)
-                r1 = XRange{0, dm.oWVint, 0, false};
-            }
-            ntn_launch_exchange(h, xb, r0, r1, false, h->stream4);
+            const XRange none{0, 0, 0, false};
+            ntn_launch_exchange(h, xb, XRange{dm.oWVint + (int64_t)w0 * dm.dq, (int64_t)wn * dm.dq, 1 + c, pushed}, none, none, false, h->stream4);
         }
     }
     if (xb && C > 1) cudaEventRecord(h->ev_xdone, h->stream4);

@@ -82,6 +82,13 @@ def main():
             dist.all_reduce(plain)
         t_lib = timed(lib)
         t_alone = timed(lambda: h.eval_dev(t_int.data_ptr(), side, plain.data_ptr(), sync=False))
+        # the exchange kernel alone: latency (16 bytes) and bandwidth (the whole vector), with and without the end barrier
+        probe = {}
+        for name, (off, n, last) in {"tiny": (0, 4, 0), "tiny+end": (0, 4, 1), "full": (0, Pint, 0), "full+end": (0, Pint, 1)}.items():
+            buf.zero_()
+            probe[name] = 1e3 * timed(lambda: h.exchange_probe(buf.data_ptr(), off, n, last, 10), n=20) / 10
+        if rank == 0:
+            print(f"{mode}: exchange kernel alone, us: " + ", ".join(f"{k} {v:.1f}" for k, v in probe.items()) + f" ({4 * Pint / 1e6:.1f} MB)", flush=True)
         if rank == 0:
             print(f"{mode}: active mode {h.exchange_mode}, world {world}, max|fused - nccl| {diff:.3e} (max |g| {scale:.3e}), "
                   f"identical bits on all ranks: {int(flags[0]) == world}, timeouts: {int(flags[1])}, "

