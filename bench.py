@@ -350,9 +350,15 @@ def main():
                     help="N > 1: fused = the library's own peer-memory exchange kernels inside the evaluation; "
                          "library = a NCCL / symmetric-memory all-reduce after it")
     ap.add_argument("--no-lbfgs", action="store_true")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="override the config's batch-job size (training triples; c5: 10,000,000 = BASELINE.json configs[4] in full, "
+                         "sharded with --scaling strong over the GPUs)")
     args = ap.parse_args()
     global SHAPE, BATCH, CONFIG_NAME, D, K_SLICES, NW
     SHAPE, BATCH, CONFIG_NAME = CONFIGS[args.config]
+    if args.batch:
+        BATCH = int(args.batch)
+        CONFIG_NAME = CONFIG_NAME.split(",")[0] + f", {BATCH:,}-triple batch job"
     if SHAPE == "scaled":
         D, K_SLICES, NW = SCALED["d"], SCALED["k"], SCALED["Nw"]
     if args.impl == "reference":

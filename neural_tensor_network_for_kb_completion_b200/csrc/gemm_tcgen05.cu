@@ -50,6 +50,12 @@ struct TcState {
     int KpP = 0, KpN = 0, NpP = 0;
     int* t_anchor = nullptr;                    // [Nu] anchor entity per unique triple, rewritten per evaluation (grow-only)
     size_t anchor_cap = 0;
+    // TMA-fed A operands (fwd: the anchor rows of E gathered into unique-triple order and pre-split by k_tc_anchor_rows;
+    // ge: M as the score kernel writes it, pre-split): no producer warp touches the data
+    bool tma_a = false;
+    float *EA_hi = nullptr, *EA_lo = nullptr;   // [Nu][Kp]
+    size_t ea_cap = 0;
+    CUtensorMap mEA_hi, mEA_lo, mM_hi, mM_lo;
     int* err = nullptr;                         // device flag: a bounded wait expired
     long long* dbg = nullptr;                   // 3 x 256 cycle stamps of CTA (0,0,0) per mode (debug timeline)
 };
@@ -137,14 +143,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
            ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// x = hi + lo with hi, lo exactly representable in TF32 (10 explicit mantissa bits).  Rounding is done with
-// full-rate integer ops (add half an ulp of the 13 dropped bits, mask): cvt.rna.tf32.f32 goes through the
-// slow conversion pipe and was measured to dominate the producers (profiles/r1_tc_timeline.txt).
-__device__ __forceinline__ float tf32_round(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
-__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
-    hi.x = tf32_round(x.x); hi.y = tf32_round(x.y); hi.z = tf32_round(x.z); hi.w = tf32_round(x.w);
-    lo.x = tf32_round(x.x - hi.x); lo.y = tf32_round(x.y - hi.y); lo.z = tf32_round(x.z - hi.z); lo.w = tf32_round(x.w - hi.w);
-}
+// (tf32_round / split_tf32: ntn_internal.h)
 __device__ __forceinline__ float4 ldg4g(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void sts4(uint8_t* base, uint32_t off, const float4& v) { *reinterpret_cast<float4*>(base + off) = v; }
 
@@ -155,6 +154,7 @@ struct TcArgs {
     const int* t_anchor;               // anchor entity of every unique triple for this evaluation's corrupt sides (k_tc_w_prep)
     const uint8_t* side;
     const float *E, *M;
+    const float* M_lo;                 // non-null: M holds the TF32 hi parts and M_lo the lo parts (written split by the score kernel)
     const float *WT, *W;
     float *T, *GA, *dWpart;
     int Kp, Np, KpP, KpN, NpP;
@@ -184,9 +184,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // 16-byte stores).  For 32-bit types the only MN-major layout is SWIZZLE_128B_BASE32B: atoms of 4 K-rows x 128 bytes,
 // 32-byte chunks XOR-ed with (row & 3); tile = [32-float MN atom][32 rows][128 B] -> LBO = 4096, SBO = 512, a k-step
 // (8 rows) advances the start address by 1024.
-template <int MODE, bool TMA_B, bool DW_MN = false>
+template <int MODE, bool TMA_B, bool DW_MN = false, bool TMA_A = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __grid_constant__ CUtensorMap mapB_hi,
-                                                           const __grid_constant__ CUtensorMap mapB_lo) {
+                                                           const __grid_constant__ CUtensorMap mapB_lo,
+                                                           const __grid_constant__ CUtensorMap mapA_hi,
+                                                           const __grid_constant__ CUtensorMap mapA_lo) {
     // SWIZZLE_128B tiles need 1024-byte alignment.  The array is used directly (no pointer arithmetic through
     // integers) so that the stores below stay in the shared state space (STS): with generic stores the compiler
     // cannot hoist the global loads above them and every load round trip is exposed.
@@ -211,10 +213,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
 
     if (threadIdx.x == 0) {
         // full: 128 producer arrivals (+ the TMA issuer's arrive.expect_tx when the weight tile comes by TMA)
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), TMA_B ? 129 : 128); mbar_init(empty_bar(s), 1); }
+        // (TMA_A: both operands come by TMA, the only arrival is the issuing thread's arrive.expect_tx)
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), TMA_A ? 1 : (TMA_B ? 129 : 128)); mbar_init(empty_bar(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
         fence_barrier_init();
         if (TMA_B) { tma_prefetch_desc(&mapB_hi); tma_prefetch_desc(&mapB_lo); }
+        if (TMA_A) { tma_prefetch_desc(&mapA_hi); tma_prefetch_desc(&mapA_lo); }
     }
     if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TC_TMEM_COLS);
     tc_fence_before();
@@ -238,7 +242,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
     const int nkb = (kext + TC_BK - 1) / TC_BK;                                                          \
     (void)bz_; (void)r; (void)m0; (void)u0; (void)n0; (void)nlen;
 
-    if (warp < 9 && warp != 4) {
+    if (TMA_A && warp < 9 && warp != 4) {
+        // ================================ producers, all-TMA ================================
+        // One thread per group (the two groups still take alternate k-blocks, so two stages are requested while the
+        // issuer works on a third): wait for the stage, announce its bytes, request the four boxes -- A hi/lo (128
+        // rows of the pre-split operand, rows past the array end arrive as zeros, rows of the next tile are computed
+        // and never stored) and the weight tile hi/lo.  Nothing is loaded, split or stored by a thread.
+        const int group = warp > 4 ? 1 : 0;
+        if (threadIdx.x == (group ? 160 : 0)) {
+            bool alive = true;
+            int g = 0;
+            for (int w = blockIdx.x; w < nwork && alive; w += gridDim.x) {
+                TC_ITEM_GEOMETRY(w)
+                (void)rows; (void)kext;
+                for (int kb = 0; kb < nkb && alive; ++kb, ++g) {
+                    if ((g & 1) != group) continue;
+                    const int s = g % TC_STAGES;
+                    const uint32_t ph = (g / TC_STAGES) & 1;
+                    alive = mbar_wait(empty_bar(s), ph ^ 1, a.err);
+                    if (!alive) break;
+                    stamp();
+                    const uint32_t sA_hi = smem_u32(smem + s * TC_STAGE_BYTES);
+                    const uint32_t sA_lo = sA_hi + TC_A_BYTES, sB_hi = sA_lo + TC_A_BYTES, sB_lo = sB_hi + TC_B_BYTES;
+                    const int k0 = kb * TC_BK;
+                    mbar_arrive_expect_tx(full_bar(s), 2u * 128u * 128u + 2u * (uint32_t)a.b_box_rows * 128u);
+                    tma_load_2d(sA_hi, &mapA_hi, k0, u0, full_bar(s));
+                    tma_load_2d(sA_lo, &mapA_lo, k0, u0, full_bar(s));
+                    const int y = r * a.b_rows_per_rel + n0;
+                    tma_load_2d(sB_hi, &mapB_hi, k0, y, full_bar(s));
+                    tma_load_2d(sB_lo, &mapB_lo, k0, y, full_bar(s));
+                    stamp();
+                }
+            }
+        }
+    } else if (warp < 9 && warp != 4) {
         // ================================ producers ================================
         // two groups of 128 threads take alternate k-blocks (of the CTA's whole item sequence), so two k-blocks'
         // global loads are in flight
@@ -354,7 +391,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
                 } else if (DW_MN) {
                     // ---- dw, MN-major tiles: rows as they are.  Thread (rsub, j): rows ul = rsub, rsub+16 of the k-block,
                     //      16-byte chunk j of every 32-float atom.
-                    float4 xa[2][4], xb[2][TC_NCH / 32];
+                    float4 xa[2][4], xb[2][TC_NCH / 32], xl[2][TC_NCH / 32];
+                    const bool msplit = a.M_lo != nullptr;
     #pragma unroll
                     for (int i2 = 0; i2 < 2; ++i2) {
                         const int u = k0 + rsub + 16 * i2;
@@ -368,6 +406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
                         for (int ni = 0; ni < TC_NCH / 32; ++ni) {
                             const int n = ni * 32 + j * 4;
                             xb[i2][ni] = (an >= 0 && n < nlen) ? ldg4g(a.M + (size_t)(u0 + u) * a.Np + n0 + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            xl[i2][ni] = (msplit && an >= 0 && n < nlen) ? ldg4g(a.M_lo + (size_t)(u0 + u) * a.Np + n0 + n) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
     #pragma unroll
@@ -383,8 +422,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
     #pragma unroll
                         for (int ni = 0; ni < TC_NCH / 32; ++ni) {
                             if (ni * 32 < nlen) {
-                                float4 hi, lo;
-                                split_tf32(xb[i2][ni], hi, lo);
+                                float4 hi = xb[i2][ni], lo = xl[i2][ni];          // already split by the score kernel ...
+                                if (!msplit) split_tf32(xb[i2][ni], hi, lo);      // ... or split here
                                 sts4(sB_hi, ni * 4096 + rowoff, hi); sts4(sB_lo, ni * 4096 + rowoff, lo);
                             }
                         }
@@ -607,6 +646,95 @@ __global__ void __launch_bounds__(256) k_tc_w_prep(const float* __restrict__ the
     }
 }
 
+
+// Weight preparation for the TMA path, tiled.  The generic kernel above walks the OUTPUT arrays element by element
+// (two 64-bit divisions and a transposed, uncoalesced read of W per element: 11 us for 13 x 3 slices of 100 x 100, all of
+// it beside the entity build on the critical path).  Here one block takes a 32 x 32 tile of a slice W_r[s], reads it
+// once, coalesced, splits it, and writes it straight into one orientation and -- through a shared-memory transpose --
+// into the other, both coalesced.  Which orientation is the straight one depends on the relation's corrupt side
+// (NTN.java:146-156): tail: Waug[p][s dq + q] = W[s][p][q];  head: Waug[p][s dq + q] = W[s][q][p].
+// The V / b border (row d and the k trailing columns) and the anchor table are done by k_tc_w_border.  Everything else
+// in the four arrays is padding: zeroed once when they are allocated, never written again.
+__global__ void __launch_bounds__(256) k_tc_w_tiles(const float* __restrict__ theta, const uint8_t* __restrict__ side,
+                                                    float* __restrict__ WT_hi, float* __restrict__ WT_lo,
+                                                    float* __restrict__ W_hi, float* __restrict__ W_lo,
+                                                    NtnDims dm, int KpP, int KpN, int NpP, int tiles) {
+    __shared__ float t_hi[32][33], t_lo[32][33];
+    const int r = blockIdx.z, s = blockIdx.y, ti = blockIdx.x / tiles, tj = blockIdx.x - ti * tiles;
+    const int d = dm.d, dq = dm.dq;
+    const bool tail = side[r] != 0;
+    const float* Wsl = theta + dm.oW + ((int64_t)r * dm.k + s) * d * d;
+    float* WTh = WT_hi + (size_t)r * dm.Np * KpP; float* WTl = WT_lo + (size_t)r * dm.Np * KpP;     // [n][p]
+    float* Wh = W_hi + (size_t)r * KpN * NpP;     float* Wl = W_lo + (size_t)r * KpN * NpP;         // [p][n]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int a = ti * 32 + j, b = tj * 32 + tx;                  // element W[s][a][b], b contiguous
+        float hi = 0.f, lo = 0.f;
+        if (a < d && b < d) {
+            const float v = __ldg(Wsl + (size_t)a * d + b);
+            hi = tf32_round(v); lo = tf32_round(v - hi);
+            // straight orientation: tail -> W[p = a][n = s dq + b];  head -> WT[n = s dq + a][p = b]
+            if (tail) { Wh[(size_t)a * NpP + s * dq + b] = hi; Wl[(size_t)a * NpP + s * dq + b] = lo; }
+            else { WTh[(size_t)(s * dq + a) * KpP + b] = hi; WTl[(size_t)(s * dq + a) * KpP + b] = lo; }
+        }
+        t_hi[j][tx] = hi; t_lo[j][tx] = lo;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int a = ti * 32 + tx, b = tj * 32 + j;                  // element W[s][a][b], now a contiguous
+        if (a < d && b < d) {
+            const float hi = t_hi[tx][j], lo = t_lo[tx][j];
+            // transposed orientation: tail -> WT[n = s dq + b][p = a];  head -> W[p = b][n = s dq + a]
+            if (tail) { WTh[(size_t)(s * dq + b) * KpP + a] = hi; WTl[(size_t)(s * dq + b) * KpP + a] = lo; }
+            else { Wh[(size_t)b * NpP + s * dq + a] = hi; Wl[(size_t)b * NpP + s * dq + a] = lo; }
+        }
+    }
+}
+
+// the V / b border of Waug (k_w_prep in ntn_kernels.cu spells the layout out) in both orientations, and the anchor
+// entity of every unique triple under this evaluation's corrupt sides
+__global__ void __launch_bounds__(256) k_tc_w_border(const float* __restrict__ theta, const uint8_t* __restrict__ side,
+                                                     float* __restrict__ WT_hi, float* __restrict__ WT_lo,
+                                                     float* __restrict__ W_hi, float* __restrict__ W_lo,
+                                                     NtnDims dm, int KpP, int KpN, int NpP, const int* __restrict__ u_rel,
+                                                     const int* __restrict__ u_e1, const int* __restrict__ u_e2, int Nu,
+                                                     int* __restrict__ t_anchor) {
+    const int d = dm.d, k = dm.k, dq = dm.dq;
+    const int per = k * d + k * (d + 1);                              // row d under the slices, then the k trailing columns
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)dm.R * per) {
+        const int r = (int)(i / per), e = (int)(i - (int64_t)r * per);
+        int p, n;
+        if (e < k * d) { const int s = e / d; p = d; n = s * dq + (e - s * d); }
+        else { const int e2 = e - k * d, s = e2 / (d + 1); p = e2 - s * (d + 1); n = k * dq + s; }
+        const float v = waug_at(theta, dm, r, side[r] != 0, p, n);
+        const float hi = tf32_round(v), lo = tf32_round(v - hi);
+        const size_t ia = (size_t)r * dm.Np * KpP + (size_t)n * KpP + p, ib = (size_t)r * KpN * NpP + (size_t)p * NpP + n;
+        WT_hi[ia] = hi; WT_lo[ia] = lo; W_hi[ib] = hi; W_lo[ib] = lo;
+    } else if (i < (int64_t)dm.R * per + Nu) {
+        const int u = (int)(i - (int64_t)dm.R * per);
+        t_anchor[u] = side[u_rel[u]] != 0 ? u_e1[u] : u_e2[u];
+    }
+}
+
+// A operand of the forward contraction for the all-TMA path: the anchor entity's augmented row of every unique triple,
+// gathered into unique-triple order and split into TF32 hi / lo (NTN.java:146-156 picks the anchor, :163-197 contracts
+// it).  One thread per (unique triple, float4 chunk); E was written by the entity build just before and sits in L2.
+__global__ void __launch_bounds__(256) k_tc_anchor_rows(const float* __restrict__ E, const int* __restrict__ t_anchor,
+                                                        float* __restrict__ EA_hi, float* __restrict__ EA_lo, int Nu, int Kp) {
+    const int cpr = Kp >> 2;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Nu * cpr) return;
+    const int u = (int)(i / cpr), c = (int)(i - (int64_t)u * cpr);
+    const float4 v = ldg4g(E + (size_t)__ldg(t_anchor + u) * Kp + 4 * c);
+    float4 hi, lo;
+    split_tf32(v, hi, lo);
+    *reinterpret_cast<float4*>(EA_hi + (size_t)u * Kp + 4 * c) = hi;
+    *reinterpret_cast<float4*>(EA_lo + (size_t)u * Kp + 4 * c) = lo;
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -647,7 +775,7 @@ static TcArgs tc_args(ntn_handle* h, bool chunks) {
     const DeviceBatch& b = h->b;
     TcArgs a{};
     a.t_rel = chunks ? b.ch_rel : b.t_rel; a.t_u0 = chunks ? b.ch_u0 : b.t_u0; a.t_n = chunks ? b.ch_n : b.t_n;
-    a.u_e1 = b.u_e1; a.u_e2 = b.u_e2; a.t_anchor = st->t_anchor; a.side = h->side; a.E = h->E; a.M = b.M;
+    a.u_e1 = b.u_e1; a.u_e2 = b.u_e2; a.t_anchor = st->t_anchor; a.side = h->side; a.E = h->E; a.M = b.M; a.M_lo = b.m_split ? b.M_lo : nullptr;
     a.WT = st->WT; a.W = st->W;
     a.T = b.T; a.GA = b.GA; a.dWpart = b.dWpart;
     a.Kp = h->dm.Kp; a.Np = h->dm.Np; a.KpP = st->KpP; a.KpN = st->KpN; a.NpP = st->NpP;
@@ -679,6 +807,12 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
                 h->err = std::string("tcgen05 TMA state: ") + cudaGetErrorString(e);
                 return NTN_ECUDA;
             }
+            // padding rows / columns stay zero for the life of the handle (the per-evaluation kernels only write live entries)
+            if ((e = cudaMemset(st->WT_hi, 0, nA * 4)) || (e = cudaMemset(st->WT_lo, 0, nA * 4)) ||
+                (e = cudaMemset(st->W_hi, 0, nB * 4)) || (e = cudaMemset(st->W_lo, 0, nB * 4))) {
+                h->err = std::string("tcgen05 TMA state: ") + cudaGetErrorString(e);
+                return NTN_ECUDA;
+            }
             st->box_fwd = std::min(TC_NCH, dm.Np);
             st->box_ge = std::min(TC_NCH, st->KpN);
             if (!make_map(&st->mWT_hi, st->WT_hi, st->KpP, (uint64_t)dm.R * dm.Np, st->box_fwd) ||
@@ -691,12 +825,25 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
         }
         const char* dw_env = getenv("NTN_TC_DW");
         st->dw_mn = dw_env ? (dw_env[0] == 'm') : true;      // NTN_TC_DW=k selects the K-major transposing producers
+        // all-TMA forward / entity-gradient contractions: opt-in (NTN_TC_TMA_A=1); needs the TMA-fed weights and the
+        // MN-major dw (the only dw producers that read M pre-split).  Measured at 20,000 x 10 on one B200 (same box,
+        // alternating runs): entity-gradient contraction 28.5 -> 26.9 us, but forward 23.4 -> 27.1 us (the anchor-row gather
+        // kernel), score 43 -> 47 us (M written twice), entity pull 56 -> 65 us (48 MB of M_hi / M_lo push T' out of the
+        // L2), evaluation 0.2164 -> 0.2255 ms.  The cycle timeline (scripts/tc_timeline.py) shows why feeding the operand
+        // faster buys so little: with every tile coming by TMA a k-block still takes ~1460 cycles -- twelve
+        // 128 x 104 x 8 MMAs at ~122 cycles each, and the 128 x 152 x 8 MMAs of the forward contraction take ~126: the
+        // issue cost of a kind::tf32 MMA is that of a full 128 x 256 x 8 one (139 cycles at the measured cuBLAS rate), so
+        // these contractions run the tensor pipe at N/256 of its rate whatever feeds them.
+        const char* ta_env = getenv("NTN_TC_TMA_A");
+        st->tma_a = st->use_tma && st->dw_mn && ta_env && ta_env[0] == '1';
         if ((e = cudaFuncSetAttribute(k_tc_gemm<TC_DW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
             (e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
             (e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
             (e = cudaFuncSetAttribute(k_tc_gemm<TC_DW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
             (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
-            (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES))) {
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES))) {
             h->err = std::string("tcgen05 smem attribute: ") + cudaGetErrorString(e);
             return NTN_ECUDA;
         }
@@ -711,6 +858,26 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
             if (e != cudaSuccess) { h->err = std::string("tcgen05 anchor table: ") + cudaGetErrorString(e); return NTN_ECUDA; }
             st->anchor_cap = need;
         }
+        // all-TMA path: the gathered anchor rows (grow-only) and the tensor maps of this batch job's A operands
+        h->b.m_split = false;
+        if (st->tma_a && h->b.Nu > 0) {
+            const uint64_t rows_a = (uint64_t)std::max(h->b.Nu, 128);       // at least one 128-row box of allocated memory
+            const size_t ea_need = (size_t)rows_a * (size_t)dm.Kp;
+            if (st->ea_cap < ea_need) {
+                cudaFree(st->EA_hi); cudaFree(st->EA_lo); st->EA_hi = st->EA_lo = nullptr; st->ea_cap = 0;
+                cudaError_t e;
+                if ((e = cudaMalloc((void**)&st->EA_hi, ea_need * 4)) || (e = cudaMalloc((void**)&st->EA_lo, ea_need * 4))) {
+                    h->err = std::string("tcgen05 anchor rows: ") + cudaGetErrorString(e); return NTN_ECUDA;
+                }
+                st->ea_cap = ea_need;
+            }
+            if (!make_map(&st->mEA_hi, st->EA_hi, dm.Kp, rows_a, 128) || !make_map(&st->mEA_lo, st->EA_lo, dm.Kp, rows_a, 128) ||
+                !make_map(&st->mM_hi, h->b.M, dm.Np, rows_a, 128) || !make_map(&st->mM_lo, h->b.M_lo, dm.Np, rows_a, 128)) {
+                h->err = "cuTensorMapEncodeTiled failed (A operands)";
+                return NTN_ECUDA;
+            }
+            h->b.m_split = true;
+        }
     }
     return NTN_OK;
 }
@@ -720,6 +887,7 @@ void ntn_tc_release(ntn_handle* h) {
     if (!st) return;
     cudaFree(st->WT); cudaFree(st->W); cudaFree(st->err); cudaFree(st->dbg); cudaFree(st->t_anchor);
     cudaFree(st->WT_hi); cudaFree(st->WT_lo); cudaFree(st->W_hi); cudaFree(st->W_lo);
+    cudaFree(st->EA_hi); cudaFree(st->EA_lo);
     delete st;
     h->tc = nullptr;
 }
@@ -727,6 +895,17 @@ void ntn_tc_release(ntn_handle* h) {
 int ntn_tc_w_prep(ntn_handle* h, const float* theta, cudaStream_t stq) {
     TcState* st = (TcState*)h->tc;
     const NtnDims& dm = h->dm;
+    static const bool tiled = [] { const char* e = getenv("NTN_TC_WPREP"); return !(e && e[0] == '0'); }();
+    if (st->use_tma && tiled) {
+        const int tiles = (dm.d + 31) / 32;
+        k_tc_w_tiles<<<dim3(tiles * tiles, dm.k, dm.R), 256, 0, stq>>>(theta, h->side, st->WT_hi, st->WT_lo, st->W_hi, st->W_lo, dm,
+                                                                         st->KpP, st->KpN, st->NpP, tiles);
+        const int64_t nb = (int64_t)dm.R * (dm.k * dm.d + dm.k * (dm.d + 1)) + h->b.Nu;
+        k_tc_w_border<<<cdivi(nb, 256), 256, 0, stq>>>(theta, h->side, st->WT_hi, st->WT_lo, st->W_hi, st->W_lo, dm, st->KpP, st->KpN,
+                                                       st->NpP, h->b.u_rel, h->b.u_e1, h->b.u_e2, h->b.Nu, st->t_anchor);
+        h->launches += 2;
+        return NTN_OK;
+    }
     int64_t n = (int64_t)dm.R * dm.Np * st->KpP + (int64_t)dm.R * st->KpN * st->NpP + h->b.Nu;
     k_tc_w_prep<<<cdivi(n, 256), 256, 0, stq>>>(theta, h->side, st->WT, st->W, st->WT_hi, st->WT_lo, st->W_hi, st->W_lo, dm,
                                                       st->KpP, st->KpN, st->NpP, h->b.u_rel, h->b.u_e1, h->b.u_e2, h->b.Nu, st->t_anchor);
@@ -746,11 +925,18 @@ int ntn_tc_gemm_fwd(ntn_handle* h) {
     TcArgs a = tc_args(h, false);
     TcState* st = (TcState*)h->tc;
     dim3 g = tc_grid(h, a, h->b.ntiles, cdivi(h->dm.Np, TC_NCH), 1);
-    if (st->use_tma) {
+    if (h->b.m_split) {
+        // all-TMA: gather + split the anchor rows once, then every operand tile is a TMA box
+        const int64_t nthr = (int64_t)h->b.Nu * (h->dm.Kp / 4);
+        k_tc_anchor_rows<<<cdivi(nthr, 256), 256, 0, h->stream>>>(h->E, st->t_anchor, st->EA_hi, st->EA_lo, h->b.Nu, h->dm.Kp);
+        h->launches++;
         a.b_rows_per_rel = h->dm.Np; a.b_box_rows = st->box_fwd;
-        k_tc_gemm<TC_FWD, true><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mWT_hi, st->mWT_lo);
+        k_tc_gemm<TC_FWD, true, false, true><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mWT_hi, st->mWT_lo, st->mEA_hi, st->mEA_lo);
+    } else if (st->use_tma) {
+        a.b_rows_per_rel = h->dm.Np; a.b_box_rows = st->box_fwd;
+        k_tc_gemm<TC_FWD, true><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mWT_hi, st->mWT_lo, st->mWT_hi, st->mWT_lo);
     } else {
-        k_tc_gemm<TC_FWD, false><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mWT_hi, st->mWT_lo);
+        k_tc_gemm<TC_FWD, false><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mWT_hi, st->mWT_lo, st->mWT_hi, st->mWT_lo);
     }
     h->launches++;
     return NTN_OK;
@@ -768,8 +954,8 @@ int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t stq) {
     const int dw_ctas = dw_env >= 0 ? dw_env : (h->b.Nu <= 65536 ? (h->sm_count + 2) / 3 : 0);
     if (dw_ctas > 0 && (int)g.x > dw_ctas) g.x = dw_ctas;
     TcState* st = (TcState*)h->tc;
-    if (st->dw_mn) k_tc_gemm<TC_DW, false, true><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo);
-    else k_tc_gemm<TC_DW, false><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo);
+    if (st->dw_mn) k_tc_gemm<TC_DW, false, true><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo, st->mWT_hi, st->mWT_lo);
+    else k_tc_gemm<TC_DW, false><<<g, TC_THREADS, TC_SMEM_BYTES, stq>>>(a, st->mWT_hi, st->mWT_lo, st->mWT_hi, st->mWT_lo);
     h->launches++;
     return NTN_OK;
 }
@@ -778,11 +964,14 @@ int ntn_tc_gemm_ge(ntn_handle* h) {
     TcArgs a = tc_args(h, false);
     TcState* st = (TcState*)h->tc;
     dim3 g = tc_grid(h, a, h->b.ntiles, cdivi(st->KpN, TC_NCH), 1);
-    if (st->use_tma) {
+    if (h->b.m_split) {
         a.b_rows_per_rel = st->KpN; a.b_box_rows = st->box_ge;
-        k_tc_gemm<TC_GE, true><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mW_hi, st->mW_lo);
+        k_tc_gemm<TC_GE, true, false, true><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mW_hi, st->mW_lo, st->mM_hi, st->mM_lo);
+    } else if (st->use_tma) {
+        a.b_rows_per_rel = st->KpN; a.b_box_rows = st->box_ge;
+        k_tc_gemm<TC_GE, true><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mW_hi, st->mW_lo, st->mW_hi, st->mW_lo);
     } else {
-        k_tc_gemm<TC_GE, false><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mW_hi, st->mW_lo);
+        k_tc_gemm<TC_GE, false><<<g, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mW_hi, st->mW_lo, st->mW_hi, st->mW_lo);
     }
     h->launches++;
     return NTN_OK;

@@ -171,7 +171,7 @@ static void free_batch(DeviceBatch& b) {
     dev_free(b.t_rel); dev_free(b.t_u0); dev_free(b.t_n); dev_free(b.ch_rel); dev_free(b.ch_u0); dev_free(b.ch_n);
     dev_free(b.relch_off); dev_free(b.reltile_off); dev_free(b.inc_off); dev_free(b.inc);
     dev_free(b.eh_ent); dev_free(b.eh_begin); dev_free(b.eh_end); dev_free(b.eh_first); dev_free(b.eh_count);
-    dev_free(b.T); dev_free(b.M); dev_free(b.GA); dev_free(b.GV); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.crec); dev_free(b.ent_order); dev_free(b.pull_rng); dev_free(b.dWpart);
+    dev_free(b.T); dev_free(b.M); dev_free(b.M_lo); dev_free(b.GA); dev_free(b.GV); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.crec); dev_free(b.ent_order); dev_free(b.pull_rng); dev_free(b.dWpart);
     dev_free(b.tp_cost); dev_free(b.tp_nact); dev_free(b.tp_dU); dev_free(b.eh_part);
     b = DeviceBatch();
 }
@@ -400,9 +400,11 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
     // Contraction tile height (rows of unique triples, <= 128 = the UMMA M).  The persistent tcgen05 grid deals
     // (tile x N-chunk) items round-robin to one CTA per SM, so a kernel lasts ceil(items / SMs) item times: 163 tiles of
     // 128 rows on 148 SMs are TWO rounds for the entity-gradient contraction (the second 10 % full) and three for the
-    // forward one (two N-chunks).  A lower tile (the MMA still runs M = 128; the gather, the epilogue and the stores
-    // scale with the valid rows) that fills the last round wins at the reference's batch size; long grids keep 128.
-    // Cost model: rounds x (rows + a fixed per-item cost worth ~24 rows), summed over the two kernels.
+    // forward one (two N-chunks).  Measured at 20,000 x 10 (NTN_TILE_ROWS = 128 / 96 / 72 / 64): forward 24.2 / 23.3 /
+    // 26.4 / 30.3 us, entity-gradient 28.8 / 28.4 / 28.3 / 36.9 us -- an item costs nearly the same whatever its height
+    // (the MMA runs M = 128 regardless, every producer thread walks its 8 rows, the weight tile is the same), so what
+    // counts is the number of rounds and only then the height.  Cost model: rounds x (rows + a fixed per-item cost worth
+    // 256 rows), summed over the two kernels.
     int tile_rows = NTN_TILE_ROWS;
     {
         const int ny_fwd = (dm.Np + 159) / 160, ny_ge = (dm.Kp + 159) / 160;     // N-chunks of <= 160 accumulator columns
@@ -410,7 +412,7 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
         double best = 1e300;
         for (int rows = NTN_TILE_ROWS; rows >= 32; rows -= 8) {
             const int64_t t = tiles_at(rows);
-            const double cost = (double)((t * ny_fwd + h->sm_count - 1) / h->sm_count + (t * ny_ge + h->sm_count - 1) / h->sm_count) * (rows + 24);
+            const double cost = (double)((t * ny_fwd + h->sm_count - 1) / h->sm_count + (t * ny_ge + h->sm_count - 1) / h->sm_count) * (rows + 256);
             if (cost < best - 1e-9) { best = cost; tile_rows = rows; }
         }
         if (const char* e = getenv("NTN_TILE_ROWS")) tile_rows = std::max(8, std::min(NTN_TILE_ROWS, atoi(e) / 8 * 8));
@@ -440,7 +442,10 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
         (rc = dev_upload(h, &b.rels_off, rels_off)) ||
         (rc = dev_upload(h, &b.ch_rel, ch_rel)) || (rc = dev_upload(h, &b.ch_u0, ch_u0)) || (rc = dev_upload(h, &b.ch_n, ch_n)) ||
         (rc = dev_upload(h, &b.relch_off, relch_off)) || (rc = dev_upload(h, &b.reltile_off, reltile_off)) ||
-        (rc = dev_alloc(h, &b.T, (size_t)Nu * dm.Np)) || (rc = dev_alloc(h, &b.M, (size_t)Nu * dm.Np)) ||
+        (rc = dev_alloc(h, &b.T, (size_t)Nu * dm.Np)) ||
+        // (M, M_lo: at least one 128-row TMA box, so that the tensor map of a tiny batch job covers allocated memory)
+        (rc = dev_alloc(h, &b.M, (size_t)std::max(Nu, 128) * dm.Np)) ||
+        (rc = dev_alloc(h, &b.M_lo, h->cfg.gemm_path != NTN_GEMM_SIMT ? (size_t)std::max(Nu, 128) * dm.Np : 1)) ||
         (rc = dev_alloc(h, &b.GA, (size_t)Nu * dm.Kp)) || (rc = dev_alloc(h, &b.GV, use_gv ? ((size_t)Nu + (size_t)n) * dm.dq : 1)) || (rc = dev_alloc(h, &b.acoef, use_gv ? ((size_t)Nu + (size_t)n) * dm.k : 1)) ||
         (rc = dev_alloc(h, &b.crec, use_gv ? 1 : ((size_t)Nu + (size_t)n) * (size_t)round_up(dm.k + 1, 4))) ||
         (rc = dev_alloc(h, &b.dWpart, (size_t)b.nchunks * dm.Kp * dm.Np)) ||
@@ -455,10 +460,11 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
     CK(cudaStreamSynchronize(h->stream));            // the small tables above come from host vectors that die here
     // contraction path for this batch
     h->gemm_path_active = NTN_GEMM_SIMT;
+    b.m_split = false;
     if (h->cfg.gemm_path != NTN_GEMM_SIMT) {
         if (ntn_tc_supported(h)) {
             rc = ntn_tc_prepare_batch(h);
-            if (rc) return rc;
+            if (rc) { ntn_tc_release(h); b.m_split = false; return rc; }     // (a half-built state must not be reused by the next job)
             h->gemm_path_active = NTN_GEMM_TCGEN05;
         } else if (h->cfg.gemm_path == NTN_GEMM_TCGEN05) {
             FAIL(NTN_EUNSUP, "tcgen05 contraction path does not support this shape");
@@ -1018,6 +1024,17 @@ extern "C" int64_t ntn_debug_fetch(ntn_handle* h, const char* name, float* out, 
     const float* src = nullptr; int64_t n = 0;
     std::string s(name);
     if (s == "T") { src = b.T; n = (int64_t)b.Nu * dm.Np; }
+    else if (s == "M" && b.m_split) {
+        // the contractions take M pre-split: hand back hi + lo
+        n = (int64_t)b.Nu * dm.Np;
+        if (out && cap >= n) {
+            std::vector<float> lo((size_t)n);
+            cudaMemcpy(out, b.M, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+            cudaMemcpy(lo.data(), b.M_lo, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+            for (int64_t i = 0; i < n; ++i) out[i] += lo[(size_t)i];
+        }
+        return n;
+    }
     else if (s == "M") { src = b.M; n = (int64_t)b.Nu * dm.Np; }
     else if (s == "GA") { src = b.GA; n = (int64_t)b.Nu * dm.Kp; }
     else if (s == "dWpart") { src = b.dWpart; n = (int64_t)b.nchunks * dm.Kp * dm.Np; }

@@ -42,6 +42,18 @@ __host__ __device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f
 #endif
     return (t + ((n - t) >> 1)) >> f.s;
 }
+// x = hi + lo with hi, lo exactly representable in TF32 (10 explicit mantissa bits): the operand split of the 3xTF32
+// contractions (gemm_tcgen05.cu).  Rounding with full-rate integer ops (add half an ulp of the 13 dropped bits, mask):
+// cvt.rna.tf32.f32 goes through the slow conversion pipe.  Shared with the kernels that PRODUCE a contraction operand
+// already split (k_score2 -> M_hi / M_lo, k_tc_anchor_rows), so that the operand can be fed by TMA untouched.
+#ifdef __CUDACC__
+__device__ __forceinline__ float tf32_round(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
+    hi.x = tf32_round(x.x); hi.y = tf32_round(x.y); hi.z = tf32_round(x.z); hi.w = tf32_round(x.w);
+    lo.x = tf32_round(x.x - hi.x); lo.y = tf32_round(x.y - hi.y); lo.z = tf32_round(x.z - hi.z); lo.w = tf32_round(x.w - hi.w);
+}
+#endif
+
 struct NtnDims {
     int d, k, R, Ne, Nw;
     int dq, Kp, Np;
@@ -92,7 +104,9 @@ struct DeviceBatch {
     int *eh_count = nullptr;     // Ne: number of segments
     // per-evaluation intermediates
     float *T = nullptr;          // Nu x Np   T' = [E_anchor | 1] * Waug
-    float *M = nullptr;          // Nu x Np   backward coefficients folded with the gathered rows
+    float *M = nullptr;          // Nu x Np   backward coefficients folded with the gathered rows (m_split: their TF32 hi parts)
+    float *M_lo = nullptr;       // Nu x Np   m_split: the TF32 lo parts (M = M + M_lo), written by the score kernels
+    bool m_split = false;        // the tcgen05 contractions take M pre-split (TMA-fed A operand of the entity-gradient contraction)
     float *GA = nullptr;         // Nu x Kp   anchor-entity gradient rows
     float *GV = nullptr;         // (Nu + N) x dq   per-incident contribution rows (non-anchor roles), written by k_score
     float *crec = nullptr;       // (Nu + N) x RS packed coefficient records (k_score2 -> k_entity_pull2), RS = ceil4(k + 1)

@@ -36,6 +36,21 @@ __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
     acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y);
     acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
 }
+// store of an M element group: plain, or split into TF32 hi / lo arrays when the contractions take M pre-split
+__device__ __forceinline__ void store_m4(float* Mhi, float* Mlo, size_t off, const float4& v) {
+    if (Mlo) {
+        float4 hi, lo;
+        split_tf32(v, hi, lo);
+        *reinterpret_cast<float4*>(Mhi + off) = hi;
+        *reinterpret_cast<float4*>(Mlo + off) = lo;
+    } else {
+        *reinterpret_cast<float4*>(Mhi + off) = v;
+    }
+}
+__device__ __forceinline__ void store_m1(float* Mhi, float* Mlo, size_t off, float v) {
+    if (Mlo) { const float hi = tf32_round(v); Mhi[off] = hi; Mlo[off] = tf32_round(v - hi); }
+    else Mhi[off] = v;
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(256) k_gemm_dw_simt(GemmTables tb, const float
 // ==========================================================================================
 struct ScoreArgs {
     const float *theta, *E, *T;
-    float *M, *acoef, *ccoef;
+    float *M, *M_lo, *acoef, *ccoef;
     float* GV;                 // (Nu + N) x dq: per-incident contribution rows for the entity pull
     int Nu;
     const int *t_rel, *t_u0, *t_n, *u_e1, *u_e2, *c_off, *c_e3;
@@ -335,7 +350,7 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane
 }
 
 template <int KS, int CH, int ACT, bool GVW>
-__global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
+__global__ void __launch_bounds__(256, (KS * CH > 8) ? 1 : 2) k_score(ScoreArgs a) {   // wide rows (k = 8, d = 256): one block per SM, 255 registers, no spill
     // corrupt columns per batch: their KS pre-activations each fill the 32 lanes (KS=3 -> 10 columns,
     // the reference's corrupt_size); all row gathers of a batch are issued before any is used.
     constexpr int COLB = (CH == 1) ? ((32 / KS) < 10 ? (32 / KS) : 10) : ((16 / KS) < 1 ? 1 : ((16 / KS) < 5 ? (16 / KS) : 5));
@@ -504,7 +519,7 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
                 }
             }
         }
-        float* Mrow = a.M + (size_t)u * a.Np;
+        const size_t Mrow = (size_t)u * a.Np;
         float4 gvo[CH];
 #pragma unroll
         for (int c = 0; c < CH; ++c) gvo[c] = zero4();
@@ -516,7 +531,7 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
             for (int c = 0; c < CH; ++c) {
                 fma4(Macc[s][c], as, eo[c]);
                 if (GVW) fma4(gvo[c], as, t[s][c]);
-                if (cv[c]) *reinterpret_cast<float4*>(Mrow + s * dq + (lane + 32 * c) * 4) = Macc[s][c];
+                if (cv[c]) store_m4(a.M, a.M_lo, Mrow + s * dq + (lane + 32 * c) * 4, Macc[s][c]);
             }
             if (lane == 0) a.acoef[(size_t)u * KS + s] = as;
         }
@@ -531,7 +546,7 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
             float vv = 0.f;
 #pragma unroll
             for (int s = 0; s < KS; ++s) if (n == KS * dq + s) vv = csum[s];
-            Mrow[n] = vv;
+            store_m1(a.M, a.M_lo, Mrow + n, vv);
         }
     }
     // tile partials, fixed order: lanes, then warps
@@ -575,7 +590,7 @@ __global__ void __launch_bounds__(256, 2) k_score(ScoreArgs a) {
 
 struct Score2Args {
     const float *theta, *E, *T;
-    float *M, *crec;
+    float *M, *M_lo, *crec;
     int Nu, RS;                    // RS = floats per coefficient record (KS + 1 rounded up to 4)
     const int *t_rel, *t_u0, *t_n, *u_e1, *u_e2, *c_off, *c_e3;
     const uint8_t* side;
@@ -757,7 +772,7 @@ __global__ void __launch_bounds__(SC2_WARPS * 32) k_score2(Score2Args a) {   // 
     const bool masked = dq != a.d;
     float4 msk = make_float4(1.f, 1.f, 1.f, 1.f);
     if (masked) { const int p = dq - 4; msk = make_float4(p < a.d ? 1.f : 0.f, p + 1 < a.d ? 1.f : 0.f, p + 2 < a.d ? 1.f : 0.f, 0.f); }
-    float* Mr = a.M + (size_t)u * a.Np;
+    const size_t Mr = (size_t)u * a.Np;
 #pragma unroll (DQT ? 8 : 1)
     for (int it = 0; it < nit; ++it) {
         const int p = l + L * it;
@@ -786,19 +801,19 @@ __global__ void __launch_bounds__(SC2_WARPS * 32) k_score2(Score2Args a) {   // 
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
             if (masked && p == nch - 1) { m[i].x *= msk.x; m[i].y *= msk.y; m[i].z *= msk.z; m[i].w *= msk.w; }
-            if (valid && sv[i]) *reinterpret_cast<float4*>(Mr + so[i] + p4) = m[i];
+            if (valid && sv[i]) store_m4(a.M, a.M_lo, Mr + so[i] + p4, m[i]);
         }
     }
     if (valid && l == 0) {
 #pragma unroll
         for (int i = 0; i < SPL; ++i)
             if (sv[i]) {
-                Mr[KS * dq + sg * SPL + i] = csum[i];                    // coefficient sums ride after the slices
+                store_m1(a.M, a.M_lo, Mr + KS * dq + sg * SPL + i, csum[i]);   // coefficient sums ride after the slices
                 a.crec[(size_t)u * RS + sg * SPL + i] = as[i];
             }
         if (sg == 0) {
             a.crec[(size_t)u * RS + KS] = tail ? 0.f : 1.f;              // anchor role: e1 when the tail is corrupted
-            for (int n = KS * dq + KS; n < a.Np; ++n) Mr[n] = 0.f;
+            for (int n = KS * dq + KS; n < a.Np; ++n) store_m1(a.M, a.M_lo, Mr + n, 0.f);
         }
     }
     // ---- tile partials, fixed order: lanes, then warps
@@ -1628,14 +1643,15 @@ void ntn_launch_gemm_dw_simt(ntn_handle* h, cudaStream_t st) {
 void ntn_launch_score(ntn_handle* h, const float* theta) {
     const NtnDims& dm = h->dm;
     if (h->b.ntiles == 0) return;
-    ScoreArgs a{theta, h->E, h->b.T, h->b.M, h->b.acoef, h->b.ccoef, h->b.GV, h->b.Nu, h->b.st_rel, h->b.st_u0, h->b.st_n,
+    float* const m_lo = h->b.m_split ? h->b.M_lo : nullptr;
+    ScoreArgs a{theta, h->E, h->b.T, h->b.M, m_lo, h->b.acoef, h->b.ccoef, h->b.GV, h->b.Nu, h->b.st_rel, h->b.st_u0, h->b.st_n,
                 h->b.u_e1, h->b.u_e2, h->b.c_off, h->b.c_e3, h->side, h->b.tp_cost, h->b.tp_nact, h->b.tp_dU,
                 dm.d, dm.dq, dm.Kp, dm.Np, dm.oU};
     int ch = cdiv(dm.dq / 4, 32);
     const bool tanh_act = h->cfg.activation == NTN_ACT_TANH;
     if (!h->b.use_gv) {
         // default: lane-per-(triple, slice) kernel writing packed coefficient records (tiles of ntn_score2_rows(k) triples)
-        Score2Args s2{theta, h->E, h->b.T, h->b.M, h->b.crec, h->b.Nu, h->b.RS, h->b.st_rel, h->b.st_u0, h->b.st_n,
+        Score2Args s2{theta, h->E, h->b.T, h->b.M, m_lo, h->b.crec, h->b.Nu, h->b.RS, h->b.st_rel, h->b.st_u0, h->b.st_n,
                       h->b.u_e1, h->b.u_e2, h->b.c_off, h->b.c_e3, h->side, h->b.tp_cost, h->b.tp_nact, h->b.tp_dU,
                       dm.d, dm.dq, dm.Kp, dm.Np, dm.oU};
 #define SC2_LAUNCH(KSv, ACTv, DQv)                                                                                       \
