@@ -149,7 +149,8 @@ int ntn_last_cost(ntn_handle* h, double* cost, int64_t* n_active);   /* synchron
  * data-parallel host all-reduce the scalars on the device together with the gradient. */
 double* ntn_result_dev(ntn_handle* h);
 /* Data-parallel hosts: with on != 0 every ntn_eval_dev also writes 4 floats after the gradient, at
- * d_grad[ntn_internal_dimension() .. +4) = {cost_hi, cost_lo, n_active >> 12, n_active & 4095} (exact float pairs),
+ * d_grad[ntn_internal_dimension() .. +4) = {cost_hi, cost_lo, n_active >> 12, n_active & 4095} (float pairs: exact on one
+ * rank; after the FP32 sum over G ranks the count is still exact and the cost is good to ~1e-7 relative),
  * so ONE sum all-reduce of Pint+4 floats carries the gradient and the scalars.  d_grad must then have Pint+4 floats. */
 int ntn_set_grad_tail(ntn_handle* h, int on);
 /* Data-parallel hosts, gradient exchange INSIDE the evaluation (csrc/exchange.cu; NTN.java:411-430 is linear, so the

@@ -1491,7 +1491,8 @@ __global__ void __launch_bounds__(1024) k_final_reduce(const double* __restrict_
         out[1] = s_b[0];
         out[2] = s_a[0] * inv_B;       // data term alone
         out[3] = s_c[0];               // sum theta^2
-        if (tail) {                    // {cost, n_active} as exact float pairs after the gradient: one collective covers all
+        if (tail) {                    // {cost, n_active} as float pairs after the gradient (exact per rank; the count stays exact under the FP32
+                                       // sum over ranks, the cost is then good to ~1e-7 relative): one collective covers all
             const float chi = (float)out[0];
             tail[0] = chi; tail[1] = (float)(out[0] - (double)chi);
             const long long na = (long long)s_b[0];

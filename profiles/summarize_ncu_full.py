@@ -13,7 +13,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
            "launch__grid_size", "launch__waves_per_multiprocessor", "smsp__issue_active.avg.pct_of_peak_sustained_active",
            "lts__t_sector_hit_rate.pct"]
-PHASE = [("k_tc_w_prep", "w_prep"), ("k_w_prep", "w_prep"), ("k_entity_build", "entity_build"), ("k_tc_gemm<0", "gemm_fwd"),
+PHASE = [("k_tc_w_prep", "w_prep"), ("k_tc_w_tiles", "w_prep"), ("k_tc_w_border", "w_prep"), ("k_tc_anchor_rows", "gemm_fwd"), ("k_w_prep", "w_prep"), ("k_entity_build", "entity_build"), ("k_tc_gemm<0", "gemm_fwd"),
          ("k_gemm_fwd", "gemm_fwd"), ("k_score", "score"), ("k_tc_gemm<1", "gemm_dw"), ("k_gemm_dw", "gemm_dw"),
          ("k_tc_gemm<2", "gemm_ge"), ("k_gemm_ge", "gemm_ge"), ("k_entity_pull", "entity_pull"), ("k_word", "word_pull"),
          ("k_finalize", "finalize"), ("k_final_reduce", "finalize")]
@@ -24,7 +24,7 @@ hdr, units = rows[0], rows[1]
 col = {n: i for i, n in enumerate(hdr)}
 # keep the last COMPLETE evaluation of the capture: from a weight-prep launch up to (not including) the next one
 names = [r[col["Kernel Name"]] for r in rows[2:]]
-starts = [i for i, n in enumerate(names) if "w_prep" in n]
+starts = [i for i, n in enumerate(names) if "w_prep" in n or "k_tc_w_tiles" in n]
 if len(starts) >= 2:
     rows = rows[:2] + rows[2 + starts[-2]: 2 + starts[-1]]
 traffic = {}

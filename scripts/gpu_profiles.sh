@@ -7,7 +7,7 @@ $CMD > gpurun_out/plain_r2.log 2>&1 || { echo "plain run failed"; tail -5 gpurun
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench_steps3.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"
 # one evaluation of every kernel with the full set (skip the set-up and warm-up launches: capture a window late in the run)
-ncu --set full --import-source on --clock-control none -k regex:"k_" -s 150 -c 60 -o gpurun_out/prof_r2_full -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:"k_" -s 150 -c 24 -o gpurun_out/prof_r2_full -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full set rc=$?"
 python scripts/tc_timeline.py > gpurun_out/r2_tc_timeline.txt 2>&1; echo "tc timeline rc=$?"
 python scripts/graph_timeline.py c3 > gpurun_out/r2_graph_timeline.txt 2>&1; echo "graph timeline rc=$?"

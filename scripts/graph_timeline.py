@@ -28,7 +28,8 @@ for i in range(30):
     if i >= 10:
         acc.append(h.debug_fetch("graph_timeline").copy())
 t = np.median(np.stack(acc), 0).reshape(-1, 2)
-names = [h.lib.ntn_phase_name(i).decode() for i in range(len(t))]
+names = [h.lib.ntn_phase_name(i).decode() or f"exchange_{i - 9}" for i in range(len(t))]
 print(cfg, "graph replay timeline (us, median of 20 evaluations; begin -> end, duration)")
 for n, (b, e) in sorted(zip(names, t), key=lambda x: x[1][0]):
-    print(f"  {n:14s} {b:8.1f} -> {e:8.1f}   {e - b:7.1f}")
+    if b >= 0:
+        print(f"  {n:14s} {b:8.1f} -> {e:8.1f}   {e - b:7.1f}")
