@@ -257,6 +257,9 @@ int ntn_host_generate_batch(const int32_t* train, int64_t ntrain, int32_t batch,
 int ntn_host_collections_shuffle(int64_t seed, int32_t n, int32_t* perm);
 /* The invariant division of the flat thread index used by the gather kernels (q[i] = n[i] / d for every 32-bit n). */
 int ntn_host_fastdiv(uint32_t d, int64_t count, const uint32_t* n, uint32_t* q);
+/* chunk layout of the word pull (data-parallel exchange): out[4c..4c+3] = {first word, words, first partial slot, blocks};
+ * returns the total number of regulariser-partial slots (> 0), or a negative NTN_E* code */
+int ntn_host_word_chunks(int32_t Nw, int32_t dq, int32_t C, int32_t* out);
 /* The staging conversions of the host-buffer entry points (double[] theta -> float, float gradient -> double[];
  * Util.java:49-55 rounding), exposed so that the CPU tests can check them on unaligned and ragged ranges. */
 int ntn_host_convert_f64_f32(const double* src, float* dst, int64_t n);

@@ -100,6 +100,7 @@ SYMBOLS = {
                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ntn_host_collections_shuffle": (C.c_int, [C.c_int64, C.c_int32, _P]),
     "ntn_host_fastdiv": (C.c_int, [C.c_uint32, C.c_int64, _P, _P]),
+    "ntn_host_word_chunks": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P]),
     "ntn_host_convert_f64_f32": (C.c_int, [_P, _P, C.c_int64]),
     "ntn_host_convert_f32_f64": (C.c_int, [_P, _P, C.c_int64]),
     "ntn_host_generate_batch": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),

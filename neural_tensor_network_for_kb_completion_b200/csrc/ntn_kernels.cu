@@ -1761,6 +1761,7 @@ void ntn_launch_entity_pull(ntn_handle* h) {
 // words [w0, w0 + wn), one thread per (word pair, float4 chunk), and owns `blocks` regulariser-partial slots from block_off.
 // (Equal chunks: an exchange kernel costs ~10 us of launch + flag barrier before it moves a byte, so the schedule that
 // ends first is the one with the fewest kernels that still overlaps half of the bytes -- two chunks, measured.)
+int ntn_word_blocks_total(const NtnDims& dm, int C);
 void ntn_word_chunk(const NtnDims& dm, int c, int C, int* w0, int* wn, int* block_off, int* blocks) {
     const int cpr = dm.dq / 4;
     int64_t bound[NTN_MAX_WORD_CHUNKS + 1];
@@ -1771,6 +1772,16 @@ void ntn_word_chunk(const NtnDims& dm, int c, int C, int* w0, int* wn, int* bloc
     *w0 = (int)bound[c]; *wn = (int)(bound[c + 1] - bound[c]);
     *block_off = off; *blocks = cdiv(((int64_t)(*wn + 1) / 2) * cpr, 256);
 }
+// test hook (CPU): the chunk layout for Nw words of dq floats in C chunks -> out[4 c .. 4 c + 3] = {first word, words,
+// first regulariser-partial slot, blocks}; returns the total number of slots
+extern "C" int ntn_host_word_chunks(int32_t Nw, int32_t dq, int32_t C, int32_t* out) {
+    if (Nw < 1 || dq < 4 || (dq & 3) || C < 1 || C > NTN_MAX_WORD_CHUNKS || !out) return NTN_EINVAL;
+    NtnDims dm{};
+    dm.Nw = Nw; dm.dq = dq;
+    for (int c = 0; c < C; ++c) ntn_word_chunk(dm, c, C, out + 4 * c, out + 4 * c + 1, out + 4 * c + 2, out + 4 * c + 3);
+    return ntn_word_blocks_total(dm, C);
+}
+
 int ntn_word_blocks_total(const NtnDims& dm, int C) {
     int w0, wn, off, nb;
     ntn_word_chunk(dm, C - 1, C, &w0, &wn, &off, &nb);

@@ -2,6 +2,7 @@
 bit for bit: java.util.Random stream, entity-name parsing -> forward/backward word maps (with the reference's
 malformed-name quirks), batch-job order and corrupt indices.  No GPU needed."""
 import ctypes as C
+C_ = C
 import os
 
 import numpy as np
@@ -186,3 +187,19 @@ def test_native_corrupt_side_drawer_continues_the_seeded_stream(lib):
     # the Python mirror adopts the advanced state and stays on the same stream
     pr.s = int(st[0])
     assert pr.nextDouble() == ref.next_double()
+
+
+@pytest.mark.parametrize("Nw,dq,C", [(67447, 100, 1), (67447, 100, 2), (67447, 100, 4), (420, 20, 3), (5, 8, 4), (500000, 256, 8)])
+def test_word_pull_chunk_layout_covers_every_word_once(lib, Nw, dq, C):
+    """The data-parallel exchange cuts the word pull into chunks (csrc/ntn_kernels.cu: ntn_word_chunk): contiguous, whole
+    words, every word in exactly one chunk, block-partial slots back to back (the regulariser sum reads them all)."""
+    out = np.zeros(4 * C, np.int32)
+    total = lib.ntn_host_word_chunks(Nw, dq, C, out.ctypes.data_as(C_.c_void_p))
+    ch = out.reshape(C, 4)
+    assert ch[0, 0] == 0 and ch[:, 1].sum() == Nw
+    assert np.array_equal(ch[1:, 0], np.cumsum(ch[:-1, 1]))
+    assert np.array_equal(ch[:, 2], np.r_[0, np.cumsum(ch[:-1, 3])])
+    assert total == ch[:, 3].sum()
+    cpr = dq // 4
+    assert np.array_equal(ch[:, 3], -(-((ch[:, 1] + 1) // 2 * cpr) // 256))      # one thread per (word pair, float4 chunk)
+    assert ch[:, 1].max() - ch[:, 1].min() <= 1 or C > Nw
