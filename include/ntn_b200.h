@@ -169,6 +169,15 @@ int ntn_exchange_bind(ntn_handle* h, int32_t rank, int32_t world, const uint64_t
                       const uint64_t* signal_pad_ptrs, uint64_t multicast_ptr, int64_t numel,
                       const uint64_t* scratch_ptrs, int64_t scratch_numel);
 int64_t ntn_exchange_scratch_numel(const ntn_handle* h);
+/* Entity-gradient exchange (after ntn_exchange_bind): bind a symmetric allocation of >= Ne * ceil4(d) floats as THE entity-
+ * gradient buffer of the handle (+ a scratch of >= ntn_exchange_ge_scratch_numel() floats in push mode).  The sum over
+ * the ranks is then taken on the entity gradient (Util.java:74-98's product, NTN.java:372,388) while the entity pull is
+ * still running; the word pull that follows (NTN.java:411-430, linear in the entity gradient) yields the full-batch word
+ * gradient on every rank and only the W/V/b/U blocks and the tail are exchanged after it.  Same volume over NVLink as
+ * exchanging the word gradient, started one kernel earlier. */
+int ntn_exchange_bind_ge(ntn_handle* h, const uint64_t* buffer_ptrs, const uint64_t* signal_pad_ptrs, uint64_t multicast_ptr,
+                         int64_t numel, const uint64_t* scratch_ptrs, int64_t scratch_numel);
+int64_t ntn_exchange_ge_scratch_numel(const ntn_handle* h);
 int ntn_exchange_unbind(ntn_handle* h);
 int ntn_exchange_check(ntn_handle* h);
 /* measurement hook: iters back-to-back all-reduce kernels over floats [off, off+n) of a bound buffer (same call on every rank) */

@@ -73,6 +73,8 @@ SYMBOLS = {
     "ntn_set_grad_tail": (C.c_int, [_P, C.c_int]),
     "ntn_exchange_bind": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_uint64, C.c_int64, _P, C.c_int64]),
     "ntn_exchange_scratch_numel": (C.c_int64, [_P]),
+    "ntn_exchange_bind_ge": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int64, _P, C.c_int64]),
+    "ntn_exchange_ge_scratch_numel": (C.c_int64, [_P]),
     "ntn_exchange_unbind": (C.c_int, [_P]),
     "ntn_exchange_check": (C.c_int, [_P]),
     "ntn_exchange_probe": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
@@ -255,6 +257,17 @@ class Handle:
         self._ck(self.lib.ntn_exchange_bind(self.h, int(rank), int(world), _ptr(bp), _ptr(sp), int(multicast_ptr), int(numel),
                                             _ptr(cp), int(scratch_numel)))
         return True
+
+    def exchange_bind_ge(self, buffer_ptrs, signal_pad_ptrs, multicast_ptr, numel, scratch_ptrs=None, scratch_numel=0):
+        """Bind a symmetric entity-gradient buffer (include/ntn_b200.h: ntn_exchange_bind_ge)."""
+        bp, sp = np.asarray(buffer_ptrs, np.uint64), np.asarray(signal_pad_ptrs, np.uint64)
+        cp = None if scratch_ptrs is None else np.asarray(scratch_ptrs, np.uint64)
+        self._ck(self.lib.ntn_exchange_bind_ge(self.h, _ptr(bp), _ptr(sp), int(multicast_ptr), int(numel), _ptr(cp), int(scratch_numel)))
+        return True
+
+    @property
+    def exchange_ge_scratch_numel(self):
+        return int(self.lib.ntn_exchange_ge_scratch_numel(self.h))
 
     @property
     def exchange_scratch_numel(self):

@@ -393,10 +393,57 @@ extern "C" int ntn_exchange_bind(ntn_handle* h, int32_t rank, int32_t world, con
     return NTN_OK;
 }
 
+// Entity-gradient exchange: bind a symmetric allocation of >= Ne * dq floats (and its scratch of
+// >= ntn_exchange_ge_scratch_numel() floats) as THE entity-gradient buffer of this handle.  Evaluations into a bound
+// gradient buffer then sum gE over the ranks while the entity pull is running (chunks of entity rows, the pull kernel
+// pushes the groups another rank owns) and the word pull that follows produces the full-batch word gradient everywhere;
+// only the W/V/b/U blocks and the tail are exchanged after it.  Needs a prior ntn_exchange_bind (rank, world, mode).
+extern "C" int64_t ntn_exchange_ge_scratch_numel(const ntn_handle* h) {
+    return h ? (int64_t)h->dm.Ne * h->dm.dq + (int64_t)NTN_XCHG_RANGE_PAD * (NTN_MAX_WORD_CHUNKS + 1) : -1;
+}
+extern "C" int ntn_exchange_bind_ge(ntn_handle* h, const uint64_t* buffer_ptrs, const uint64_t* signal_pad_ptrs,
+                                    uint64_t multicast_ptr, int64_t numel, const uint64_t* scratch_ptrs, int64_t scratch_numel) {
+    if (!h) return NTN_EINVAL;
+    if (h->xb.empty()) { h->err = "exchange: bind a gradient buffer first (ntn_exchange_bind)"; return NTN_ESTATE; }
+    if (!buffer_ptrs || !signal_pad_ptrs) { h->err = "exchange: null pointer table"; return NTN_EINVAL; }
+    if (numel < (int64_t)h->dm.Ne * h->dm.dq) { h->err = "exchange: gE buffer shorter than Ne * dq"; return NTN_EINVAL; }
+    const bool want_scratch = h->x_mode == 2;
+    if (want_scratch && (!scratch_ptrs || scratch_numel < ntn_exchange_ge_scratch_numel(h))) {
+        h->err = "exchange: gE scratch missing or too short (ntn_exchange_ge_scratch_numel)"; return NTN_EINVAL;
+    }
+    if (h->x_mode == 1 && !multicast_ptr) { h->err = "exchange: multimem mode needs the multicast alias of the gE buffer"; return NTN_EINVAL; }
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    ExchangeBinding b;
+    for (int r = 0; r < h->x_world; ++r) {
+        if (!buffer_ptrs[r] || !signal_pad_ptrs[r] || (buffer_ptrs[r] & 15)) { h->err = "exchange: null or misaligned peer pointer"; return NTN_EINVAL; }
+        b.peer[r] = reinterpret_cast<float*>(buffer_ptrs[r]);
+        b.sig[r] = reinterpret_cast<uint32_t*>(signal_pad_ptrs[r]);
+        if (want_scratch) {
+            if (!scratch_ptrs[r] || (scratch_ptrs[r] & 15)) { h->err = "exchange: null or misaligned scratch pointer"; return NTN_EINVAL; }
+            b.scratch[r] = reinterpret_cast<float*>(scratch_ptrs[r]);
+        }
+    }
+    b.local = b.peer[h->x_rank];
+    b.mc = reinterpret_cast<float*>(multicast_ptr);
+    b.numel = numel;
+    b.scratch_numel = want_scratch ? scratch_numel : 0;
+    b.epoch = b.sig[h->x_rank] + NTN_XCHG_SIG_WORD0 - 2;
+    if (!h->gE_own) h->gE_own = h->gE;
+    h->gE = b.local;
+    h->xge = b;
+    h->xge_set = true;
+    if (const char* e = getenv("NTN_EXCHANGE_GE_CHUNKS")) h->xge_chunks = std::max(1, std::min(NTN_MAX_WORD_CHUNKS, atoi(e)));
+    ntn_drop_graphs(h);
+    return NTN_OK;
+}
+
 extern "C" int ntn_exchange_unbind(ntn_handle* h) {
     if (!h) return NTN_EINVAL;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->gE_own) { h->gE = h->gE_own; h->gE_own = nullptr; }
+    h->xge_set = false;
     h->xb.clear();
     ntn_drop_graphs(h);
     return NTN_OK;

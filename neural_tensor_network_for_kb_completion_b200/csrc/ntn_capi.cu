@@ -211,6 +211,7 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     for (cudaEvent_t e : {h->ev_f0, h->ev_j0, h->ev_f1, h->ev_j1}) if (e) cudaEventDestroy(e);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
+    if (h->gE_own) { h->gE = h->gE_own; h->gE_own = nullptr; }      // (a bound symmetric gE belongs to the caller)
     if (h->stream4) cudaStreamDestroy(h->stream4);
     for (int i = 0; i < NTN_MAX_WORD_CHUNKS; ++i) if (h->ev_x[i]) cudaEventDestroy(h->ev_x[i]);
     if (h->ev_xdone) cudaEventDestroy(h->ev_xdone);
@@ -685,7 +686,12 @@ static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_gr
     // data-parallel: when the gradient buffer is a bound symmetric allocation (and carries the {cost, n_active} tail) the
     // all-reduce over the ranks runs inside the evaluation, chunk by chunk beside the word pull (exchange.cu)
     const ExchangeBinding* xb = h->grad_tail ? ntn_find_binding(h, d_grad) : nullptr;
-    h->word_chunks = xb ? h->x_chunks : 1;
+    // ... and when gE itself is bound (ntn_exchange_bind_ge) the sum over the ranks is taken one stage earlier, on the entity
+    // gradient, while the entity pull is running: the word pull then produces the full-batch word gradient on every rank
+    // and only the small blocks and the tail are exchanged after it
+    const ExchangeBinding* xge = (xb && h->xge_set) ? &h->xge : nullptr;
+    h->ge_mode = xge != nullptr;
+    h->word_chunks = (xb && !xge) ? h->x_chunks : 1;
     h->x_stamp = 0;
     if (h->d_stamps) cudaMemsetAsync(h->d_stamps, 0, 2 * NTN_STAMP_SLOTS * sizeof(unsigned long long), h->stream);
     // ---- fork: weight preparation runs beside the entity build
@@ -714,8 +720,9 @@ static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_gr
     begin(P_GE, s0);
     if (tc) { if ((rc = ntn_tc_gemm_ge(h))) return rc; } else ntn_launch_gemm_ge_simt(h);     // :352-388
     end(P_GE, s0);
-    begin(P_EP, s0); ntn_launch_entity_pull(h); end(P_EP, s0);                                // Util.java:74-98
-    begin(P_WPULL, s0); ntn_launch_word_pull(h, d_theta, d_grad, xb); end(P_WPULL, s0);       // :411-430
+    begin(P_EP, s0); ntn_launch_entity_pull(h, xge); end(P_EP, s0);                           // Util.java:74-98
+    if (xge) CK(cudaStreamWaitEvent(s0, h->ev_xdone, 0));                                     // gE summed over the ranks, everywhere
+    begin(P_WPULL, s0); ntn_launch_word_pull(h, d_theta, d_grad, xge ? nullptr : xb); end(P_WPULL, s0);   // :411-430
     CK(cudaStreamWaitEvent(s0, h->ev_j1, 0));
     ntn_launch_final_reduce(h, h->grad_tail ? d_grad + h->dm.Pint : nullptr);                 // :430,437
     if (xb) {
@@ -727,7 +734,8 @@ static int enqueue_eval_kernels(ntn_handle* h, const float* d_theta, float* d_gr
         const bool pushed = h->x_mode == 2;
         XRange r0{dm.oWVint + (int64_t)w0 * dm.dq, (int64_t)wn * dm.dq, h->word_chunks, pushed};
         XRange r1{0, dm.oWVint, 0, false}, r2{dm.Pint, 4, h->word_chunks + 1, false};
-        if (h->word_chunks > 1) CK(cudaStreamWaitEvent(s0, h->ev_xdone, 0));
+        if (xge) r0 = XRange{0, 0, 0, false};                    // the word block is already the full-batch one on every rank
+        else if (h->word_chunks > 1) CK(cudaStreamWaitEvent(s0, h->ev_xdone, 0));
         ntn_launch_exchange(h, xb, r0, r1, r2, true, s0);
     }
     CK(cudaMemcpyAsync(h->h_out, h->d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, s0));

@@ -229,6 +229,14 @@ struct ntn_handle {
     int x_stamp = 0;                              // exchange kernels launched in the evaluation being enqueued (timeline slots)
     int x_chunks = 2, x_blocks = 64, x_mode = 0;   // word-pull chunks, blocks per exchange kernel, 0: peer loads/stores, 1: multimem, 2: push
     std::vector<ExchangeBinding> xb;
+    // entity-gradient exchange (ntn_exchange_bind_ge): gE itself is a symmetric allocation and is summed over the ranks
+    // while the entity pull is still running; the word pull then works on the full-batch gE on every rank and only the
+    // small W/V/b/U blocks and the tail are left to exchange after it
+    ExchangeBinding xge;
+    bool xge_set = false;
+    float* gE_own = nullptr;                      // the handle's own gE while a symmetric one is bound
+    int xge_chunks = 2;
+    bool ge_mode = false;                         // the evaluation being enqueued exchanges gE (the word block then takes the full lambda)
     cudaStream_t stream4 = nullptr;               // exchange of the finished chunks, beside the word pull (highest priority)
     cudaEvent_t ev_x[NTN_MAX_WORD_CHUNKS] = {}, ev_xdone = nullptr;
     unsigned* d_xerr = nullptr;                   // set when a bounded flag wait expired (results invalid)
@@ -263,7 +271,7 @@ int ntn_score2_rows(int k);   // tile height of the default score kernel
 void ntn_launch_gemm_dw_simt(ntn_handle* h, cudaStream_t st);
 void ntn_launch_gemm_ge_simt(ntn_handle* h);
 void ntn_stamp(ntn_handle* h, int slot, cudaStream_t st);   // NTN_GRAPH_TIMELINE: store %globaltimer into stamp slot (no-op otherwise)
-void ntn_launch_entity_pull(ntn_handle* h);
+void ntn_launch_entity_pull(ntn_handle* h, const ExchangeBinding* xge);
 int ntn_pull_ranges(const ntn_handle* h);
 void ntn_launch_pull_ranges(ntn_handle* h);
 void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad, const ExchangeBinding* xb);

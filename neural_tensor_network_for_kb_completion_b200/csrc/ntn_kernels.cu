@@ -51,6 +51,23 @@ __device__ __forceinline__ void store_m1(float* Mhi, float* Mlo, size_t off, flo
     if (Mlo) { const float hi = tf32_round(v); Mhi[off] = hi; Mlo[off] = tf32_round(v - hi); }
     else Mhi[off] = v;
 }
+// store of one float4 group of an entity-gradient row; PUSH (data-parallel entity-gradient exchange, exchange.cu): a group
+// that another rank owns also goes straight into that rank's scratch -- a posted store over NVLink from the kernel that
+// produces it
+template <bool PUSH>
+__device__ __forceinline__ void ge_store(float* gE, const XPushRange& xp, size_t o, const float4& v) {
+    *reinterpret_cast<float4*>(gE + o) = v;
+    if (PUSH) {
+        const unsigned rel4 = (unsigned)((o - (size_t)xp.off) >> 2);
+        const unsigned owner = fd_div(rel4, FastDiv{xp.per4, xp.per_m, xp.per_s});
+        if ((int)owner != xp.rank) {
+            float* dst = xp.dst[0];
+#pragma unroll
+            for (int s = 1; s < NTN_MAX_PEERS; ++s) dst = (owner == (unsigned)s) ? xp.dst[s] : dst;
+            *reinterpret_cast<float4*>(dst + 4 * (size_t)(rel4 - owner * xp.per4)) = v;
+        }
+    }
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
@@ -925,11 +942,12 @@ __global__ void __launch_bounds__(256) k_entity_pull_hub(PullArgs a) {
     *reinterpret_cast<float4*>(a.eh_part + (size_t)seg * a.dq + c * 4) = acc;
 }
 
-template <int KS, bool GVR>
-__global__ void __launch_bounds__(256, (KS <= 4) ? 6 : 2) k_entity_pull(PullArgs a) {
+template <int KS, bool GVR, bool PUSH>
+__global__ void __launch_bounds__(256, (KS <= 4) ? 6 : 2) k_entity_pull(PullArgs a, XPushRange xp, int row0, int nrows) {
     const unsigned gid = flat_index();
-    const int n = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)n * a.fd.d);
-    if (n >= a.Ne) return;
+    const int nl = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)nl * a.fd.d);
+    if (nl >= nrows) return;
+    const int n = row0 + nl;                                         // entities [row0, row0 + nrows): all, or one exchange chunk
     float4 acc;
     int nseg = a.eh_count ? a.eh_count[n] : 0;
     if (nseg == 0) {
@@ -946,7 +964,7 @@ __global__ void __launch_bounds__(256, (KS <= 4) ? 6 : 2) k_entity_pull(PullArgs
             for (int i = 0; i < 4; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
         }
     }
-    *reinterpret_cast<float4*>(a.gE + (size_t)n * a.dq + c * 4) = acc;
+    ge_store<PUSH>(a.gE, xp, (size_t)n * a.dq + c * 4, acc);
 }
 
 // ==========================================================================================
@@ -1018,12 +1036,13 @@ __global__ void __launch_bounds__(256) k_entity_pull2_hub(Pull2Args a) {
     *reinterpret_cast<float4*>(a.eh_part + (size_t)seg * a.dq + c * 4) = acc;
 }
 
-template <int KS>
-__global__ void __launch_bounds__(256, (KS <= 4) ? 4 : 2) k_entity_pull2(Pull2Args a) {
+template <int KS, bool PUSH>
+__global__ void __launch_bounds__(256, (KS <= 4) ? 4 : 2) k_entity_pull2(Pull2Args a, XPushRange xp, int row0, int nrows) {
     const unsigned gid = flat_index();
     const int slot = (int)fd_div(gid, a.fd), c = (int)(gid - (unsigned)slot * a.fd.d);
-    if (slot >= a.Ne) return;
-    const int n = __ldg(a.order + slot);
+    if (slot >= nrows) return;
+    // single GPU: slots in descending order of degree (a.order); exchange chunks: entities [row0, row0 + nrows) as they come
+    const int n = a.order ? __ldg(a.order + slot) : row0 + slot;
     float4 acc;
     const int nseg = a.eh_count ? a.eh_count[n] : 0;
     if (nseg == 0) {
@@ -1040,7 +1059,7 @@ __global__ void __launch_bounds__(256, (KS <= 4) ? 4 : 2) k_entity_pull2(Pull2Ar
             for (int i = 0; i < 4; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
         }
     }
-    *reinterpret_cast<float4*>(a.gE + (size_t)n * a.dq + c * 4) = acc;
+    ge_store<PUSH>(a.gE, xp, (size_t)n * a.dq + c * 4, acc);
 }
 
 // ==========================================================================================
@@ -1699,62 +1718,77 @@ void ntn_launch_pull_ranges(ntn_handle* h) {
     k_pull_ranges<<<cdiv(h->dm.Ne, 256), 256, 0, h->stream>>>(b.inc_off, b.n_ent_hub_segs ? b.eh_count : nullptr, h->dm.Ne, b.pull_rng);
 }
 
-void ntn_launch_entity_pull(ntn_handle* h) {
+// Entity pull.  xge != null (data parallel, entity-gradient exchange): the entities are cut into contiguous row chunks;
+// the kernel of a chunk also stores every group another rank owns into that rank's scratch, and the chunk's all-reduce
+// runs on the exchange stream while the next chunk is pulled; the caller waits for ev_xdone before it reads gE.
+void ntn_launch_entity_pull(ntn_handle* h, const ExchangeBinding* xge) {
     const NtnDims& dm = h->dm;
     const DeviceBatch& b = h->b;
+    const int cpr = dm.dq / 4;
+    const int C = xge ? std::max(1, std::min(NTN_MAX_WORD_CHUNKS, h->xge_chunks)) : 1;
     // (the warp-per-range kernel is the opt-in variant: at 20,000 x 10 it measured 48.7 us against 42.3 us of the
     //  thread-per-(entity, chunk) kernel -- 83 warp instructions per incident and 26 % occupancy, ncu profiles/r2_*)
     static const int pull_variant = [] { const char* e = getenv("NTN_PULL"); return e ? atoi(e) : 2; }();
-    if (!b.use_gv && pull_variant == 3 && dm.dq <= 256) {
+    if (!xge && !b.use_gv && pull_variant == 3 && dm.dq <= 256) {
         Pull2Args a2{b.T, b.crec, b.GA, b.inc, b.inc_off, b.ent_order, h->gE,
                      b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
                      b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.RS, b.n_ent_hub_segs,
                      make_fastdiv((unsigned)(dm.dq / 4))};
         Pull3Args a{b.T, b.crec, b.GA, b.inc, b.inc_off, b.pull_rng, h->gE, b.n_ent_hub_segs ? b.eh_first : nullptr,
                     b.n_ent_hub_segs ? b.eh_count : nullptr, b.eh_part, ntn_pull_ranges(h), dm.dq, dm.Kp, dm.Np, b.RS};
-        const int cpr3 = dm.dq / 4;
         const int blocks = cdiv((int64_t)a.nranges * 32, 128);
         DISPATCH_KS(dm.k, {
             if (b.n_ent_hub_segs) {
-                k_entity_pull2_hub<KS><<<cdiv((int64_t)b.n_ent_hub_segs * cpr3, 256), 256, 0, h->stream>>>(a2);
+                k_entity_pull2_hub<KS><<<cdiv((int64_t)b.n_ent_hub_segs * cpr, 256), 256, 0, h->stream>>>(a2);
                 h->launches++;
             }
-            if (cpr3 <= 32) k_entity_pull3<KS, 1><<<blocks, 128, 0, h->stream>>>(a);
+            if (cpr <= 32) k_entity_pull3<KS, 1><<<blocks, 128, 0, h->stream>>>(a);
             else k_entity_pull3<KS, 2><<<blocks, 128, 0, h->stream>>>(a);
         });
         h->launches++;
         return;
     }
-    if (!b.use_gv) {
-        Pull2Args a{b.T, b.crec, b.GA, b.inc, b.inc_off, b.ent_order, h->gE,
-                    b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
-                    b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.RS, b.n_ent_hub_segs,
-                    make_fastdiv((unsigned)(dm.dq / 4))};
-        const int cpr2 = dm.dq / 4;
+    Pull2Args a2{b.T, b.crec, b.GA, b.inc, b.inc_off, xge ? nullptr : b.ent_order, h->gE,
+                 b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
+                 b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.RS, b.n_ent_hub_segs,
+                 make_fastdiv((unsigned)cpr)};
+    PullArgs a1{b.T, b.acoef, b.GV, b.GA, b.inc, b.inc_off, h->side, h->gE,
+                b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
+                b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.n_ent_hub_segs, make_fastdiv((unsigned)cpr)};
+    // hub entities: their segments are pre-reduced first (one kernel for all chunks)
+    if (b.n_ent_hub_segs) {
+        const int hb = cdiv((int64_t)b.n_ent_hub_segs * cpr, 256);
         DISPATCH_KS(dm.k, {
-            if (b.n_ent_hub_segs) {
-                k_entity_pull2_hub<KS><<<cdiv((int64_t)b.n_ent_hub_segs * cpr2, 256), 256, 0, h->stream>>>(a);
-                h->launches++;
-            }
-            k_entity_pull2<KS><<<cdiv((int64_t)dm.Ne * cpr2, 256), 256, 0, h->stream>>>(a);
+            if (b.use_gv) k_entity_pull_hub<KS, true><<<hb, 256, 0, h->stream>>>(a1);
+            else k_entity_pull2_hub<KS><<<hb, 256, 0, h->stream>>>(a2);
         });
         h->launches++;
-        return;
     }
-    PullArgs a{b.T, b.acoef, b.GV, b.GA, b.inc, b.inc_off, h->side, h->gE,
-               b.n_ent_hub_segs ? b.eh_first : nullptr, b.n_ent_hub_segs ? b.eh_count : nullptr,
-               b.eh_begin, b.eh_end, b.eh_part, dm.Ne, dm.dq, dm.Kp, dm.Np, b.n_ent_hub_segs, make_fastdiv((unsigned)(dm.dq / 4))};
-    const int cpr = dm.dq / 4;
-    DISPATCH_KS(dm.k, {
-        if (b.n_ent_hub_segs) {
-            if (b.use_gv) k_entity_pull_hub<KS, true><<<cdiv((int64_t)b.n_ent_hub_segs * cpr, 256), 256, 0, h->stream>>>(a);
-            else k_entity_pull_hub<KS, false><<<cdiv((int64_t)b.n_ent_hub_segs * cpr, 256), 256, 0, h->stream>>>(a);
+    for (int c = 0; c < C; ++c) {
+        const int row0 = (int)((int64_t)dm.Ne * c / C), nrows = (int)((int64_t)dm.Ne * (c + 1) / C) - row0;
+        const XPushRange xp = ntn_push_range(h, xge, (int64_t)row0 * dm.dq, (int64_t)nrows * dm.dq, c);
+        const bool push = xp.world != 0;
+        const int nb = cdiv((int64_t)nrows * cpr, 256);
+        if (nb > 0) {
+            DISPATCH_KS(dm.k, {
+                if (b.use_gv) {
+                    if (push) k_entity_pull<KS, true, true><<<nb, 256, 0, h->stream>>>(a1, xp, row0, nrows);
+                    else k_entity_pull<KS, true, false><<<nb, 256, 0, h->stream>>>(a1, xp, row0, nrows);
+                } else {
+                    if (push) k_entity_pull2<KS, true><<<nb, 256, 0, h->stream>>>(a2, xp, row0, nrows);
+                    else k_entity_pull2<KS, false><<<nb, 256, 0, h->stream>>>(a2, xp, row0, nrows);
+                }
+            });
             h->launches++;
         }
-        if (b.use_gv) k_entity_pull<KS, true><<<cdiv((int64_t)dm.Ne * cpr, 256), 256, 0, h->stream>>>(a);
-        else k_entity_pull<KS, false><<<cdiv((int64_t)dm.Ne * cpr, 256), 256, 0, h->stream>>>(a);
-    });
-    h->launches++;
+        if (xge) {
+            cudaEventRecord(h->ev_x[c], h->stream);
+            cudaStreamWaitEvent(h->stream4, h->ev_x[c], 0);
+            const XRange none{0, 0, 0, false};
+            ntn_launch_exchange(h, xge, XRange{(int64_t)row0 * dm.dq, (int64_t)nrows * dm.dq, c, push}, none, none, c + 1 == C, h->stream4);
+        }
+    }
+    if (xge) cudaEventRecord(h->ev_xdone, h->stream4);
 }
 
 // The word pull covers the Nw words in C chunks of whole words (C = 1 unless a gradient exchange is bound): chunk c is
@@ -1794,7 +1828,9 @@ void ntn_launch_word_pull(ntn_handle* h, const float* theta, float* grad, const 
     const int C = h->word_chunks;
     WordArgs a{h->gE, w.len_bwd /* reciprocals */, theta, grad, w.w_off, w.w_ent, w.w_rec, w.wh_first, w.wh_count, w.wh_begin, w.wh_end,
                w.hub_words, w.wh_part, h->reg_part, dm.Nw, dm.d, dm.dq, w.n_hub_segs, w.n_hub_words, ntn_word_blocks_total(dm, C),
-               dm.oWVint, 1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * h->cfg.reg_scale, make_fastdiv((unsigned)(dm.dq / 4))};
+               // (entity-gradient exchange: gE already holds the sum over the ranks, so every rank computes the FULL word
+               //  gradient and nothing adds the word block up afterwards -- it takes lambda undivided)
+               dm.oWVint, 1.0f / (float)h->cfg.batch_divisor, h->cfg.lambda * (h->ge_mode ? 1.0f : h->cfg.reg_scale), make_fastdiv((unsigned)(dm.dq / 4))};
     const int cpr = dm.dq / 4;
     int ch = cdiv(cpr, 32);
     // range ids of an evaluation (their scratch regions, exchange.cu): 0 = the W/V/b/U blocks, 1 + c = word chunk c,

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode", ["push", "p2p"])
+@pytest.mark.parametrize("mode", ["push", "p2p", "push+ge", "p2p+ge"])   # +ge: the sum is taken on the entity gradient
 @pytest.mark.parametrize("G,chunks", [(2, 4), (2, 1), (3, 2), (3, 3)])   # (4 ranks x 5 streams in one process exhaust the hardware queues; G = 4, 8 run under torchrun: scripts/exchange_check.py)
 def test_loopback_exchange_gives_every_rank_the_full_batch_result(G, chunks, mode):
     # (priority streams draw on a smaller pool of hardware queues: the G ranks of this one-process test give theirs up;
@@ -28,7 +28,7 @@ def test_loopback_exchange_gives_every_rank_the_full_batch_result(G, chunks, mod
     env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", NTN_STREAM_PRIORITY="0", CUDA_MODULE_LOADING="EAGER",
                NTN_EXCHANGE_TIMEOUT_MS="30000",      # the ranks of this test capture their graphs one after the other
                NTN_EXCHANGE_CHUNKS=str(chunks),
-               NTN_EXCHANGE_BLOCKS="4", NTN_EXCHANGE=mode)
+               NTN_EXCHANGE_BLOCKS="4", NTN_EXCHANGE=mode.split("+")[0], NTN_EXCHANGE_GE_CHUNKS=str(max(chunks, 1)))
     r = subprocess.run([sys.executable, os.path.abspath(__file__), str(G), mode], env=env, cwd=ROOT, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
@@ -61,9 +61,18 @@ def loopback(G, mode):
         hr = make_handle(p, "theta", reg_scale=1.0 / G)
         hr.set_batch(*shard_columns(*batch, r, G))
         hr.set_grad_tail(True)
+        base = mode.split("+")[0]
         hr.exchange_bind(r, G, [b.data_ptr() for b in bufs], [s.data_ptr() for s in pads], 0, Pint + 4,
-                         [s.data_ptr() for s in scr] if mode == "push" else None, scr[0].numel())
-        assert hr.exchange_mode == mode
+                         [s.data_ptr() for s in scr] if base == "push" else None, scr[0].numel())
+        assert hr.exchange_mode == base
+        if mode.endswith("+ge"):
+            if r == 0:
+                nge = hr.exchange_ge_scratch_numel
+                ges = [torch.full((nge,), float("nan"), dtype=torch.float32, device="cuda") for _ in range(G)]
+                gscr = [torch.full((nge,), float("nan"), dtype=torch.float32, device="cuda") for _ in range(G)]
+                gpads = [torch.zeros(9216 // 4, dtype=torch.int32, device="cuda") for _ in range(G)]
+            hr.exchange_bind_ge([b.data_ptr() for b in ges], [s.data_ptr() for s in gpads], 0, nge,
+                                [s.data_ptr() for s in gscr] if base == "push" else None, nge)
         ranks.append(hr)
     torch.cuda.synchronize()
     for rep in range(3):                                   # flags return to 0: consecutive evaluations reuse them
