@@ -478,6 +478,8 @@ def main():
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     cost, nact = handles[(args.steps - 1) & 1].last_cost()
+    if fused and any(h.exchange_check() for h in handles):
+        raise RuntimeError("gradient exchange: a flag wait expired during the timed region (a rank fell > 2 s behind); results invalid")
     if dist is not None:
         cost, nact = _capi.Handle.unpack_tail(grads[(args.steps - 1) & 1][Pint:Pint + 4].cpu().numpy())
     # per-kernel-group times: the same steps again with CUDA events bracketing every group on the stream it

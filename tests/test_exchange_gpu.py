@@ -19,8 +19,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode", ["push", "p2p", "push+ge", "p2p+ge"])   # +ge: the sum is taken on the entity gradient
-@pytest.mark.parametrize("G,chunks", [(2, 4), (2, 1), (3, 2), (3, 3)])   # (4 ranks x 5 streams in one process exhaust the hardware queues; G = 4, 8 run under torchrun: scripts/exchange_check.py)
+# (G, word-pull / entity-pull chunks, variant); "+ge": the sum over the ranks is taken on the entity gradient.  G = 4, 8:
+# 4 ranks x 5 streams in one process exhaust the hardware queues -- those run under torchrun (scripts/exchange_check.py)
+@pytest.mark.parametrize("G,chunks,mode", [(2, 4, "push"), (2, 1, "push"), (3, 2, "push"), (3, 3, "push"), (2, 4, "p2p"),
+                                           (3, 2, "p2p"), (2, 2, "push+ge"), (3, 3, "push+ge"), (2, 1, "p2p+ge")])
 def test_loopback_exchange_gives_every_rank_the_full_batch_result(G, chunks, mode):
     # (priority streams draw on a smaller pool of hardware queues: the G ranks of this one-process test give theirs up;
     # eager module loading: a kernel first used by a later rank must not be loaded -- a context-wide synchronisation --
