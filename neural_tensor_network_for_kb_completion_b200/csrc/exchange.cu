@@ -5,9 +5,10 @@
 //
 // The buffers are symmetric allocations (same size on every rank, every rank's copy mapped into every process; torch
 // symmetric memory does the allocation and the handle exchange -- plumbing).  The kernels here are the data plane:
-//   * the word pull is cut into chunks (ntn_word_chunk); as soon as chunk c is final in this rank's buffer, k_exchange
-//     all-reduces it on a side stream while the pull goes on with chunk c + 1; the last chunk and the {cost, n_active}
-//     tail follow the final reduce.  Only the last, smallest exchange is not overlapped;
+//   * the word pull is cut into chunks (ntn_word_chunk); as soon as chunk c is final in this rank's buffer, an exchange
+//     kernel all-reduces it on a side stream while the pull goes on with chunk c + 1; the last chunk, the W/V/b/U blocks and
+//     the {cost, n_active} tail follow the final reduce.  Only that last exchange is not overlapped.  (Variant,
+//     ntn_exchange_bind_ge: the same done one stage earlier, on the entity gradient, beside the entity pull.);
 //   * an all-reduce of a range is two-shot: rank r owns the r-th slice, SUMS that slice over all ranks and writes the
 //     result into every rank's buffer.
 //       mode 2 (push, the default when a scratch allocation is bound): NO peer loads at all.  The producer of a range --
@@ -15,7 +16,8 @@
 //              that another rank owns straight into that rank's scratch while it computes it (posted writes over NVLink:
 //              the reduce-scatter half rides inside the pull and costs it nothing but store slots); after ONE flag
 //              barrier the owner adds its own group and the G-1 scratch copies in rank order (all local reads) and stores
-//              the sum into every rank's buffer.  Loads from a peer cost a 2-3 us round trip each and a few dozen blocks
+//              the sum into every rank's buffer -- G stores, or one multimem.st on the multicast alias (the NVSwitch
+//              replicates it) on a box of >= 4 ranks.  Loads from a peer cost a 2-3 us round trip each and a few dozen blocks
 //              cannot keep enough of them in flight (measured on 2 GPUs: the pull-based exchange of mode 0 took
 //              ~35 us per 7 MB chunk, longer than the chunk's pull); stores are fire-and-forget;
 //       mode 0 (peer loads / stores): 16-byte loads from every peer in rank order 0..G-1 (a fixed order: every rank
@@ -24,11 +26,11 @@
 //              fabric and returns one value -- then multimem.st broadcasts it; one load and one store per 16 bytes
 //              whatever G is;
 //   * ranks synchronise through 32-bit flags in the signal pad of the symmetric allocation: block b of a kernel pairs
-//     with block b of the same kernel on every peer (put = CAS 0->1 on the peer's flag with release semantics at system
-//     scope, wait = CAS 1->0 on the own flag with acquire semantics; the flags are 0 again after every barrier, so
-//     consecutive kernels reuse them).  A start barrier says "every rank has finished producing this range", an end
-//     barrier "every rank's stores have landed".  Every wait is bounded: a lost peer sets an error flag
-//     (ntn_exchange_check) instead of hanging the GPU.
+//     with block b of the same kernel on every peer (x_barrier below: a signal is a store of the barrier's epoch number
+//     with release semantics at system scope, a wait polls the own flag with acquire loads).  A start barrier says "every
+//     rank has finished producing this range", the end barrier -- only in the kernel that closes an evaluation -- "every
+//     rank's stores have landed".  Every wait is bounded: a lost peer sets an error flag (ntn_exchange_check) instead of
+//     hanging the GPU.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
