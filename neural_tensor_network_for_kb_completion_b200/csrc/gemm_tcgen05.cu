@@ -46,7 +46,9 @@ struct TcState {
     bool dw_mn = false;                         // dw with MN-major (SWIZZLE_128B_BASE32B) operand tiles
     float *WT_hi = nullptr, *WT_lo = nullptr, *W_hi = nullptr, *W_lo = nullptr;
     CUtensorMap mWT_hi, mWT_lo, mW_hi, mW_lo;
-    int box_fwd = 0, box_ge = 0;                // rows per TMA box
+    CUtensorMap mW2_hi, mW2_lo;                 // W again with boxes of <= 128 rows: the A operand of the swapped-role contraction
+    int box_fwd = 0, box_ge = 0, box_ge2 = 0;   // rows per TMA box
+    bool ge2 = true;                            // entity-gradient contraction with swapped operand roles (NTN_TC_GE2=0: off)
     int KpP = 0, KpN = 0, NpP = 0;
     int* t_anchor = nullptr;                    // [Nu] anchor entity per unique triple, rewritten per evaluation (grow-only)
     size_t anchor_cap = 0;
@@ -165,7 +167,7 @@ struct TcArgs {
     int nitems, ny, nz;                // work items = nitems x ny (N chunks) x nz (M chunks, dw)
 };
 
-enum { TC_FWD = 0, TC_DW = 1, TC_GE = 2 };
+enum { TC_FWD = 0, TC_DW = 1, TC_GE = 2, TC_GE2 = 3 };   // GE2: the entity-gradient contraction with swapped operand roles
 
 #define TC_THREADS 416            // warps 0-3, 5-8: producer groups, warp 4: MMA issuer, warps 9-12: epilogue
 
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // debug timeline: thread 0 (producer group 0) stamps slots [0,128), thread 128 (MMA issuer) slots [128,256)
     long long* dbg = (a.dbg && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 128))
-                         ? a.dbg + MODE * 256 + (threadIdx.x == 128 ? 128 : 0) : nullptr;
+                         ? a.dbg + (MODE == TC_GE2 ? TC_GE : MODE) * 256 + (threadIdx.x == 128 ? 128 : 0) : nullptr;
     int dbg_n = 0;
     auto stamp = [&]() { if (dbg && dbg_n < 128) dbg[dbg_n++] = clock64(); };
     stamp();
@@ -214,10 +216,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
     if (threadIdx.x == 0) {
         // full: 128 producer arrivals (+ the TMA issuer's arrive.expect_tx when the weight tile comes by TMA)
         // (TMA_A: both operands come by TMA, the only arrival is the issuing thread's arrive.expect_tx)
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), TMA_A ? 1 : (TMA_B ? 129 : 128)); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), TMA_A ? 1 : ((TMA_B || MODE == TC_GE2) ? 129 : 128)); mbar_init(empty_bar(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
         fence_barrier_init();
-        if (TMA_B) { tma_prefetch_desc(&mapB_hi); tma_prefetch_desc(&mapB_lo); }
+        if (TMA_B || MODE == TC_GE2) { tma_prefetch_desc(&mapB_hi); tma_prefetch_desc(&mapB_lo); }
         if (TMA_A) { tma_prefetch_desc(&mapA_hi); tma_prefetch_desc(&mapA_lo); }
     }
     if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TC_TMEM_COLS);
@@ -242,6 +244,143 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(TcArgs a, const __gri
     const int nkb = (kext + TC_BK - 1) / TC_BK;                                                          \
     (void)bz_; (void)r; (void)m0; (void)u0; (void)n0; (void)nlen;
 
+
+    if (MODE == TC_GE2) {
+        // ================================ entity-gradient contraction, operand roles swapped ================================
+        //   GA^T[p][u] = sum_n Waug_r[p][n] * M[u][n]        (NTN.java:352-388)
+        // A (the 128 TMEM lanes) = a 128-row chunk of Waug_r -- the pre-split K-major copy k_tc_w_tiles writes, by TMA --
+        // and B (the N dimension) = the M rows of up to TC_NCH unique triples, loaded and split by the producers.  The
+        // issue cost of a kind::tf32 MMA does not depend on N (~125-139 cycles for N = 104 ... 256, measured), so the
+        // orientation with Kp = 104 as N runs the tensor pipe at 104/256 of its rate; here N is the tile height
+        // (160: 130 tiles at 20,000 unique triples -- ONE round of the persistent grid instead of two).
+        // Work items: (tile of the ge table) x (128-row chunk of p); accumulator = [128 lanes p] x [N columns u].
+        const int nz2 = a.nz, nwork2 = a.nitems * nz2;
+        const int nkb2 = (a.Np + TC_BK - 1) / TC_BK;
+        if (warp < 9 && warp != 4) {
+            const int group = warp > 4 ? 1 : 0;
+            const int t = threadIdx.x - (group ? 160 : 0);
+            const int j = t & 7, rsub = t >> 3;
+            bool alive = true;
+            int g = 0;
+            for (int w = blockIdx.x; w < nwork2 && alive; w += gridDim.x) {
+                const int item = w / nz2, bz = w - item * nz2;
+                const int r = __ldg(a.t_rel + item), u0 = __ldg(a.t_u0 + item), rows = __ldg(a.t_n + item);
+                const int nlen = (rows + 15) & ~15;
+                for (int kb = 0; kb < nkb2 && alive; ++kb, ++g) {
+                    if ((g & 1) != group) continue;
+                    const int s = g % TC_STAGES;
+                    const uint32_t ph = (g / TC_STAGES) & 1;
+                    alive = mbar_wait(empty_bar(s), ph ^ 1, a.err);
+                    stamp();
+                    uint8_t* sA_hi = smem + s * TC_STAGE_BYTES;
+                    uint8_t* sA_lo = sA_hi + TC_A_BYTES;
+                    uint8_t* sB_hi = sA_lo + TC_A_BYTES;
+                    uint8_t* sB_lo = sB_hi + TC_B_BYTES;
+                    const int k0 = kb * TC_BK;
+                    if (t == 0) {
+                        // weight chunk: two boxes (hi, lo) of 32 floats x b_box_rows rows of Waug_r (rows past the chunk's
+                        // valid p belong to the next relation or arrive as zeros: lanes nobody reads)
+                        mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)a.b_box_rows * 128u);
+                        const int y = r * a.b_rows_per_rel + bz * 128;
+                        tma_load_2d(smem_u32(sA_hi), &mapB_hi, k0, y, full_bar(s));
+                        tma_load_2d(smem_u32(sA_lo), &mapB_lo, k0, y, full_bar(s));
+                    }
+                    constexpr int BR = TC_NCH / 16;                  // M rows per thread
+                    float4 xb[BR];
+                    const int kk = k0 + j * 4;
+#pragma unroll
+                    for (int i = 0; i < BR; ++i) {
+                        const int row = rsub + 16 * i;
+                        xb[i] = (row < rows && kk < a.Np) ? ldg4g(a.M + (size_t)(u0 + row) * a.Np + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < BR; ++i) {
+                        const int row = rsub + 16 * i;
+                        if (row < nlen) {
+                            float4 hi, lo;
+                            split_tf32(xb[i], hi, lo);
+                            const uint32_t off = row * 128 + ((j ^ (row & 7)) << 4);
+                            sts4(sB_hi, off, hi); sts4(sB_lo, off, lo);
+                        }
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(full_bar(s));
+                    stamp();
+                }
+            }
+        } else if (warp == 4) {
+            bool alive = true;
+            int g = 0, tl = 0;
+            for (int w = blockIdx.x; w < nwork2 && alive; w += gridDim.x, ++tl) {
+                const int item = w / nz2;
+                const int rows = a.t_n[item];
+                const int nlen = (rows + 15) & ~15;
+                const uint32_t idesc = make_idesc(nlen, 0, 0);
+                const int b = tl & 1;
+                const uint32_t tacc = tmem_base + (uint32_t)(b * TC_ACC_COLS);
+                alive = mbar_wait(acc_empty(b), (uint32_t)((tl >> 1) & 1) ^ 1u, a.err);
+                tc_fence_after();
+                for (int kb = 0; kb < nkb2 && alive; ++kb, ++g) {
+                    const int s = g % TC_STAGES;
+                    const uint32_t ph = (g / TC_STAGES) & 1;
+                    alive = mbar_wait(full_bar(s), ph, a.err);
+                    tc_fence_after();
+                    stamp();
+                    if (lane == 0 && alive) {
+                        const uint32_t sA_hi = smem_u32(smem + s * TC_STAGE_BYTES);
+                        const uint32_t sA_lo = sA_hi + TC_A_BYTES, sB_hi = sA_lo + TC_A_BYTES, sB_lo = sB_hi + TC_B_BYTES;
+                        const int kleft = a.Np - kb * TC_BK;
+                        const int nks = (kleft >= TC_BK) ? 4 : (kleft + 7) / 8;
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint64_t dAh = make_desc(sA_hi + ks * 32, 16, 1024), dAl = make_desc(sA_lo + ks * 32, 16, 1024);
+                            const uint64_t dBh = make_desc(sB_hi + ks * 32, 16, 1024), dBl = make_desc(sB_lo + ks * 32, 16, 1024);
+                            const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                            umma_tf32(tacc, dAl, dBh, idesc, first);
+                            umma_tf32(tacc, dAh, dBl, idesc, 1u);
+                            umma_tf32(tacc, dAh, dBh, idesc, 1u);
+                        }
+                        umma_commit(empty_bar(s));
+                        if (kb == nkb2 - 1) umma_commit(acc_full(b));
+                    }
+                    stamp();
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+        } else {
+            // epilogue: TMEM lane = row p of the chunk, columns = the tile's unique triples; GA is [u][p], so for a fixed
+            // column the 32 lanes of a warp store 32 consecutive floats
+            const int q = warp & 3;
+            const int row = q * 32 + lane;
+            bool alive = true;
+            int tl = 0;
+            for (int w = blockIdx.x; w < nwork2 && alive; w += gridDim.x, ++tl) {
+                const int item = w / nz2, bz = w - item * nz2;
+                const int u0 = a.t_u0[item], rows = a.t_n[item];
+                const int nlen = (rows + 15) & ~15;
+                const int b = tl & 1;
+                alive = mbar_wait(acc_full(b), (uint32_t)((tl >> 1) & 1), a.err);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + (uint32_t)(b * TC_ACC_COLS) + ((uint32_t)(q * 32) << 16);
+                const int p = bz * 128 + row;
+                for (int c0 = 0; c0 < nlen && alive; c0 += 32) {
+                    float v[32];
+                    tmem_ld16_issue(trow + c0, v);
+                    if (c0 + 16 < nlen) tmem_ld16_issue(trow + c0 + 16, v + 16);
+                    tmem_ld_wait();
+                    if (p < a.Kp) {
+                        float* dst = a.GA + (size_t)(u0 + c0) * a.Kp + p;
+#pragma unroll
+                        for (int qq = 0; qq < 32; ++qq)
+                            if (c0 + qq < rows) dst[(size_t)qq * a.Kp] = v[qq];
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(acc_empty(b));
+                stamp();
+            }
+        }
+    } else
     if (TMA_A && warp < 9 && warp != 4) {
         // ================================ producers, all-TMA ================================
         // One thread per group (the two groups still take alternate k-blocks, so two stages are requested while the
@@ -815,14 +954,18 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
             }
             st->box_fwd = std::min(TC_NCH, dm.Np);
             st->box_ge = std::min(TC_NCH, st->KpN);
+            st->box_ge2 = std::min(128, st->KpN);
             if (!make_map(&st->mWT_hi, st->WT_hi, st->KpP, (uint64_t)dm.R * dm.Np, st->box_fwd) ||
                 !make_map(&st->mWT_lo, st->WT_lo, st->KpP, (uint64_t)dm.R * dm.Np, st->box_fwd) ||
                 !make_map(&st->mW_hi, st->W_hi, st->NpP, (uint64_t)dm.R * st->KpN, st->box_ge) ||
-                !make_map(&st->mW_lo, st->W_lo, st->NpP, (uint64_t)dm.R * st->KpN, st->box_ge)) {
+                !make_map(&st->mW_lo, st->W_lo, st->NpP, (uint64_t)dm.R * st->KpN, st->box_ge) ||
+                !make_map(&st->mW2_hi, st->W_hi, st->NpP, (uint64_t)dm.R * st->KpN, st->box_ge2) ||
+                !make_map(&st->mW2_lo, st->W_lo, st->NpP, (uint64_t)dm.R * st->KpN, st->box_ge2)) {
                 h->err = "cuTensorMapEncodeTiled failed";
                 return NTN_ECUDA;
             }
         }
+        { const char* e2 = getenv("NTN_TC_GE2"); st->ge2 = st->use_tma && !(e2 && e2[0] == '0'); }
         const char* dw_env = getenv("NTN_TC_DW");
         st->dw_mn = dw_env ? (dw_env[0] == 'm') : true;      // NTN_TC_DW=k selects the K-major transposing producers
         // all-TMA forward / entity-gradient contractions: opt-in (NTN_TC_TMA_A=1); needs the TMA-fed weights and the
@@ -843,7 +986,8 @@ int ntn_tc_prepare_batch(ntn_handle* h) {
             (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
             (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
             (e = cudaFuncSetAttribute(k_tc_gemm<TC_FWD, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
-            (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES))) {
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)) ||
+            (e = cudaFuncSetAttribute(k_tc_gemm<TC_GE2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES))) {
             h->err = std::string("tcgen05 smem attribute: ") + cudaGetErrorString(e);
             return NTN_ECUDA;
         }
@@ -963,6 +1107,15 @@ int ntn_tc_gemm_dw(ntn_handle* h, cudaStream_t stq) {
 int ntn_tc_gemm_ge(ntn_handle* h) {
     TcArgs a = tc_args(h, false);
     TcState* st = (TcState*)h->tc;
+    if (st->ge2 && !h->b.m_split && h->b.ngtiles > 0) {
+        // swapped operand roles: A = a 128-row chunk of Waug_r (TMA), N = the tile's unique triples
+        a.t_rel = h->b.g_rel; a.t_u0 = h->b.g_u0; a.t_n = h->b.g_n;
+        dim3 g2 = tc_grid(h, a, h->b.ngtiles, 1, cdivi(h->dm.Kp, 128));
+        a.b_rows_per_rel = st->KpN; a.b_box_rows = st->box_ge2;
+        k_tc_gemm<TC_GE2, false><<<g2, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a, st->mW2_hi, st->mW2_lo, st->mW2_hi, st->mW2_lo);
+        h->launches++;
+        return NTN_OK;
+    }
     dim3 g = tc_grid(h, a, h->b.ntiles, cdivi(st->KpN, TC_NCH), 1);
     if (h->b.m_split) {
         a.b_rows_per_rel = st->KpN; a.b_box_rows = st->box_ge;

@@ -171,7 +171,7 @@ static void free_batch(DeviceBatch& b) {
     dev_free(b.t_rel); dev_free(b.t_u0); dev_free(b.t_n); dev_free(b.ch_rel); dev_free(b.ch_u0); dev_free(b.ch_n);
     dev_free(b.relch_off); dev_free(b.reltile_off); dev_free(b.inc_off); dev_free(b.inc);
     dev_free(b.eh_ent); dev_free(b.eh_begin); dev_free(b.eh_end); dev_free(b.eh_first); dev_free(b.eh_count);
-    dev_free(b.T); dev_free(b.M); dev_free(b.M_lo); dev_free(b.GA); dev_free(b.GV); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.crec); dev_free(b.ent_order); dev_free(b.pull_rng); dev_free(b.dWpart);
+    dev_free(b.T); dev_free(b.M); dev_free(b.M_lo); dev_free(b.GA); dev_free(b.g_rel); dev_free(b.g_u0); dev_free(b.g_n); dev_free(b.GV); dev_free(b.acoef); b.ccoef = nullptr; dev_free(b.crec); dev_free(b.ent_order); dev_free(b.pull_rng); dev_free(b.dWpart);
     dev_free(b.tp_cost); dev_free(b.tp_nact); dev_free(b.tp_dU); dev_free(b.eh_part);
     b = DeviceBatch();
 }
@@ -418,6 +418,24 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
         }
         if (const char* e = getenv("NTN_TILE_ROWS")) tile_rows = std::max(8, std::min(NTN_TILE_ROWS, atoi(e) / 8 * 8));
     }
+    // tiles of the swapped-role entity-gradient contraction (gemm_tcgen05.cu, TC_GE2): the tile height is its N dimension,
+    // up to 160 rows; the tallest height that needs the fewest rounds of the persistent grid
+    std::vector<int> g_rel, g_u0, g_n;
+    {
+        const int nzg = (dm.Kp + 127) / 128;
+        auto tiles_at = [&](int rows) { int64_t t = 0; for (int r = 0; r < dm.R; ++r) t += (rel_count[r] + rows - 1) / rows; return t; };
+        int ge_rows = 160;
+        int64_t best = (tiles_at(160) * nzg + h->sm_count - 1) / h->sm_count;
+        for (int rows = 144; rows >= 64; rows -= 16) {
+            const int64_t rounds = (tiles_at(rows) * nzg + h->sm_count - 1) / h->sm_count;
+            if (rounds < best) { best = rounds; ge_rows = rows; }
+        }
+        if (const char* e = getenv("NTN_GE_ROWS")) ge_rows = std::max(16, std::min(160, atoi(e) / 16 * 16));
+        for (int r = 0; r < dm.R; ++r)
+            for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += ge_rows) {
+                g_rel.push_back(r); g_u0.push_back(u0); g_n.push_back(std::min(ge_rows, rel_off[r + 1] - u0));
+            }
+    }
     for (int r = 0; r < dm.R; ++r) {
         for (int u0 = rel_off[r]; u0 < rel_off[r + 1]; u0 += tile_rows) {
             t_rel.push_back(r); t_u0.push_back(u0); t_n.push_back(std::min(tile_rows, rel_off[r + 1] - u0));
@@ -435,12 +453,14 @@ static int finish_batch(ntn_handle* h, int64_t n, int Nu, const std::vector<int>
     DeviceBatch& b = h->b;
     b.N = n; b.Nu = Nu; b.ntiles = (int)t_rel.size(); b.nchunks = (int)ch_rel.size(); b.n_inc = 2 * Nu + (int)n;
     b.nstiles = (int)st_rel.size();
+    b.ngtiles = (int)g_rel.size();
     b.use_gv = use_gv;
     b.n_ent_hub_segs = n_hub_segs;
     int rc;
     if ((rc = dev_upload(h, &b.t_rel, t_rel)) || (rc = dev_upload(h, &b.t_u0, t_u0)) || (rc = dev_upload(h, &b.t_n, t_n)) ||
         (rc = dev_upload(h, &b.st_rel, st_rel)) || (rc = dev_upload(h, &b.st_u0, st_u0)) || (rc = dev_upload(h, &b.st_n, st_n)) ||
         (rc = dev_upload(h, &b.rels_off, rels_off)) ||
+        (rc = dev_upload(h, &b.g_rel, g_rel)) || (rc = dev_upload(h, &b.g_u0, g_u0)) || (rc = dev_upload(h, &b.g_n, g_n)) ||
         (rc = dev_upload(h, &b.ch_rel, ch_rel)) || (rc = dev_upload(h, &b.ch_u0, ch_u0)) || (rc = dev_upload(h, &b.ch_n, ch_n)) ||
         (rc = dev_upload(h, &b.relch_off, relch_off)) || (rc = dev_upload(h, &b.reltile_off, reltile_off)) ||
         (rc = dev_alloc(h, &b.T, (size_t)Nu * dm.Np)) ||

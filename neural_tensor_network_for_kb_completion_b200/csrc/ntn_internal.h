@@ -90,6 +90,8 @@ struct DeviceBatch {
     int *c_off = nullptr;        // Nu+1: corrupt columns of each unique triple
     int *c_e3 = nullptr;         // N
     int *t_rel = nullptr, *t_u0 = nullptr, *t_n = nullptr;        // contraction tiles
+    int *g_rel = nullptr, *g_u0 = nullptr, *g_n = nullptr;        // tiles of the swapped-role entity-gradient contraction (<= 160 rows)
+    int ngtiles = 0;
     int *st_rel = nullptr, *st_u0 = nullptr, *st_n = nullptr;     // score tiles
     int *rels_off = nullptr;     // R+1: score-tile range per relation
     int *ch_rel = nullptr, *ch_u0 = nullptr, *ch_n = nullptr;     // dW chunks
