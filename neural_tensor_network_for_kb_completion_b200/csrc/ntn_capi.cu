@@ -138,7 +138,9 @@ extern "C" int ntn_create(const ntn_config* cfg, ntn_handle** out) {
     CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));      // numerically: hi <= lo
     static const bool use_prio = [] { const char* e = getenv("NTN_STREAM_PRIORITY"); return !(e && e[0] == '0'); }();
     CKC(cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
-    CKC(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo));
+    // (the hub-word branch: NTN_HUB_PRIORITY=1 gives it the chain's priority)
+    static const bool hub_hi = [] { const char* e = getenv("NTN_HUB_PRIORITY"); return e && e[0] == '1'; }();
+    CKC(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hub_hi ? prio_hi : prio_lo));
     CKC(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prio_lo));
     CKC(cudaEventCreateWithFlags(&h->ev_f0, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_j0, cudaEventDisableTiming));
