@@ -430,6 +430,7 @@ def main():
         for h in handles:
             h.set_grad_tail(True)
         fused = False
+        os.environ.setdefault("NTN_EXCHANGE_TIMEOUT_MS", "10000")   # bound of the exchange's flag waits (graph capture skews the first evaluation)
         if args.exchange in ("auto", "fused"):
             fused = exchange.bind_fused(handles, grads)     # the library's own peer-memory exchange, inside the evaluation
             if args.exchange == "fused" and not fused:
@@ -466,6 +467,9 @@ def main():
         sampler.start()
     for i in range(args.warmup):
         step(i, sync=True)
+    if fused:
+        for h in handles:
+            h.exchange_check()          # (clears the flag: a rank that was late to its FIRST evaluation does not void the run)
     launches_per_eval = h0.launches
     barrier()
     sampler.mark()
