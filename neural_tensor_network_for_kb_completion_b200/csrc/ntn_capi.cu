@@ -189,6 +189,7 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     dev_free(w.fwd_off); dev_free(w.fwd_idx); dev_free(w.w_off); dev_free(w.w_ent); dev_free(w.len_bwd);
     dev_free(w.wh_word); dev_free(w.wh_begin); dev_free(w.wh_end); dev_free(w.wh_first); dev_free(w.wh_count);
     dev_free(w.wh_part); dev_free(w.hub_words); dev_free(w.w_rec); dev_free(w.fwd_rec);
+    if (h->gE_own) { h->gE = h->gE_own; h->gE_own = nullptr; }      // (a bound symmetric gE belongs to the caller)
     dev_free(h->wv_frozen); dev_free(h->E); dev_free(h->gE); dev_free(h->Waug); dev_free(h->side);
     dev_free(h->reg_part); dev_free(h->d_out); dev_free(h->d_ref_theta); dev_free(h->d_ref_grad);
     dev_free(h->d_int_theta); dev_free(h->d_int_grad);
@@ -213,7 +214,6 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     for (cudaEvent_t e : {h->ev_f0, h->ev_j0, h->ev_f1, h->ev_j1}) if (e) cudaEventDestroy(e);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
-    if (h->gE_own) { h->gE = h->gE_own; h->gE_own = nullptr; }      // (a bound symmetric gE belongs to the caller)
     if (h->stream4) cudaStreamDestroy(h->stream4);
     for (int i = 0; i < NTN_MAX_WORD_CHUNKS; ++i) if (h->ev_x[i]) cudaEventDestroy(h->ev_x[i]);
     if (h->ev_xdone) cudaEventDestroy(h->ev_xdone);
