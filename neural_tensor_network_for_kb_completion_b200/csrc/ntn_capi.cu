@@ -194,6 +194,7 @@ extern "C" void ntn_destroy(ntn_handle* h) {
     dev_free(h->reg_part); dev_free(h->d_out); dev_free(h->d_ref_theta); dev_free(h->d_ref_grad);
     dev_free(h->d_int_theta); dev_free(h->d_int_grad);
     if (h->lbfgs_ws) cudaFree(h->lbfgs_ws);
+    if (h->lbfgs_scal) cudaFreeHost(h->lbfgs_scal);
     if (h->d_stamps) cudaFree(h->d_stamps);
     if (h->bi_ws) cudaFree(h->bi_ws);
     if (h->h_meta) cudaFreeHost(h->h_meta);
